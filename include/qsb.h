@@ -1,0 +1,198 @@
+/* qsb.h -- C ABI of libqsb.so, the B200 (sm_100a) statevector backend that sits
+ * behind the Python entry points of justinbrianhwang/Quantum-Simulator's NumPy
+ * engine (quantum_sim/engine).
+ *
+ * The reference has no FFI layer at all (pure Python + NumPy); the boundary is
+ * its Python API.  Each entry point below names the reference code whose array
+ * work it replaces (file:line relative to the reference tree).  The Python side
+ * (quantum-simulator_b200/qsb/capi.py) binds these with ctypes; INTEGRATION.md
+ * shows the stub a maintainer adds to the reference.
+ *
+ * Conventions
+ *   - every function returns int: 0 = QSB_OK, negative = error; text through
+ *     qsb_last_error().  There is NO CPU fallback: without a CUDA device
+ *     qsb_ctx_create fails with QSB_E_NODEV.
+ *   - host pointers are caller-owned, borrowed for the duration of the call.
+ *   - device memory is owned by opaque handles (or wrapped, never freed, when
+ *     created with *_wrap from a caller's device pointer, e.g. a torch tensor).
+ *   - a ctx is single-threaded by contract; calls are synchronous on return
+ *     unless QSB_RUN_ASYNC is given (then order on the ctx stream; qsb_ctx_sync).
+ *   - state layout: complex128[batch][2^n] (or complex64 in c64 mode, later),
+ *     qubit 0 = most significant bit of the amplitude index (state_vector.py:87-88).
+ */
+#ifndef QSB_H
+#define QSB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QSB_VERSION 100
+
+enum {
+  QSB_OK = 0,
+  QSB_E_INVAL = -1,       /* bad argument (Python raises ValueError)            */
+  QSB_E_NODEV = -2,       /* no CUDA device / device index out of range         */
+  QSB_E_CUDA = -3,        /* CUDA runtime error                                 */
+  QSB_E_OOM = -4,         /* device allocation failed                           */
+  QSB_E_UNSUPPORTED = -5  /* valid request this build cannot run (e.g. n > 16)  */
+};
+
+typedef struct qsb_ctx qsb_ctx;
+typedef struct qsb_buffer qsb_buffer;     /* raw device bytes                      */
+typedef struct qsb_program qsb_program;   /* lowered circuit (+noise) on device    */
+
+/* ---- lowered operation ------------------------------------------------------
+ * One entry of a program.  Bit fields are SLOT bit positions of the amplitude
+ * index inside the resident tile (0 = least significant); the host compiler
+ * (qsb/compiler.py) maps reference qubits -> physical bits -> slots, tracks the
+ * reference's axis scramble (state_vector.py:66-73) and inserts QSB_OP_REMAP
+ * when a target lives in a cluster-rank bit.
+ *   data  : offset (in doubles) into the program's cdata
+ *   param : offset into the per-state parameter row (QSB_OP_R*), else -1
+ *   draw  : index of the uniform this Kraus op consumes, else -1
+ *   aux   : op specific (snapshot: offset of its bit permutation in idata)
+ */
+typedef struct qsb_op {
+  int32_t kind;
+  int32_t b0, b1, b2;
+  int32_t data;
+  int32_t param;
+  int32_t draw;
+  int32_t aux;
+} qsb_op;
+
+enum {
+  QSB_OP_NOP = 0,
+  /* dense unitaries: cdata[data ..] = row-major (re,im) matrix; b0 = MSB of the
+   * matrix index = target_qubits[0] (state_vector.py:57-63)                      */
+  QSB_OP_U1 = 1,      /* 2x2,  8 doubles   */
+  QSB_OP_U2 = 2,      /* 4x4,  32 doubles  */
+  QSB_OP_U3Q = 3,     /* 8x8,  128 doubles */
+  QSB_OP_D1 = 4,      /* diagonal 2x2: cdata = d0.re d0.im d1.re d1.im (Z,S,T,Rz,Phase) */
+  /* structured gates (gates.py:99-125) */
+  QSB_OP_X = 10, QSB_OP_Y = 11, QSB_OP_Z = 12,
+  QSB_OP_CX = 13,     /* b0 control, b1 target                    */
+  QSB_OP_CZ = 14,
+  QSB_OP_SWAP = 15,
+  QSB_OP_CCX = 16,    /* b0,b1 controls, b2 target (Toffoli)      */
+  QSB_OP_CSWAP = 17,  /* b0 control, swaps b1,b2 (Fredkin)        */
+  /* per-state parameterised 1-qubit gates (gates.py:66-94): angle(s) read from
+   * the state's parameter row at [param], [param+1], [param+2]               */
+  QSB_OP_RX = 20, QSB_OP_RY = 21, QSB_OP_RZ = 22, QSB_OP_PHASE = 23, QSB_OP_U3 = 24,
+  /* stochastic Kraus steps (noise.py:224-260), one uniform each              */
+  QSB_OP_KRAUS_PAULI = 30,  /* cdata: c0 c1 c2 (cdf of choice()), then 4 Pauli codes 0..3 as doubles */
+  QSB_OP_KRAUS_AD = 31,     /* cdata: gamma, sqrt(1-gamma), sqrt(gamma)                   */
+  QSB_OP_KRAUS_GEN = 32,    /* cdata: nK, then per K: 8 doubles K, 4 doubles K^dag K (e00,e11,re e01,im e01) */
+  /* cluster data movement: swap rank bit b0 (0..log2 C-1) with local slot bit b1 */
+  QSB_OP_REMAP = 40,
+  /* copy the (normalised) state to snapshot slot b0 with bit permutation idata[aux..aux+n) */
+  QSB_OP_SNAPSHOT = 50
+};
+
+/* flags of qsb_run */
+enum {
+  QSB_RUN_LOAD = 1,        /* start from states[first+t] instead of a basis state        */
+  QSB_RUN_STORE = 2,       /* write the final state to states[first+t] in reference order */
+  QSB_RUN_NORMALIZE = 4,   /* divide by ||psi|| on store/snapshot (set when Kraus ops ran) */
+  QSB_RUN_ASYNC = 8,       /* do not synchronise the ctx stream before returning          */
+  QSB_RUN_ACCUM_PROBS = 16 /* atomically add |psi|^2 (reference order) into probs_accum   */
+};
+
+typedef struct qsb_run_args {
+  qsb_buffer* states;        /* complex128[batch][2^n] or NULL (no LOAD/STORE)             */
+  int64_t first, count;      /* states / trajectories [first, first+count)                  */
+  qsb_buffer* params;        /* double[>=count][params_stride] or NULL                      */
+  int64_t params_stride;
+  qsb_buffer* uniforms;      /* double[>=count][uniforms_stride] ("reference draws" mode)   */
+  int64_t uniforms_stride;   /*   NULL => counter-based Philox4x32-10 in the kernel         */
+  uint64_t philox_seed;
+  int64_t traj_offset;       /* global index of trajectory `first` (Philox counter, shards) */
+  qsb_buffer* init_basis;    /* int64[>=count] reference-order basis index per state, or NULL */
+  int64_t default_basis;     /* used when init_basis is NULL                                */
+  qsb_buffer* branches;      /* int32[>=count][branches_stride] chosen Kraus index per draw, or NULL */
+  int64_t branches_stride;
+  qsb_buffer* snapshots;     /* complex128[>=count][n_snapshots][2^n] or NULL               */
+  qsb_buffer* probs_accum;   /* double[2^n] or NULL                                         */
+  int32_t flags;
+  int32_t reserved;
+} qsb_run_args;
+
+/* ---- lifecycle --------------------------------------------------------------- */
+int qsb_version(void);
+int qsb_device_count(void);                       /* <0 on error                              */
+int qsb_ctx_create(int device, qsb_ctx** out);
+int qsb_ctx_destroy(qsb_ctx* ctx);
+int qsb_ctx_set_stream(qsb_ctx* ctx, void* cuda_stream);  /* run on a caller's stream (torch) */
+int qsb_ctx_sync(qsb_ctx* ctx);
+const char* qsb_last_error(qsb_ctx* ctx);         /* ctx may be NULL: last error of the thread */
+int qsb_ctx_info(qsb_ctx* ctx, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor,
+                 int64_t* total_mem);
+/* device timer on the ctx stream (CUDA events) */
+int qsb_timer_start(qsb_ctx* ctx);
+int qsb_timer_stop(qsb_ctx* ctx, float* ms_out);  /* synchronises */
+/* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
+int64_t qsb_launch_count(qsb_ctx* ctx);
+
+/* ---- device buffers / host staging ------------------------------------------- */
+int qsb_buffer_alloc(qsb_ctx* ctx, int64_t bytes, qsb_buffer** out);
+int qsb_buffer_wrap(qsb_ctx* ctx, void* device_ptr, int64_t bytes, qsb_buffer** out);
+int qsb_buffer_free(qsb_buffer* buf);
+int qsb_buffer_upload(qsb_buffer* buf, int64_t offset, const void* host, int64_t bytes);
+int qsb_buffer_download(qsb_buffer* buf, int64_t offset, void* host, int64_t bytes);
+int qsb_buffer_zero(qsb_buffer* buf, int64_t offset, int64_t bytes);
+int qsb_buffer_copy(qsb_buffer* dst, int64_t dst_off, qsb_buffer* src, int64_t src_off, int64_t bytes);
+void* qsb_buffer_ptr(qsb_buffer* buf);
+int64_t qsb_buffer_bytes(qsb_buffer* buf);
+int qsb_host_alloc(int64_t bytes, void** out);    /* pinned host memory for NumPy views */
+int qsb_host_free(void* p);
+
+/* ---- programs ------------------------------------------------------------------
+ * Replaces the per-gate loop of Simulator.run (simulator.py:57-71), NoiseModel.apply
+ * (noise.py:212-260) and StateVector.apply_gate (state_vector.py:41-74).
+ *   n_qubits <= 16, local_bits = bits resident per CTA (cluster size = 2^(n-local_bits) <= 8,
+ *   local_bits <= 13);  load_perm/store_perm = idata offsets of n-entry bit permutations
+ *   (slot bit j -> reference-order bit).                                              */
+int qsb_program_create(qsb_ctx* ctx, int32_t n_qubits, int32_t local_bits,
+                       const qsb_op* ops, int64_t n_ops, int64_t ops_stride /*0 = shared*/,
+                       int64_t n_programs /*1 if shared*/,
+                       const double* cdata, int64_t n_cdata,
+                       const int32_t* idata, int64_t n_idata,
+                       int32_t load_perm, int32_t store_perm, int32_t n_snapshots,
+                       qsb_program** out);
+int qsb_program_free(qsb_program* prog);
+int qsb_run(qsb_program* prog, const qsb_run_args* args);
+
+/* ---- reductions over stored (reference-order) states ---------------------------- */
+/* StateVector.probabilities (state_vector.py:36-39): out double[count][2^n] */
+int qsb_probabilities(qsb_ctx* ctx, int32_t n, qsb_buffer* states, int64_t first, int64_t count,
+                      qsb_buffer* out, int64_t out_first);
+/* sum_t |psi_t|^2 -> double[2^n] (added into out) */
+int qsb_probabilities_sum(qsb_ctx* ctx, int32_t n, qsb_buffer* states, int64_t first, int64_t count,
+                          qsb_buffer* out);
+/* StateVector.measure_all (state_vector.py:107-113): idx = choice(2^n, p) from one uniform each */
+int qsb_sample_index(qsb_ctx* ctx, int32_t n, qsb_buffer* states, int64_t first, int64_t count,
+                     qsb_buffer* uniforms /*double[count]*/, qsb_buffer* out /*int64[count]*/);
+/* <a_t|b_t> (np.vdot, analysis.py:40): out complex128[count]; stride_b = 0 broadcasts one b */
+int qsb_overlap(qsb_ctx* ctx, int32_t n, qsb_buffer* a, int64_t a_first, qsb_buffer* b,
+                int64_t b_first, int64_t b_stride_states, int64_t count, qsb_buffer* out);
+/* masked parity weights (qec.py:466-484, :131-151): out double[count][n_masks][2] = (p_even, p_odd) */
+int qsb_masked_parity(qsb_ctx* ctx, int32_t n, qsb_buffer* states, int64_t first, int64_t count,
+                      const uint64_t* masks, int32_t n_masks, qsb_buffer* out);
+/* all 1- and 2-qubit reduced density matrices (analysis.py:120-166, state_vector.py:121-140):
+ * rdm1 complex128[count][n][2][2], rdm2 complex128[count][n(n-1)/2][4][4], pair order (i<j) row-major */
+int qsb_rdm_all(qsb_ctx* ctx, int32_t n, qsb_buffer* states, int64_t first, int64_t count,
+                qsb_buffer* rdm1, qsb_buffer* rdm2);
+/* ensemble rho (simulator.py:195-198): rho[i][j] += scale * sum_t psi_t[i] conj(psi_t[j]) */
+int qsb_rho_accumulate(qsb_ctx* ctx, int32_t n, qsb_buffer* states, int64_t first, int64_t count,
+                       double scale, qsb_buffer* rho);
+/* ReadoutError.apply_to_distribution (noise.py:141-175) in place on double[count][2^n] */
+int qsb_readout_transform(qsb_ctx* ctx, int32_t n, qsb_buffer* probs, int64_t count,
+                          double p01, double p10);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QSB_H */

@@ -1,0 +1,693 @@
+// qsb_api.cu -- extern "C" entry points of libqsb.so (see include/qsb.h).
+// Thin host glue: handles, argument checks, launches.  No CPU compute path exists here:
+// every function that produces numbers launches a kernel from qsb_kernels.cuh.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "qsb_kernels.cuh"
+
+struct qsb_ctx {
+  int device;
+  cudaStream_t stream;
+  bool own_stream;
+  cudaEvent_t ev0, ev1;
+  int sm_count, cc_major, cc_minor;
+  size_t total_mem;
+  int64_t launches;
+  std::string err;
+  uint64_t* d_masks;      // scratch for qsb_masked_parity
+};
+
+struct qsb_buffer {
+  qsb_ctx* ctx;
+  void* ptr;
+  int64_t bytes;
+  bool owned;
+};
+
+struct qsb_program {
+  qsb_ctx* ctx;
+  int32_t n, m;
+  int64_t n_ops, ops_stride, n_programs;
+  qsb_op* d_ops;
+  double* d_cdata;
+  int32_t* d_idata;
+  int32_t load_perm, store_perm, n_snapshots;
+  int64_t n_idata, n_cdata;
+  int32_t max_param, max_draw;   // highest parameter / draw index any op touches (argument checks)
+  bool has_param;
+};
+
+static thread_local std::string g_err;
+
+static int fail(qsb_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  if (ctx) ctx->err = buf;
+  return code;
+}
+
+#define CU(ctx, call)                                                                          \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess)                                                                     \
+      return fail(ctx, e_ == cudaErrorMemoryAllocation ? QSB_E_OOM : QSB_E_CUDA, "%s: %s", #call, \
+                  cudaGetErrorString(e_));                                                     \
+  } while (0)
+
+extern "C" {
+
+int qsb_version(void) { return QSB_VERSION; }
+
+int qsb_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    fail(nullptr, QSB_E_NODEV, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+    return QSB_E_NODEV;
+  }
+  return n;
+}
+
+const char* qsb_last_error(qsb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+int qsb_ctx_create(int device, qsb_ctx** out) {
+  if (!out) return fail(nullptr, QSB_E_INVAL, "qsb_ctx_create: out is NULL");
+  *out = nullptr;
+  int n = qsb_device_count();
+  if (n <= 0) return fail(nullptr, QSB_E_NODEV, "no CUDA device visible (libqsb has no CPU fallback)");
+  if (device < 0 || device >= n) return fail(nullptr, QSB_E_NODEV, "device %d out of range [0, %d)", device, n);
+  CU(nullptr, cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(nullptr, cudaGetDeviceProperties(&prop, device));
+  qsb_ctx* c = new qsb_ctx();
+  c->device = device;
+  c->own_stream = true;
+  c->sm_count = prop.multiProcessorCount;
+  c->cc_major = prop.major;
+  c->cc_minor = prop.minor;
+  c->total_mem = prop.totalGlobalMem;
+  c->launches = 0;
+  c->d_masks = nullptr;
+  cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
+  if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+  if (e == cudaSuccess) e = cudaMalloc(&c->d_masks, 8 * sizeof(uint64_t));
+  if (e != cudaSuccess) {
+    delete c;
+    return fail(nullptr, QSB_E_CUDA, "context setup: %s", cudaGetErrorString(e));
+  }
+  *out = c;
+  return QSB_OK;
+}
+
+int qsb_ctx_destroy(qsb_ctx* ctx) {
+  if (!ctx) return QSB_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  cudaEventDestroy(ctx->ev0);
+  cudaEventDestroy(ctx->ev1);
+  cudaFree(ctx->d_masks);
+  delete ctx;
+  return QSB_OK;
+}
+
+int qsb_ctx_set_stream(qsb_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return fail(nullptr, QSB_E_INVAL, "ctx is NULL");
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  ctx->stream = (cudaStream_t)cuda_stream;
+  ctx->own_stream = false;
+  return QSB_OK;
+}
+
+int qsb_ctx_sync(qsb_ctx* ctx) {
+  if (!ctx) return fail(nullptr, QSB_E_INVAL, "ctx is NULL");
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return QSB_OK;
+}
+
+int qsb_ctx_info(qsb_ctx* ctx, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, int64_t* total_mem) {
+  if (!ctx) return fail(nullptr, QSB_E_INVAL, "ctx is NULL");
+  if (sm_count) *sm_count = ctx->sm_count;
+  if (cc_major) *cc_major = ctx->cc_major;
+  if (cc_minor) *cc_minor = ctx->cc_minor;
+  if (total_mem) *total_mem = (int64_t)ctx->total_mem;
+  return QSB_OK;
+}
+
+int qsb_timer_start(qsb_ctx* ctx) {
+  if (!ctx) return fail(nullptr, QSB_E_INVAL, "ctx is NULL");
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  return QSB_OK;
+}
+
+int qsb_timer_stop(qsb_ctx* ctx, float* ms_out) {
+  if (!ctx || !ms_out) return fail(ctx, QSB_E_INVAL, "qsb_timer_stop: NULL argument");
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  CU(ctx, cudaEventSynchronize(ctx->ev1));
+  CU(ctx, cudaEventElapsedTime(ms_out, ctx->ev0, ctx->ev1));
+  return QSB_OK;
+}
+
+int64_t qsb_launch_count(qsb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- buffers ---------------------------------------------------------------------------
+int qsb_buffer_alloc(qsb_ctx* ctx, int64_t bytes, qsb_buffer** out) {
+  if (!ctx || !out || bytes < 0) return fail(ctx, QSB_E_INVAL, "qsb_buffer_alloc: bad argument");
+  CU(ctx, cudaSetDevice(ctx->device));
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes > 0 ? (size_t)bytes : 16);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(ctx, QSB_E_OOM, "cudaMalloc(%lld bytes): %s", (long long)bytes, cudaGetErrorString(e));
+  }
+  *out = new qsb_buffer{ctx, p, bytes, true};
+  return QSB_OK;
+}
+
+int qsb_buffer_wrap(qsb_ctx* ctx, void* device_ptr, int64_t bytes, qsb_buffer** out) {
+  if (!ctx || !out || !device_ptr || bytes < 0) return fail(ctx, QSB_E_INVAL, "qsb_buffer_wrap: bad argument");
+  *out = new qsb_buffer{ctx, device_ptr, bytes, false};
+  return QSB_OK;
+}
+
+int qsb_buffer_free(qsb_buffer* buf) {
+  if (!buf) return QSB_OK;
+  if (buf->owned) {
+    cudaSetDevice(buf->ctx->device);
+    cudaStreamSynchronize(buf->ctx->stream);
+    cudaFree(buf->ptr);
+  }
+  delete buf;
+  return QSB_OK;
+}
+
+static int check_range(qsb_buffer* buf, int64_t off, int64_t bytes, const char* what) {
+  if (!buf) return fail(nullptr, QSB_E_INVAL, "%s: buffer is NULL", what);
+  if (off < 0 || bytes < 0 || off + bytes > buf->bytes)
+    return fail(buf->ctx, QSB_E_INVAL, "%s: range [%lld, %lld) outside buffer of %lld bytes", what, (long long)off,
+                (long long)(off + bytes), (long long)buf->bytes);
+  return QSB_OK;
+}
+
+int qsb_buffer_upload(qsb_buffer* buf, int64_t offset, const void* host, int64_t bytes) {
+  int rc = check_range(buf, offset, bytes, "qsb_buffer_upload");
+  if (rc) return rc;
+  if (!host && bytes) return fail(buf->ctx, QSB_E_INVAL, "qsb_buffer_upload: host is NULL");
+  qsb_ctx* ctx = buf->ctx;
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaMemcpyAsync((char*)buf->ptr + offset, host, (size_t)bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return QSB_OK;
+}
+
+int qsb_buffer_download(qsb_buffer* buf, int64_t offset, void* host, int64_t bytes) {
+  int rc = check_range(buf, offset, bytes, "qsb_buffer_download");
+  if (rc) return rc;
+  if (!host && bytes) return fail(buf->ctx, QSB_E_INVAL, "qsb_buffer_download: host is NULL");
+  qsb_ctx* ctx = buf->ctx;
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaMemcpyAsync(host, (char*)buf->ptr + offset, (size_t)bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return QSB_OK;
+}
+
+int qsb_buffer_zero(qsb_buffer* buf, int64_t offset, int64_t bytes) {
+  int rc = check_range(buf, offset, bytes, "qsb_buffer_zero");
+  if (rc) return rc;
+  qsb_ctx* ctx = buf->ctx;
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaMemsetAsync((char*)buf->ptr + offset, 0, (size_t)bytes, ctx->stream));
+  return QSB_OK;
+}
+
+int qsb_buffer_copy(qsb_buffer* dst, int64_t dst_off, qsb_buffer* src, int64_t src_off, int64_t bytes) {
+  int rc = check_range(dst, dst_off, bytes, "qsb_buffer_copy(dst)");
+  if (rc) return rc;
+  rc = check_range(src, src_off, bytes, "qsb_buffer_copy(src)");
+  if (rc) return rc;
+  qsb_ctx* ctx = dst->ctx;
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaMemcpyAsync((char*)dst->ptr + dst_off, (char*)src->ptr + src_off, (size_t)bytes, cudaMemcpyDeviceToDevice,
+                          ctx->stream));
+  return QSB_OK;
+}
+
+void* qsb_buffer_ptr(qsb_buffer* buf) { return buf ? buf->ptr : nullptr; }
+int64_t qsb_buffer_bytes(qsb_buffer* buf) { return buf ? buf->bytes : 0; }
+
+int qsb_host_alloc(int64_t bytes, void** out) {
+  if (!out || bytes < 0) return fail(nullptr, QSB_E_INVAL, "qsb_host_alloc: bad argument");
+  CU(nullptr, cudaHostAlloc(out, bytes > 0 ? (size_t)bytes : 16, cudaHostAllocDefault));
+  return QSB_OK;
+}
+
+int qsb_host_free(void* p) {
+  if (p) CU(nullptr, cudaFreeHost(p));
+  return QSB_OK;
+}
+
+// ---- programs --------------------------------------------------------------------------
+static bool is_perm(const int32_t* p, int n) {
+  unsigned seen = 0;
+  for (int i = 0; i < n; ++i) {
+    if (p[i] < 0 || p[i] >= n || (seen >> p[i]) & 1) return false;
+    seen |= 1u << p[i];
+  }
+  return true;
+}
+
+int qsb_program_create(qsb_ctx* ctx, int32_t n, int32_t m, const qsb_op* ops, int64_t n_ops, int64_t ops_stride,
+                       int64_t n_programs, const double* cdata, int64_t n_cdata, const int32_t* idata, int64_t n_idata,
+                       int32_t load_perm, int32_t store_perm, int32_t n_snapshots, qsb_program** out) {
+  if (!ctx || !out) return fail(ctx, QSB_E_INVAL, "qsb_program_create: NULL argument");
+  *out = nullptr;
+  if (n < 1) return fail(ctx, QSB_E_INVAL, "num_qubits must be >= 1, got %d", n);
+  if (n > QSB_MAX_QUBITS)
+    return fail(ctx, QSB_E_UNSUPPORTED, "resident executor holds n <= %d qubits, got %d", QSB_MAX_QUBITS, n);
+  if (m < 1 || m > n || m > QSB_MAX_LOCAL_BITS || n - m > 3)
+    return fail(ctx, QSB_E_INVAL, "local_bits %d invalid for n = %d (need n-3 <= m <= min(n, %d))", m, n,
+                QSB_MAX_LOCAL_BITS);
+  if (n_ops < 0 || (n_ops > 0 && !ops) || n_programs < 1 || (ops_stride != 0 && ops_stride < n_ops))
+    return fail(ctx, QSB_E_INVAL, "bad op list");
+  if (n_idata < 0 || load_perm < 0 || store_perm < 0 || load_perm + n > n_idata || store_perm + n > n_idata)
+    return fail(ctx, QSB_E_INVAL, "load/store permutation outside idata");
+  if (!is_perm(idata + load_perm, n) || !is_perm(idata + store_perm, n))
+    return fail(ctx, QSB_E_INVAL, "load/store entries are not permutations of 0..n-1");
+  const int64_t total_ops = ops_stride ? ops_stride * n_programs : n_ops;
+  int32_t max_param = -1, max_draw = -1;
+  bool has_param = false;
+  const int gbits = n - m;
+  for (int64_t i = 0; i < total_ops; ++i) {
+    const qsb_op& o = ops[i];
+    int nb = 0, need = 0;
+    switch (o.kind) {
+      case QSB_OP_NOP: break;
+      case QSB_OP_U1: nb = 1; need = 8; break;
+      case QSB_OP_D1: nb = 1; need = 4; break;
+      case QSB_OP_U2: nb = 2; need = 32; break;
+      case QSB_OP_U3Q: nb = 3; need = 128; break;
+      case QSB_OP_X: case QSB_OP_Y: case QSB_OP_Z: nb = 1; break;
+      case QSB_OP_CX: case QSB_OP_CZ: case QSB_OP_SWAP: nb = 2; break;
+      case QSB_OP_CCX: case QSB_OP_CSWAP: nb = 3; break;
+      case QSB_OP_RX: case QSB_OP_RY: case QSB_OP_RZ: case QSB_OP_PHASE: case QSB_OP_U3:
+        nb = 1;
+        has_param = true;
+        if (o.param < 0) return fail(ctx, QSB_E_INVAL, "op %lld: parameterised gate without param index", (long long)i);
+        if (o.param + (o.kind == QSB_OP_U3 ? 2 : 0) > max_param) max_param = o.param + (o.kind == QSB_OP_U3 ? 2 : 0);
+        break;
+      case QSB_OP_KRAUS_PAULI: nb = 1; need = 7; break;
+      case QSB_OP_KRAUS_AD: nb = 1; need = 3; break;
+      case QSB_OP_KRAUS_GEN: nb = 1; need = 1; break;
+      case QSB_OP_REMAP:
+        if (o.b0 < 0 || o.b0 >= gbits || o.b1 < 0 || o.b1 >= m)
+          return fail(ctx, QSB_E_INVAL, "op %lld: remap bits (%d, %d) invalid", (long long)i, o.b0, o.b1);
+        break;
+      case QSB_OP_SNAPSHOT:
+        if (o.b0 < 0 || o.b0 >= n_snapshots || o.aux < 0 || o.aux + n > n_idata || !is_perm(idata + o.aux, n))
+          return fail(ctx, QSB_E_INVAL, "op %lld: bad snapshot slot / permutation", (long long)i);
+        break;
+      default:
+        return fail(ctx, QSB_E_INVAL, "op %lld: unknown kind %d", (long long)i, o.kind);
+    }
+    const int bits[3] = {o.b0, o.b1, o.b2};
+    if (o.kind != QSB_OP_REMAP && o.kind != QSB_OP_SNAPSHOT) {
+      for (int k = 0; k < nb; ++k) {
+        if (bits[k] < 0 || bits[k] >= m)
+          return fail(ctx, QSB_E_INVAL, "op %lld: target bit %d not resident (local_bits = %d)", (long long)i, bits[k], m);
+        for (int l = 0; l < k; ++l)
+          if (bits[l] == bits[k]) return fail(ctx, QSB_E_INVAL, "op %lld: repeated target bit", (long long)i);
+      }
+    }
+    if (need > 0) {
+      if (o.data < 0 || o.data + need > n_cdata) return fail(ctx, QSB_E_INVAL, "op %lld: cdata out of range", (long long)i);
+      if (o.kind == QSB_OP_KRAUS_GEN) {
+        int nk = (int)cdata[o.data];
+        if (nk < 1 || nk > 8 || o.data + 1 + 12 * nk > n_cdata)
+          return fail(ctx, QSB_E_INVAL, "op %lld: bad Kraus set", (long long)i);
+      }
+      if ((o.kind == QSB_OP_U2 || o.kind == QSB_OP_U3Q) && (o.data & 1))
+        return fail(ctx, QSB_E_INVAL, "op %lld: dense matrix must be 16-byte aligned in cdata", (long long)i);
+    }
+    if (o.kind >= QSB_OP_KRAUS_PAULI && o.kind <= QSB_OP_KRAUS_GEN) {
+      if (o.draw < 0) return fail(ctx, QSB_E_INVAL, "op %lld: Kraus op without draw index", (long long)i);
+      if (o.draw > max_draw) max_draw = o.draw;
+    }
+  }
+  CU(ctx, cudaSetDevice(ctx->device));
+  qsb_program* p = new qsb_program();
+  p->ctx = ctx;
+  p->n = n;
+  p->m = m;
+  p->n_ops = n_ops;
+  p->ops_stride = ops_stride;
+  p->n_programs = n_programs;
+  p->load_perm = load_perm;
+  p->store_perm = store_perm;
+  p->n_snapshots = n_snapshots;
+  p->n_idata = n_idata;
+  p->n_cdata = n_cdata;
+  p->max_param = max_param;
+  p->max_draw = max_draw;
+  p->has_param = has_param;
+  p->d_ops = nullptr;
+  p->d_cdata = nullptr;
+  p->d_idata = nullptr;
+  cudaError_t e = cudaMalloc(&p->d_ops, sizeof(qsb_op) * (size_t)(total_ops > 0 ? total_ops : 1));
+  if (e == cudaSuccess) e = cudaMalloc(&p->d_cdata, sizeof(double) * (size_t)(n_cdata > 0 ? n_cdata : 2));
+  if (e == cudaSuccess) e = cudaMalloc(&p->d_idata, sizeof(int32_t) * (size_t)n_idata);
+  if (e == cudaSuccess && total_ops)
+    e = cudaMemcpyAsync(p->d_ops, ops, sizeof(qsb_op) * (size_t)total_ops, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess && n_cdata)
+    e = cudaMemcpyAsync(p->d_cdata, cdata, sizeof(double) * (size_t)n_cdata, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(p->d_idata, idata, sizeof(int32_t) * (size_t)n_idata, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) {
+    cudaFree(p->d_ops);
+    cudaFree(p->d_cdata);
+    cudaFree(p->d_idata);
+    delete p;
+    cudaGetLastError();
+    return fail(ctx, e == cudaErrorMemoryAllocation ? QSB_E_OOM : QSB_E_CUDA, "program upload: %s", cudaGetErrorString(e));
+  }
+  *out = p;
+  return QSB_OK;
+}
+
+int qsb_program_free(qsb_program* p) {
+  if (!p) return QSB_OK;
+  cudaSetDevice(p->ctx->device);
+  cudaStreamSynchronize(p->ctx->stream);
+  cudaFree(p->d_ops);
+  cudaFree(p->d_cdata);
+  cudaFree(p->d_idata);
+  delete p;
+  return QSB_OK;
+}
+
+}  // extern "C"
+
+template <int C>
+static cudaError_t launch_traj(qsb_ctx* ctx, const qsb_exec_args& a, int threads, size_t smem, int* grid_out) {
+  auto kern = qsb_traj_kernel<C>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.blockDim = dim3(threads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int64_t max_units;
+  if (C > 1) {
+    int nclusters = 0;
+    cfg.gridDim = dim3(C * ctx->sm_count, 1, 1);
+    e = cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg);
+    if (e != cudaSuccess) return e;
+    if (nclusters < 1) return cudaErrorLaunchOutOfResources;
+    max_units = nclusters;
+  } else {
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    max_units = (int64_t)per_sm * ctx->sm_count;
+  }
+  int64_t units = a.count < max_units ? a.count : max_units;
+  cfg.gridDim = dim3((unsigned)(units * C), 1, 1);
+  *grid_out = (int)(units * C);
+  return cudaLaunchKernelEx(&cfg, kern, a);
+}
+
+extern "C" {
+
+static int need(qsb_ctx* ctx, qsb_buffer* b, int64_t bytes, const char* what) {
+  if (!b) return fail(ctx, QSB_E_INVAL, "%s buffer is NULL", what);
+  if (b->bytes < bytes)
+    return fail(ctx, QSB_E_INVAL, "%s buffer too small: %lld < %lld bytes", what, (long long)b->bytes, (long long)bytes);
+  return QSB_OK;
+}
+
+int qsb_run(qsb_program* p, const qsb_run_args* r) {
+  if (!p || !r) return fail(nullptr, QSB_E_INVAL, "qsb_run: NULL argument");
+  qsb_ctx* ctx = p->ctx;
+  if (r->count < 0 || r->first < 0) return fail(ctx, QSB_E_INVAL, "qsb_run: negative range");
+  if (r->count == 0) return QSB_OK;
+  const int64_t dim = (int64_t)1 << p->n;
+  int rc;
+  if (r->flags & (QSB_RUN_LOAD | QSB_RUN_STORE))
+    if ((rc = need(ctx, r->states, (r->first + r->count) * dim * 16, "states"))) return rc;
+  if (p->ops_stride && r->count > p->n_programs)
+    return fail(ctx, QSB_E_INVAL, "qsb_run: %lld trajectories but only %lld per-trajectory programs",
+                (long long)r->count, (long long)p->n_programs);
+  if (p->has_param) {
+    if (r->params_stride <= p->max_param) return fail(ctx, QSB_E_INVAL, "qsb_run: params_stride too small");
+    if ((rc = need(ctx, r->params, r->count * r->params_stride * 8, "params"))) return rc;
+  }
+  if (r->uniforms && p->max_draw >= 0) {
+    if (r->uniforms_stride <= p->max_draw) return fail(ctx, QSB_E_INVAL, "qsb_run: uniforms_stride too small");
+    if ((rc = need(ctx, r->uniforms, r->count * r->uniforms_stride * 8, "uniforms"))) return rc;
+  }
+  if (r->branches && p->max_draw >= 0) {
+    if (r->branches_stride <= p->max_draw) return fail(ctx, QSB_E_INVAL, "qsb_run: branches_stride too small");
+    if ((rc = need(ctx, r->branches, r->count * r->branches_stride * 4, "branches"))) return rc;
+  }
+  if (r->init_basis && (rc = need(ctx, r->init_basis, r->count * 8, "init_basis"))) return rc;
+  if (!r->init_basis && (r->default_basis < 0 || r->default_basis >= dim) && !(r->flags & QSB_RUN_LOAD))
+    return fail(ctx, QSB_E_INVAL, "qsb_run: default_basis out of range");
+  if (p->n_snapshots > 0 && r->snapshots &&
+      (rc = need(ctx, r->snapshots, r->count * p->n_snapshots * dim * 16, "snapshots")))
+    return rc;
+  if ((r->flags & QSB_RUN_ACCUM_PROBS) && (rc = need(ctx, r->probs_accum, dim * 8, "probs_accum"))) return rc;
+
+  qsb_exec_args a;
+  memset(&a, 0, sizeof a);
+  a.ops = p->d_ops;
+  a.n_ops = p->n_ops;
+  a.ops_stride = p->ops_stride;
+  a.cdata = p->d_cdata;
+  a.idata = p->d_idata;
+  a.n = p->n;
+  a.m = p->m;
+  a.load_perm = p->load_perm;
+  a.store_perm = p->store_perm;
+  a.n_snapshots = p->n_snapshots;
+  a.flags = r->flags;
+  a.states = r->states ? (c128*)r->states->ptr + r->first * dim : nullptr;
+  a.count = r->count;
+  a.params = r->params ? (const double*)r->params->ptr : nullptr;
+  a.params_stride = r->params_stride;
+  a.uniforms = r->uniforms ? (const double*)r->uniforms->ptr : nullptr;
+  a.uniforms_stride = r->uniforms_stride;
+  a.seed = r->philox_seed;
+  a.traj_offset = r->traj_offset;
+  a.init_basis = r->init_basis ? (const int64_t*)r->init_basis->ptr : nullptr;
+  a.default_basis = r->default_basis;
+  a.branches = r->branches ? (int32_t*)r->branches->ptr : nullptr;
+  a.branches_stride = r->branches_stride;
+  a.snapshots = (p->n_snapshots > 0 && r->snapshots) ? (c128*)r->snapshots->ptr : nullptr;
+  a.probs_accum = (r->flags & QSB_RUN_ACCUM_PROBS) ? (double*)r->probs_accum->ptr : nullptr;
+
+  CU(ctx, cudaSetDevice(ctx->device));
+  const int C = 1 << (p->n - p->m);
+  int threads = 1 << (p->m > 4 ? p->m - 4 : 1);       // 16 amplitudes per thread per pass
+  if (threads < 32) threads = 32;
+  if (threads > QSB_TRAJ_THREADS) threads = QSB_TRAJ_THREADS;
+  const size_t smem = ((size_t)16 << p->m) + QSB_SMEM_EXTRA;
+  int grid = 0;
+  cudaError_t e;
+  switch (C) {
+    case 1: e = launch_traj<1>(ctx, a, threads, smem, &grid); break;
+    case 2: e = launch_traj<2>(ctx, a, threads, smem, &grid); break;
+    case 4: e = launch_traj<4>(ctx, a, threads, smem, &grid); break;
+    case 8: e = launch_traj<8>(ctx, a, threads, smem, &grid); break;
+    default: return fail(ctx, QSB_E_UNSUPPORTED, "cluster size %d", C);
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(ctx, QSB_E_CUDA, "trajectory kernel launch (C=%d, threads=%d, smem=%zu): %s", C, threads, smem,
+                cudaGetErrorString(e));
+  }
+  ctx->launches += 1;
+  if (!(r->flags & QSB_RUN_ASYNC)) CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return QSB_OK;
+}
+
+// ---- reductions ------------------------------------------------------------------------
+#define CHECK_N(ctx, n)                                                                       \
+  if (!(ctx)) return fail(nullptr, QSB_E_INVAL, "ctx is NULL");                               \
+  if ((n) < 1 || (n) > 30) return fail(ctx, QSB_E_INVAL, "num_qubits %d out of range", (int)(n))
+
+static int after_launch(qsb_ctx* ctx, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(ctx, QSB_E_CUDA, "%s launch: %s", what, cudaGetErrorString(e));
+  ctx->launches += 1;
+  e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) return fail(ctx, QSB_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  return QSB_OK;
+}
+
+static int grid_for(qsb_ctx* ctx, int64_t items, int threads) {
+  int64_t g = (items + threads - 1) / threads;
+  int64_t cap = (int64_t)ctx->sm_count * 16;
+  if (g > cap) g = cap;
+  return g < 1 ? 1 : (int)g;
+}
+
+int qsb_probabilities(qsb_ctx* ctx, int32_t n, qsb_buffer* states, int64_t first, int64_t count, qsb_buffer* out,
+                      int64_t out_first) {
+  CHECK_N(ctx, n);
+  const int64_t dim = (int64_t)1 << n;
+  int rc;
+  if (count <= 0) return count == 0 ? QSB_OK : fail(ctx, QSB_E_INVAL, "negative count");
+  if ((rc = need(ctx, states, (first + count) * dim * 16, "states"))) return rc;
+  if ((rc = need(ctx, out, (out_first + count) * dim * 8, "probabilities"))) return rc;
+  CU(ctx, cudaSetDevice(ctx->device));
+  qsb_probs_kernel<<<grid_for(ctx, count * dim, 256), 256, 0, ctx->stream>>>(
+      (const c128*)states->ptr + first * dim, (double*)out->ptr + out_first * dim, count * dim);
+  return after_launch(ctx, "probabilities");
+}
+
+int qsb_probabilities_sum(qsb_ctx* ctx, int32_t n, qsb_buffer* states, int64_t first, int64_t count, qsb_buffer* out) {
+  CHECK_N(ctx, n);
+  const int64_t dim = (int64_t)1 << n;
+  int rc;
+  if (count <= 0) return count == 0 ? QSB_OK : fail(ctx, QSB_E_INVAL, "negative count");
+  if ((rc = need(ctx, states, (first + count) * dim * 16, "states"))) return rc;
+  if ((rc = need(ctx, out, dim * 8, "probability sum"))) return rc;
+  CU(ctx, cudaSetDevice(ctx->device));
+  qsb_probs_sum_kernel<<<grid_for(ctx, dim, 128), 128, 0, ctx->stream>>>((const c128*)states->ptr + first * dim,
+                                                                         (double*)out->ptr, dim, count);
+  return after_launch(ctx, "probabilities_sum");
+}
+
+int qsb_sample_index(qsb_ctx* ctx, int32_t n, qsb_buffer* states, int64_t first, int64_t count, qsb_buffer* uniforms,
+                     qsb_buffer* out) {
+  CHECK_N(ctx, n);
+  const int64_t dim = (int64_t)1 << n;
+  int rc;
+  if (count <= 0) return count == 0 ? QSB_OK : fail(ctx, QSB_E_INVAL, "negative count");
+  if ((rc = need(ctx, states, (first + count) * dim * 16, "states"))) return rc;
+  if ((rc = need(ctx, uniforms, count * 8, "uniforms"))) return rc;
+  if ((rc = need(ctx, out, count * 8, "sample output"))) return rc;
+  CU(ctx, cudaSetDevice(ctx->device));
+  int threads = dim >= 256 ? 256 : 32;
+  qsb_sample_kernel<<<(unsigned)count, threads, 0, ctx->stream>>>((const c128*)states->ptr + first * dim,
+                                                                  (const double*)uniforms->ptr, (int64_t*)out->ptr, dim);
+  return after_launch(ctx, "sample_index");
+}
+
+int qsb_overlap(qsb_ctx* ctx, int32_t n, qsb_buffer* a, int64_t a_first, qsb_buffer* b, int64_t b_first,
+                int64_t b_stride_states, int64_t count, qsb_buffer* out) {
+  CHECK_N(ctx, n);
+  const int64_t dim = (int64_t)1 << n;
+  int rc;
+  if (count <= 0) return count == 0 ? QSB_OK : fail(ctx, QSB_E_INVAL, "negative count");
+  if (b_stride_states != 0 && b_stride_states != 1) return fail(ctx, QSB_E_INVAL, "b_stride_states must be 0 or 1");
+  if ((rc = need(ctx, a, (a_first + count) * dim * 16, "states a"))) return rc;
+  if ((rc = need(ctx, b, (b_first + (b_stride_states ? count : 1)) * dim * 16, "states b"))) return rc;
+  if ((rc = need(ctx, out, count * 16, "overlap output"))) return rc;
+  CU(ctx, cudaSetDevice(ctx->device));
+  qsb_overlap_kernel<<<(unsigned)count, 256, 0, ctx->stream>>>((const c128*)a->ptr + a_first * dim,
+                                                               (const c128*)b->ptr + b_first * dim,
+                                                               b_stride_states * dim, (c128*)out->ptr, dim);
+  return after_launch(ctx, "overlap");
+}
+
+int qsb_masked_parity(qsb_ctx* ctx, int32_t n, qsb_buffer* states, int64_t first, int64_t count, const uint64_t* masks,
+                      int32_t n_masks, qsb_buffer* out) {
+  CHECK_N(ctx, n);
+  const int64_t dim = (int64_t)1 << n;
+  int rc;
+  if (count <= 0) return count == 0 ? QSB_OK : fail(ctx, QSB_E_INVAL, "negative count");
+  if (n_masks < 1 || n_masks > 8 || !masks) return fail(ctx, QSB_E_INVAL, "n_masks must be 1..8");
+  if ((rc = need(ctx, states, (first + count) * dim * 16, "states"))) return rc;
+  if ((rc = need(ctx, out, count * n_masks * 16, "parity output"))) return rc;
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaMemcpyAsync(ctx->d_masks, masks, sizeof(uint64_t) * n_masks, cudaMemcpyHostToDevice, ctx->stream));
+  qsb_parity_kernel<<<(unsigned)count, 256, 0, ctx->stream>>>((const c128*)states->ptr + first * dim, dim, ctx->d_masks,
+                                                              n_masks, (double*)out->ptr);
+  return after_launch(ctx, "masked_parity");
+}
+
+int qsb_rdm_all(qsb_ctx* ctx, int32_t n, qsb_buffer* states, int64_t first, int64_t count, qsb_buffer* rdm1,
+                qsb_buffer* rdm2) {
+  CHECK_N(ctx, n);
+  const int64_t dim = (int64_t)1 << n;
+  const int npairs = n * (n - 1) / 2;
+  int rc;
+  if (count <= 0) return count == 0 ? QSB_OK : fail(ctx, QSB_E_INVAL, "negative count");
+  if ((rc = need(ctx, states, (first + count) * dim * 16, "states"))) return rc;
+  CU(ctx, cudaSetDevice(ctx->device));
+  const c128* s = (const c128*)states->ptr + first * dim;
+  if (rdm1) {
+    if ((rc = need(ctx, rdm1, count * n * 4 * 16, "rdm1"))) return rc;
+    qsb_rdm1_kernel<<<(unsigned)(count * n), 256, 0, ctx->stream>>>(s, n, (c128*)rdm1->ptr);
+    if ((rc = after_launch(ctx, "rdm1"))) return rc;
+  }
+  if (rdm2 && npairs > 0) {
+    if ((rc = need(ctx, rdm2, count * npairs * 16 * 16, "rdm2"))) return rc;
+    qsb_rdm2_kernel<<<(unsigned)(count * npairs), 256, 0, ctx->stream>>>(s, n, npairs, (c128*)rdm2->ptr);
+    if ((rc = after_launch(ctx, "rdm2"))) return rc;
+  }
+  return QSB_OK;
+}
+
+int qsb_rho_accumulate(qsb_ctx* ctx, int32_t n, qsb_buffer* states, int64_t first, int64_t count, double scale,
+                       qsb_buffer* rho) {
+  CHECK_N(ctx, n);
+  if (n > 14) return fail(ctx, QSB_E_UNSUPPORTED, "rho of %d qubits does not fit (4^n complex128)", n);
+  const int64_t dim = (int64_t)1 << n;
+  int rc;
+  if (count <= 0) return count == 0 ? QSB_OK : fail(ctx, QSB_E_INVAL, "negative count");
+  if ((rc = need(ctx, states, (first + count) * dim * 16, "states"))) return rc;
+  if ((rc = need(ctx, rho, dim * dim * 16, "rho"))) return rc;
+  CU(ctx, cudaSetDevice(ctx->device));
+  const unsigned g = (unsigned)((dim + QSB_RHO_TILE - 1) / QSB_RHO_TILE);
+  qsb_rho_kernel<<<dim3(g, g, 1), 256, 0, ctx->stream>>>((const c128*)states->ptr + first * dim, dim, count, scale,
+                                                         (c128*)rho->ptr);
+  return after_launch(ctx, "rho_accumulate");
+}
+
+int qsb_readout_transform(qsb_ctx* ctx, int32_t n, qsb_buffer* probs, int64_t count, double p01, double p10) {
+  CHECK_N(ctx, n);
+  const int64_t dim = (int64_t)1 << n;
+  int rc;
+  if (count <= 0) return count == 0 ? QSB_OK : fail(ctx, QSB_E_INVAL, "negative count");
+  if (!(p01 >= 0 && p01 <= 1 && p10 >= 0 && p10 <= 1))
+    return fail(ctx, QSB_E_INVAL, "Readout error probabilities must be in [0, 1]");
+  if ((rc = need(ctx, probs, count * dim * 8, "probabilities"))) return rc;
+  CU(ctx, cudaSetDevice(ctx->device));
+  // axis q of the reference's [2]*n tensor is bit n-1-q; axes are transformed in order q = 0..n-1 (noise.py:163)
+  for (int q = 0; q < n; ++q) {
+    qsb_readout_axis_kernel<<<grid_for(ctx, count * dim / 2, 256), 256, 0, ctx->stream>>>(
+        (double*)probs->ptr, dim, count, n - 1 - q, 1.0 - p01, p10, p01, 1.0 - p10);
+    ctx->launches += 1;
+  }
+  qsb_normalize_dist_kernel<<<(unsigned)count, 256, 0, ctx->stream>>>((double*)probs->ptr, dim);
+  return after_launch(ctx, "readout_transform");
+}
+
+}  // extern "C"

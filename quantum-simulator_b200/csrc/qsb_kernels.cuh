@@ -1,0 +1,362 @@
+// qsb_kernels.cuh -- CUDA side of the executor (DeviceEnv + trajectory kernel) and the
+// reduction kernels over stored states.  sm_100a only.
+#pragma once
+
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+
+#include "qsb_exec.cuh"
+
+namespace cg = cooperative_groups;
+
+#define QSB_TRAJ_THREADS 512
+#define QSB_SMEM_EXTRA (512 * 4 + 16 * 4 * 8 + 2 * 4 * 8)   // perm table + warp partials + cluster partials
+
+template <int C>
+struct DeviceEnv {
+  int tid, T, rank;
+  c128* tile_;
+  uint32_t* perm_;
+  double* wpart_;
+  double* cl_;
+  int parity;
+
+  __device__ DeviceEnv(unsigned char* smem, int m) {
+    tid = threadIdx.x;
+    T = blockDim.x;
+    rank = (C > 1) ? (int)cg::this_cluster().block_rank() : 0;
+    tile_ = reinterpret_cast<c128*>(smem);
+    unsigned char* p = smem + ((size_t)16 << m);
+    perm_ = reinterpret_cast<uint32_t*>(p);
+    wpart_ = reinterpret_cast<double*>(p + 2048);
+    cl_ = reinterpret_cast<double*>(p + 2048 + 512);
+    parity = 0;
+  }
+  __device__ __forceinline__ c128* tile() { return tile_; }
+  __device__ __forceinline__ uint32_t* perm_table() { return perm_; }
+  __device__ __forceinline__ void sync_block() { __syncthreads(); }
+  __device__ __forceinline__ void sync_cluster() {
+    if (C > 1) cg::this_cluster().sync(); else __syncthreads();
+  }
+  __device__ __forceinline__ const c128* peer_tile(int r) {
+    if (C > 1) return cg::this_cluster().map_shared_rank(tile_, r);
+    return tile_;
+  }
+  __device__ __forceinline__ void atomic_add(double* p, double v) { atomicAdd(p, v); }
+
+  // sum v[0..nv) over every thread of the cluster; all threads get bit-identical results
+  __device__ void allreduce(double* v, int nv) {
+    const int lane = tid & 31, warp = tid >> 5, nw = (T + 31) >> 5;
+    __syncthreads();
+    for (int k = 0; k < nv; ++k) {
+      double x = v[k];
+      for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+      if (lane == 0) wpart_[warp * 4 + k] = x;
+    }
+    __syncthreads();
+    for (int k = 0; k < nv; ++k) {
+      double s = 0.0;
+      for (int w = 0; w < nw; ++w) s += wpart_[w * 4 + k];
+      v[k] = s;
+    }
+    if (C > 1) {
+      cg::cluster_group cl = cg::this_cluster();
+      if (tid == 0)
+        for (int k = 0; k < nv; ++k) cl_[parity * 4 + k] = v[k];
+      cl.sync();
+      for (int k = 0; k < nv; ++k) {
+        double s = 0.0;
+        for (int r = 0; r < C; ++r) s += cl.map_shared_rank(cl_, r)[parity * 4 + k];
+        v[k] = s;
+      }
+      parity ^= 1;   // the buffer of reduction k is rewritten at k+2, after everyone passed barrier k+1
+    }
+  }
+};
+
+template <int C>
+__global__ void __launch_bounds__(QSB_TRAJ_THREADS, 1) qsb_traj_kernel(const __grid_constant__ qsb_exec_args a) {
+  extern __shared__ __align__(16) unsigned char qsb_smem[];
+  DeviceEnv<C> env(qsb_smem, a.m);
+  const int64_t cluster_id = blockIdx.x / C, n_clusters = gridDim.x / C;
+  for (int64_t t = cluster_id; t < a.count; t += n_clusters) qsb_exec_trajectory(env, a, t);
+  if (C > 1) cg::this_cluster().sync();   // no CTA may exit while a peer can still read its shared memory
+}
+
+// ---------------------------------------------------------------------------------------
+// block-wide sum of NV doubles (result valid in every thread); scratch >= 32 * NV doubles
+template <int NV>
+__device__ __forceinline__ void qsb_block_sum(double* v, double* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double x = v[k];
+    for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+    if (lane == 0) scratch[warp * NV + k] = x;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double s = 0.0;
+    for (int w = 0; w < nw; ++w) s += scratch[w * NV + k];
+    v[k] = s;
+  }
+}
+
+// |a|^2 elementwise (state_vector.py:36-39)
+__global__ void qsb_probs_kernel(const c128* __restrict__ psi, double* __restrict__ out, int64_t total) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    c128 a = psi[i];
+    out[i] = a.x * a.x + a.y * a.y;
+  }
+}
+
+// out[i] += sum_t |psi_t[i]|^2
+__global__ void qsb_probs_sum_kernel(const c128* __restrict__ psi, double* __restrict__ out, int64_t dim, int64_t count) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < dim; i += (int64_t)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int64_t t = 0; t < count; ++t) {
+      c128 a = psi[t * dim + i];
+      s += a.x * a.x + a.y * a.y;
+    }
+    out[i] += s;
+  }
+}
+
+// StateVector.measure_all (state_vector.py:107-113): first index whose running probability mass exceeds
+// u * total  (== searchsorted(cumsum(p / p.sum()) / cdf[-1], u, side='right'))
+__global__ void qsb_sample_kernel(const c128* __restrict__ psi, const double* __restrict__ u, int64_t* __restrict__ out,
+                                  int64_t dim) {
+  __shared__ double chunk_sum[256];
+  __shared__ double prefix[257];
+  const c128* s = psi + blockIdx.x * dim;
+  const int T = blockDim.x, tid = threadIdx.x;
+  const int64_t per = (dim + T - 1) / T, lo = tid * per, hi = (lo + per < dim) ? lo + per : dim;
+  double acc = 0.0;
+  for (int64_t i = lo; i < hi; ++i) { c128 a = s[i]; acc += a.x * a.x + a.y * a.y; }
+  chunk_sum[tid] = acc;
+  __syncthreads();
+  if (tid == 0) {
+    double run = 0.0;
+    for (int k = 0; k < T; ++k) { prefix[k] = run; run += chunk_sum[k]; }
+    prefix[T] = run;
+    out[blockIdx.x] = dim - 1;     // fallback when rounding leaves the target at the very end
+  }
+  __syncthreads();
+  const double target = u[blockIdx.x] * prefix[T];
+  if (lo < hi && prefix[tid] <= target && (target < prefix[tid + 1] || tid == T - 1)) {
+    // the in-chunk running sum can differ from chunk_sum by rounding: fall back to the chunk's last
+    // amplitude with weight instead of leaving the sample unassigned
+    double run = prefix[tid];
+    int64_t pick = -1, last_nz = hi - 1;
+    for (int64_t i = lo; i < hi; ++i) {
+      c128 a = s[i];
+      double p = a.x * a.x + a.y * a.y;
+      run += p;
+      if (p > 0.0) last_nz = i;
+      if (run > target) { pick = i; break; }
+    }
+    out[blockIdx.x] = pick >= 0 ? pick : last_nz;
+  }
+}
+
+// out[t] = sum_i conj(a_t[i]) * b_t[i]   (np.vdot, analysis.py:40)
+__global__ void qsb_overlap_kernel(const c128* __restrict__ a, const c128* __restrict__ b, int64_t b_stride,
+                                   c128* __restrict__ out, int64_t dim) {
+  __shared__ double scratch[64];
+  const c128* x = a + blockIdx.x * dim;
+  const c128* y = b + blockIdx.x * b_stride;
+  double v[2] = {0.0, 0.0};
+  for (int64_t i = threadIdx.x; i < dim; i += blockDim.x) {
+    c128 p = x[i], q = y[i];
+    v[0] += p.x * q.x + p.y * q.y;
+    v[1] += p.x * q.y - p.y * q.x;
+  }
+  qsb_block_sum<2>(v, scratch);
+  if (threadIdx.x == 0) out[blockIdx.x] = make_double2(v[0], v[1]);
+}
+
+// (p_even, p_odd) per mask (qec.py:466-484); up to 8 masks per launch
+__global__ void qsb_parity_kernel(const c128* __restrict__ psi, int64_t dim, const uint64_t* __restrict__ masks,
+                                  int n_masks, double* __restrict__ out) {
+  __shared__ double scratch[32 * 16];
+  const c128* s = psi + blockIdx.x * dim;
+  double v[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) v[k] = 0.0;
+  uint64_t mk[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) mk[k] = k < n_masks ? masks[k] : 0;
+  for (int64_t i = threadIdx.x; i < dim; i += blockDim.x) {
+    c128 a = s[i];
+    double p = a.x * a.x + a.y * a.y;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      int odd = __popcll((uint64_t)i & mk[k]) & 1;
+      v[2 * k] += odd ? 0.0 : p;
+      v[2 * k + 1] += odd ? p : 0.0;
+    }
+  }
+  qsb_block_sum<16>(v, scratch);
+  if (threadIdx.x == 0)
+    for (int k = 0; k < n_masks; ++k) {
+      out[(blockIdx.x * (int64_t)n_masks + k) * 2] = v[2 * k];
+      out[(blockIdx.x * (int64_t)n_masks + k) * 2 + 1] = v[2 * k + 1];
+    }
+}
+
+// 1-qubit RDMs: block (t, q) -> rdm1[t][q][2][2]  (state_vector.py:121-140)
+__global__ void qsb_rdm1_kernel(const c128* __restrict__ psi, int n, c128* __restrict__ out) {
+  __shared__ double scratch[32 * 4];
+  const int64_t dim = (int64_t)1 << n;
+  const int q = blockIdx.x % n;
+  const int64_t t = blockIdx.x / n;
+  const int b = n - 1 - q;
+  const c128* s = psi + t * dim;
+  double v[4] = {0, 0, 0, 0};
+  for (int64_t g = threadIdx.x; g < dim / 2; g += blockDim.x) {
+    int64_t i0 = ((g >> b) << (b + 1)) | (g & (((int64_t)1 << b) - 1));
+    c128 a0 = s[i0], a1 = s[i0 | ((int64_t)1 << b)];
+    v[0] += a0.x * a0.x + a0.y * a0.y;
+    v[1] += a1.x * a1.x + a1.y * a1.y;
+    v[2] += a0.x * a1.x + a0.y * a1.y;      // a0 conj(a1)
+    v[3] += a0.y * a1.x - a0.x * a1.y;
+  }
+  qsb_block_sum<4>(v, scratch);
+  if (threadIdx.x == 0) {
+    c128* o = out + (t * n + q) * 4;
+    o[0] = make_double2(v[0], 0.0);
+    o[1] = make_double2(v[2], v[3]);
+    o[2] = make_double2(v[2], -v[3]);
+    o[3] = make_double2(v[1], 0.0);
+  }
+}
+
+// 2-qubit RDMs: block (t, pair) -> rdm2[t][pair][4][4], row index = (bit_i << 1 | bit_j), i < j
+// rho[r][c] = sum_env psi[r,env] conj(psi[c,env])   (analysis.py:159-166)
+__global__ void qsb_rdm2_kernel(const c128* __restrict__ psi, int n, int npairs, c128* __restrict__ out) {
+  __shared__ double scratch[32 * 16];
+  const int64_t dim = (int64_t)1 << n;
+  int pair = blockIdx.x % npairs;
+  const int64_t t = blockIdx.x / npairs;
+  int qi = 0, rem = pair;
+  while (rem >= n - 1 - qi) { rem -= n - 1 - qi; ++qi; }
+  const int qj = qi + 1 + rem;
+  const int bh = n - 1 - qi, bl = n - 1 - qj;    // bh > bl
+  const c128* s = psi + t * dim;
+  double v[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) v[k] = 0.0;
+  for (int64_t g = threadIdx.x; g < dim / 4; g += blockDim.x) {
+    int64_t i = ((g >> bl) << (bl + 1)) | (g & (((int64_t)1 << bl) - 1));
+    i = ((i >> bh) << (bh + 1)) | (i & (((int64_t)1 << bh) - 1));
+    c128 a[4];
+    a[0] = s[i];
+    a[1] = s[i | ((int64_t)1 << bl)];
+    a[2] = s[i | ((int64_t)1 << bh)];
+    a[3] = s[i | ((int64_t)1 << bh) | ((int64_t)1 << bl)];
+    // diag (4 reals) + upper triangle (6 complex)
+    int k = 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) v[k++] += a[r].x * a[r].x + a[r].y * a[r].y;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = r + 1; c < 4; ++c) {
+        v[k++] += a[r].x * a[c].x + a[r].y * a[c].y;
+        v[k++] += a[r].y * a[c].x - a[r].x * a[c].y;
+      }
+  }
+  qsb_block_sum<16>(v, scratch);
+  if (threadIdx.x == 0) {
+    c128* o = out + (t * npairs + pair) * 16;
+    int k = 4;
+    for (int r = 0; r < 4; ++r) o[r * 4 + r] = make_double2(v[r], 0.0);
+    for (int r = 0; r < 4; ++r)
+      for (int c = r + 1; c < 4; ++c) {
+        o[r * 4 + c] = make_double2(v[k], v[k + 1]);
+        o[c * 4 + r] = make_double2(v[k], -v[k + 1]);
+        k += 2;
+      }
+  }
+}
+
+// rho[i][j] += scale * sum_t psi_t[i] conj(psi_t[j])   (simulator.py:195-198)
+// 64x64 tile of rho per CTA (256 threads, 4x4 outputs each), 16 trajectories per shared-memory stage.
+#define QSB_RHO_TILE 64
+#define QSB_RHO_KC 16
+__global__ void __launch_bounds__(256) qsb_rho_kernel(const c128* __restrict__ psi, int64_t dim, int64_t count,
+                                                       double scale, c128* __restrict__ rho) {
+  __shared__ c128 sa[QSB_RHO_KC][QSB_RHO_TILE];
+  __shared__ c128 sb[QSB_RHO_KC][QSB_RHO_TILE];
+  const int64_t i0 = (int64_t)blockIdx.y * QSB_RHO_TILE, j0 = (int64_t)blockIdx.x * QSB_RHO_TILE;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  c128 acc[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = make_double2(0.0, 0.0);
+  for (int64_t t0 = 0; t0 < count; t0 += QSB_RHO_KC) {
+    for (int e = threadIdx.x; e < QSB_RHO_KC * QSB_RHO_TILE; e += 256) {
+      int k = e / QSB_RHO_TILE, x = e % QSB_RHO_TILE;
+      c128 z = make_double2(0.0, 0.0);
+      sa[k][x] = (t0 + k < count && i0 + x < dim) ? psi[(t0 + k) * dim + i0 + x] : z;
+      sb[k][x] = (t0 + k < count && j0 + x < dim) ? psi[(t0 + k) * dim + j0 + x] : z;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int k = 0; k < QSB_RHO_KC; ++k) {
+      c128 av[4], bv[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) av[r] = sa[k][ty + 16 * r];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) bv[c] = sb[k][tx + 16 * c];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {   // a * conj(b)
+          acc[r][c].x = fma(av[r].x, bv[c].x, fma(av[r].y, bv[c].y, acc[r][c].x));
+          acc[r][c].y = fma(av[r].y, bv[c].x, fma(-av[r].x, bv[c].y, acc[r][c].y));
+        }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      int64_t i = i0 + ty + 16 * r, j = j0 + tx + 16 * c;
+      if (i < dim && j < dim) {
+        c128 o = rho[i * dim + j];
+        o.x += scale * acc[r][c].x;
+        o.y += scale * acc[r][c].y;
+        rho[i * dim + j] = o;
+      }
+    }
+}
+
+// one axis of ReadoutError.apply_to_distribution (noise.py:163-169): out[m] = C[m][0] p0 + C[m][1] p1
+__global__ void qsb_readout_axis_kernel(double* __restrict__ p, int64_t dim, int64_t count, int b, double c00, double c01,
+                                        double c10, double c11) {
+  const int64_t half = dim / 2, total = half * count;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = e / half, g = e % half;
+    int64_t i0 = ((g >> b) << (b + 1)) | (g & (((int64_t)1 << b) - 1));
+    double* q = p + t * dim;
+    double p0 = q[i0], p1 = q[i0 | ((int64_t)1 << b)];
+    q[i0] = c00 * p0 + c01 * p1;
+    q[i0 | ((int64_t)1 << b)] = c10 * p0 + c11 * p1;
+  }
+}
+
+// divide each distribution by its total if total > 1e-15 (noise.py:172-174); one CTA per distribution
+__global__ void qsb_normalize_dist_kernel(double* __restrict__ p, int64_t dim) {
+  __shared__ double scratch[32];
+  double* q = p + blockIdx.x * dim;
+  double v[1] = {0.0};
+  for (int64_t i = threadIdx.x; i < dim; i += blockDim.x) v[0] += q[i];
+  qsb_block_sum<1>(v, scratch);
+  if (v[0] > 1e-15)
+    for (int64_t i = threadIdx.x; i < dim; i += blockDim.x) q[i] = q[i] / v[0];
+}

@@ -1,0 +1,190 @@
+"""Executor + host compiler vs the oracle, on the test-only host emulator (CPU, no GPU).
+
+Same `qsb_exec.cuh` op loop the CUDA kernel runs, same `qsb_op` programs; what this cannot see is
+the CUDA-only glue (DeviceEnv barriers/reductions, launch config, C ABI) -- that is tests/test_gpu_*."""
+
+import numpy as np
+import pytest
+
+from oracle import qsim_oracle as O
+from conftest import as_gates, as_noise
+from emu_util import emu_run
+from qsb.lowering import lower_circuit
+from qsb.compiler import Lowering
+from qsb.workloads import layered_circuit, config3_noise
+from quantum_sim.engine.circuit import QuantumCircuit, GateInstance
+from quantum_sim.engine.gate_registry import GateRegistry
+
+TOL = 1e-12
+REG = GateRegistry.instance()
+
+
+def make_circuit(n, gates, initial=None):
+    qc = QuantumCircuit(n, initial_states=list(initial) if initial else [])
+    for g in gates:
+        qc.add_gate(GateInstance(g[0], list(g[1]), list(g[2]), g[3]))
+    return qc
+
+
+def channels_of_factory(noise):
+    if noise is None:
+        return None
+    def f(name):
+        return [(k, p, None) for k, p in O.channels_for(noise, name)]
+    return f
+
+
+def basis_index(initial):
+    n = len(initial)
+    return sum(1 << (n - 1 - i) for i, b in enumerate(initial) if b)
+
+
+@pytest.mark.parametrize("gbits", [0, 1, 2, 3])
+def test_random_circuits_vs_oracle(golden, gbits):
+    j, a = golden
+    for rec in j["random_circuits"]:
+        n = rec["n"]
+        m = n - gbits
+        if m < 3:
+            continue
+        qc = make_circuit(n, as_gates(rec["gates"]), rec["initial"])
+        prog, _ = lower_circuit(n, qc.get_ordered_gates(), REG, record_steps=True, local_bits=m)
+        out = emu_run(prog, T=[1, 2, 3][n % 3], default_basis=basis_index(rec["initial"]))
+        assert np.max(np.abs(out["states"][0] - a[rec["tag"]])) < TOL, rec["tag"]
+        assert np.max(np.abs(out["snapshots"][0] - a[rec["tag"] + "_steps"])) < TOL, rec["tag"]
+        if gbits:
+            assert prog.n_remaps >= 0
+
+
+def test_sigma_dense_ops(golden):
+    j, a = golden
+    n = j["sigma"]["n"]
+    for i, t in enumerate(j["sigma"]["targets"]):
+        k = len(t)
+        u = a["sigma_mat"][i][:4 ** k].reshape(2 ** k, 2 ** k)
+        for m in (n, n - 2):
+            lw = Lowering(n)
+            lw.matrix(u, t)
+            out = emu_run(lw.finish(m), T=2, states=a["sigma_in"][i][None])
+            assert np.max(np.abs(out["states"][0] - a["sigma_out"][i])) < TOL, (t, m)
+
+
+def test_kron_string_observable(golden):
+    j, a = golden
+    rng = np.random.default_rng(3)
+    n = 7
+    psi = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+    psi /= np.linalg.norm(psi)
+    for label, targets in (("XYZX", [5, 0, 3, 1]), ("ZZYXI", [6, 2, 0, 4, 1])):
+        obs = np.array([[1]], dtype=complex)
+        for ch in label:
+            obs = np.kron(obs, O.gate_matrix(ch))
+        lw = Lowering(n)
+        lw.matrix(obs, targets)
+        out = emu_run(lw.finish(5), T=2, states=psi[None])
+        assert np.max(np.abs(out["states"][0] - O.apply_gate(psi, n, obs, targets))) < TOL
+    with pytest.raises(NotImplementedError):
+        lw = Lowering(n)
+        lw.matrix(a["bigk_0_mat"], [3, 0, 5, 1])
+
+
+@pytest.mark.parametrize("gbits", [0, 2])
+def test_noisy_trajectories_reference_draws(golden, gbits):
+    j, a = golden
+    for rec in j["noisy"]:
+        n = rec["n"]
+        m = n - gbits
+        if m < 3:
+            continue
+        g, noise = as_gates(rec["gates"]), as_noise(rec["noise"])
+        qc = make_circuit(n, g)
+        prog, _ = lower_circuit(n, qc.get_ordered_gates(), REG, channels_of_factory(noise),
+                                record_steps=True, local_bits=m)
+        assert prog.n_draws == O.draw_count(n, g, noise)
+        draws = np.random.default_rng(rec["noise_seed"]).random(max(prog.n_draws, 1))
+        out = emu_run(prog, T=2, uniforms=draws[None], want_branches=True)
+        _, _, branches, _ = O.run_state(n, g, None, noise, draws)
+        assert out["branches"][0][:len(branches)].tolist() == branches, rec["tag"]
+        assert np.max(np.abs(out["states"][0] - a[rec["tag"]])) < TOL, rec["tag"]
+        assert np.max(np.abs(out["snapshots"][0] - a[rec["tag"] + "_steps"])) < TOL, rec["tag"]
+
+
+def test_generic_kraus_matches_builtin_channels():
+    rng = np.random.default_rng(11)
+    n = 5
+    gates = layered_circuit(n, 4, 3)
+    noise = {"global": [("amplitude_damping", 0.3), ("depolarizing", 0.2)], "gate": {}}
+    qc = make_circuit(n, gates)
+
+    def generic(name):
+        return [("generic", p, O.kraus_ops(k, p)) for k, p in O.channels_for(noise, name)]
+
+    prog, _ = lower_circuit(n, qc.get_ordered_gates(), REG, generic, local_bits=4)
+    draws = rng.random((6, prog.n_draws))
+    out = emu_run(prog, count=6, T=2, uniforms=draws, want_branches=True)
+    for t in range(6):
+        psi, _, br, _ = O.run_state(n, gates, None, noise, draws[t])
+        assert out["branches"][t].tolist() == br
+        assert np.max(np.abs(out["states"][t] - psi)) < TOL
+
+
+def test_parameter_batch(golden):
+    n = 6
+    gates = layered_circuit(n, 5, 21)
+    qc = make_circuit(n, gates)
+    slots = O.param_slots(gates)
+    offs, off = {}, 0
+    for gi, g in enumerate(qc.gates):
+        k = O.NUM_PARAMS.get(g.gate_name, 0)
+        if k:
+            offs[id(g)] = off
+            off += k
+    assert off == len(slots)
+    prog, _ = lower_circuit(n, qc.get_ordered_gates(), REG, param_offsets=offs, local_bits=4)
+    vals = np.random.default_rng(5).uniform(-np.pi, np.pi, (5, off))
+    out = emu_run(prog, count=5, T=3, params=vals)
+    for t in range(5):
+        psi = O.run_state(n, O.bind_values(gates, vals[t]))[0]
+        assert np.max(np.abs(out["states"][t] - psi)) < TOL
+
+
+def test_philox_mode_matches_oracle_uniforms():
+    n = 5
+    gates = layered_circuit(n, 3, 8)
+    noise = {"global": [("depolarizing", 0.3), ("amplitude_damping", 0.4)], "gate": {}}
+    qc = make_circuit(n, gates)
+    prog, _ = lower_circuit(n, qc.get_ordered_gates(), REG, channels_of_factory(noise), local_bits=3)
+    out = emu_run(prog, count=4, T=2, seed=0xDEADBEEF12345, traj_offset=100, want_branches=True,
+                  accum_probs=True)
+    acc = np.zeros(2 ** n)
+    for t in range(4):
+        u = O.philox_uniforms(0xDEADBEEF12345, 100 + t, prog.n_draws)
+        psi, _, br, _ = O.run_state(n, gates, None, noise, u)
+        assert out["branches"][t].tolist() == br
+        assert np.max(np.abs(out["states"][t] - psi)) < TOL
+        acc += np.abs(psi) ** 2
+    assert np.max(np.abs(out["probs"] - acc)) < 1e-12
+
+
+def test_config3_trajectory_12q(golden):
+    j, a = golden
+    g, noise = layered_circuit(12, 16, 2026), config3_noise()
+    qc = make_circuit(12, g)
+    for m in (12, 10):
+        prog, _ = lower_circuit(12, qc.get_ordered_gates(), REG, channels_of_factory(noise), local_bits=m)
+        seed = j["cfg3_traj_seeds"][0]
+        draws = np.random.default_rng(seed).random(prog.n_draws)
+        out = emu_run(prog, T=2, uniforms=draws[None])
+        assert np.max(np.abs(out["states"][0] - a[f"cfg3_traj_{seed}"])) < TOL
+
+
+def test_layered16_cluster8(golden):
+    j, a = golden
+    g = layered_circuit(16, 64, 2026)
+    qc = make_circuit(16, g)
+    prog, _ = lower_circuit(16, qc.get_ordered_gates(), REG)
+    assert (prog.n, prog.m) == (16, 13)
+    out = emu_run(prog, T=1)
+    psi = out["states"][0]
+    assert np.max(np.abs(psi[a["layered16_idx"]] - a["layered16_amps"])) < TOL
+    assert int(np.argmax(np.abs(psi))) == j["layered16"]["argmax"]
