@@ -1,0 +1,346 @@
+"""ctypes binding of libqsb.so (include/qsb.h) over NumPy buffers.
+
+There is no CPU fallback: if the library is missing, or no CUDA device is visible, the first use
+raises RuntimeError.  Errors from the library map to ValueError (QSB_E_INVAL, the reference's own
+error class for bad arguments), NotImplementedError (QSB_E_UNSUPPORTED) or RuntimeError.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+from .compiler import OP_DTYPE, Program
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libqsb.so")
+
+RUN_LOAD, RUN_STORE, RUN_NORMALIZE, RUN_ASYNC, RUN_ACCUM_PROBS = 1, 2, 4, 8, 16
+
+SYMBOLS = [
+    "qsb_version", "qsb_device_count", "qsb_ctx_create", "qsb_ctx_destroy", "qsb_ctx_set_stream",
+    "qsb_ctx_sync", "qsb_last_error", "qsb_ctx_info", "qsb_timer_start", "qsb_timer_stop",
+    "qsb_launch_count", "qsb_buffer_alloc", "qsb_buffer_wrap", "qsb_buffer_free", "qsb_buffer_upload",
+    "qsb_buffer_download", "qsb_buffer_zero", "qsb_buffer_copy", "qsb_buffer_ptr", "qsb_buffer_bytes",
+    "qsb_host_alloc", "qsb_host_free", "qsb_program_create", "qsb_program_free", "qsb_run",
+    "qsb_probabilities", "qsb_probabilities_sum", "qsb_sample_index", "qsb_overlap",
+    "qsb_masked_parity", "qsb_rdm_all", "qsb_rho_accumulate", "qsb_readout_transform",
+]
+
+
+class RunArgs(C.Structure):
+    _fields_ = [
+        ("states", C.c_void_p), ("first", C.c_int64), ("count", C.c_int64),
+        ("params", C.c_void_p), ("params_stride", C.c_int64),
+        ("uniforms", C.c_void_p), ("uniforms_stride", C.c_int64),
+        ("philox_seed", C.c_uint64), ("traj_offset", C.c_int64),
+        ("init_basis", C.c_void_p), ("default_basis", C.c_int64),
+        ("branches", C.c_void_p), ("branches_stride", C.c_int64),
+        ("snapshots", C.c_void_p), ("probs_accum", C.c_void_p),
+        ("flags", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def load_library():
+    """dlopen libqsb.so and declare the prototypes.  Raises RuntimeError when it is not built."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python __graft_entry__.py build` "
+                "(nvcc, sm_100a).  This backend has no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        vp, i32, i64, u64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_double
+        P = C.POINTER
+        proto = {
+            "qsb_version": (C.c_int, []),
+            "qsb_device_count": (C.c_int, []),
+            "qsb_ctx_create": (C.c_int, [C.c_int, P(vp)]),
+            "qsb_ctx_destroy": (C.c_int, [vp]),
+            "qsb_ctx_set_stream": (C.c_int, [vp, vp]),
+            "qsb_ctx_sync": (C.c_int, [vp]),
+            "qsb_last_error": (C.c_char_p, [vp]),
+            "qsb_ctx_info": (C.c_int, [vp, P(i32), P(i32), P(i32), P(i64)]),
+            "qsb_timer_start": (C.c_int, [vp]),
+            "qsb_timer_stop": (C.c_int, [vp, P(C.c_float)]),
+            "qsb_launch_count": (i64, [vp]),
+            "qsb_buffer_alloc": (C.c_int, [vp, i64, P(vp)]),
+            "qsb_buffer_wrap": (C.c_int, [vp, vp, i64, P(vp)]),
+            "qsb_buffer_free": (C.c_int, [vp]),
+            "qsb_buffer_upload": (C.c_int, [vp, i64, vp, i64]),
+            "qsb_buffer_download": (C.c_int, [vp, i64, vp, i64]),
+            "qsb_buffer_zero": (C.c_int, [vp, i64, i64]),
+            "qsb_buffer_copy": (C.c_int, [vp, i64, vp, i64, i64]),
+            "qsb_buffer_ptr": (vp, [vp]),
+            "qsb_buffer_bytes": (i64, [vp]),
+            "qsb_host_alloc": (C.c_int, [i64, P(vp)]),
+            "qsb_host_free": (C.c_int, [vp]),
+            "qsb_program_create": (C.c_int, [vp, i32, i32, vp, i64, i64, i64, vp, i64, vp, i64, i32, i32, i32, P(vp)]),
+            "qsb_program_free": (C.c_int, [vp]),
+            "qsb_run": (C.c_int, [vp, P(RunArgs)]),
+            "qsb_probabilities": (C.c_int, [vp, i32, vp, i64, i64, vp, i64]),
+            "qsb_probabilities_sum": (C.c_int, [vp, i32, vp, i64, i64, vp]),
+            "qsb_sample_index": (C.c_int, [vp, i32, vp, i64, i64, vp, vp]),
+            "qsb_overlap": (C.c_int, [vp, i32, vp, i64, vp, i64, i64, i64, vp]),
+            "qsb_masked_parity": (C.c_int, [vp, i32, vp, i64, i64, vp, i32, vp]),
+            "qsb_rdm_all": (C.c_int, [vp, i32, vp, i64, i64, vp, vp]),
+            "qsb_rho_accumulate": (C.c_int, [vp, i32, vp, i64, i64, dbl, vp]),
+            "qsb_readout_transform": (C.c_int, [vp, i32, vp, i64, dbl, dbl]),
+        }
+        for name, (res, args) in proto.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return lib
+
+
+_ERR = {-1: ValueError, -5: NotImplementedError}
+
+
+def _check(rc, ctx_handle=None):
+    if rc == 0:
+        return
+    msg = load_library().qsb_last_error(ctx_handle)
+    msg = msg.decode() if msg else f"libqsb error {rc}"
+    raise _ERR.get(rc, RuntimeError)(msg)
+
+
+def _hostptr(arr):
+    return arr.ctypes.data_as(C.c_void_p)
+
+
+class Buffer:
+    """Device bytes owned by (or wrapped for) a Context."""
+
+    def __init__(self, ctx, handle, nbytes):
+        self.ctx, self.handle, self.nbytes = ctx, handle, nbytes
+
+    def upload(self, arr, offset=0):
+        arr = np.ascontiguousarray(arr)
+        _check(self.ctx.lib.qsb_buffer_upload(self.handle, offset, _hostptr(arr), arr.nbytes), self.ctx.handle)
+        return self
+
+    def download(self, dtype, shape, offset=0, out=None):
+        if out is None:
+            out = np.empty(shape, dtype=dtype)
+        _check(self.ctx.lib.qsb_buffer_download(self.handle, offset, _hostptr(out), out.nbytes), self.ctx.handle)
+        return out
+
+    def zero(self, offset=0, nbytes=None):
+        _check(self.ctx.lib.qsb_buffer_zero(self.handle, offset, self.nbytes - offset if nbytes is None else nbytes),
+               self.ctx.handle)
+        return self
+
+    def copy_from(self, src, nbytes, dst_off=0, src_off=0):
+        _check(self.ctx.lib.qsb_buffer_copy(self.handle, dst_off, src.handle, src_off, nbytes), self.ctx.handle)
+        return self
+
+    @property
+    def ptr(self):
+        return self.ctx.lib.qsb_buffer_ptr(self.handle)
+
+    def free(self):
+        if self.handle is not None:
+            self.ctx.lib.qsb_buffer_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class DeviceProgram:
+    def __init__(self, ctx, prog: Program):
+        self.ctx, self.prog = ctx, prog
+        ops = np.ascontiguousarray(prog.ops, dtype=OP_DTYPE)
+        cdata = np.ascontiguousarray(prog.cdata, dtype=np.float64)
+        idata = np.ascontiguousarray(prog.idata, dtype=np.int32)
+        n_ops = prog.ops_stride if prog.ops_stride else len(ops)
+        h = C.c_void_p()
+        _check(ctx.lib.qsb_program_create(ctx.handle, prog.n, prog.m, _hostptr(ops), n_ops, prog.ops_stride,
+                                          prog.n_programs, _hostptr(cdata), len(cdata), _hostptr(idata), len(idata),
+                                          prog.load_perm, prog.store_perm, prog.n_snapshots, C.byref(h)), ctx.handle)
+        self.handle = h
+
+    def free(self):
+        if self.handle is not None:
+            self.ctx.lib.qsb_program_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    """One CUDA device + stream.  Single-threaded by contract (use one per thread)."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        _check(self.lib.qsb_ctx_create(device, C.byref(h)))
+        self.handle = h
+        self.device = device
+        sm, ma, mi, mem = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int64()
+        _check(self.lib.qsb_ctx_info(h, C.byref(sm), C.byref(ma), C.byref(mi), C.byref(mem)), h)
+        self.sm_count, self.cc, self.total_mem = sm.value, (ma.value, mi.value), mem.value
+
+    # -- memory -------------------------------------------------------------------------
+    def alloc(self, nbytes):
+        h = C.c_void_p()
+        _check(self.lib.qsb_buffer_alloc(self.handle, int(nbytes), C.byref(h)), self.handle)
+        return Buffer(self, h, int(nbytes))
+
+    def wrap(self, device_ptr, nbytes):
+        h = C.c_void_p()
+        _check(self.lib.qsb_buffer_wrap(self.handle, C.c_void_p(device_ptr), int(nbytes), C.byref(h)), self.handle)
+        return Buffer(self, h, int(nbytes))
+
+    def to_device(self, arr):
+        arr = np.ascontiguousarray(arr)
+        return self.alloc(max(arr.nbytes, 16)).upload(arr)
+
+    def pinned(self, shape, dtype):
+        """NumPy array backed by pinned host memory (kept alive by the array's base object)."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        _check(self.lib.qsb_host_alloc(max(n, 16), C.byref(p)))
+        raw = (C.c_char * max(n, 16)).from_address(p.value)
+        arr = np.frombuffer(raw, dtype=dtype, count=int(np.prod(shape))).reshape(shape).view(PinnedArray)
+        arr._owner = _Pinned(self.lib, p)      # freed when the last view dies
+        return arr
+
+    # -- execution ------------------------------------------------------------------------
+    def program(self, prog: Program):
+        return DeviceProgram(self, prog)
+
+    def run(self, dprog, count, *, states=None, first=0, load=False, store=True, params=None, params_stride=0,
+            uniforms=None, uniforms_stride=0, seed=0, traj_offset=0, init_basis=None, default_basis=0,
+            branches=None, branches_stride=0, snapshots=None, probs_accum=None, async_=False, normalize=None):
+        a = RunArgs()
+        a.states = states.handle if states is not None else None
+        a.first, a.count = first, count
+        a.params = params.handle if params is not None else None
+        a.params_stride = params_stride
+        a.uniforms = uniforms.handle if uniforms is not None else None
+        a.uniforms_stride = uniforms_stride
+        a.philox_seed, a.traj_offset = seed & 0xFFFFFFFFFFFFFFFF, traj_offset
+        a.init_basis = init_basis.handle if init_basis is not None else None
+        a.default_basis = default_basis
+        a.branches = branches.handle if branches is not None else None
+        a.branches_stride = branches_stride
+        a.snapshots = snapshots.handle if snapshots is not None else None
+        a.probs_accum = probs_accum.handle if probs_accum is not None else None
+        norm = dprog.prog.normalize if normalize is None else normalize
+        a.flags = ((RUN_LOAD if load else 0) | (RUN_STORE if store and states is not None else 0) |
+                   (RUN_NORMALIZE if norm else 0) | (RUN_ASYNC if async_ else 0) |
+                   (RUN_ACCUM_PROBS if probs_accum is not None else 0))
+        _check(self.lib.qsb_run(dprog.handle, C.byref(a)), self.handle)
+
+    def sync(self):
+        _check(self.lib.qsb_ctx_sync(self.handle), self.handle)
+
+    def set_stream(self, cuda_stream_ptr):
+        _check(self.lib.qsb_ctx_set_stream(self.handle, C.c_void_p(cuda_stream_ptr)), self.handle)
+
+    def timer_start(self):
+        _check(self.lib.qsb_timer_start(self.handle), self.handle)
+
+    def timer_stop(self):
+        ms = C.c_float()
+        _check(self.lib.qsb_timer_stop(self.handle, C.byref(ms)), self.handle)
+        return ms.value
+
+    @property
+    def launches(self):
+        return int(self.lib.qsb_launch_count(self.handle))
+
+    # -- reductions -----------------------------------------------------------------------
+    def probabilities(self, n, states, first, count, out, out_first=0):
+        _check(self.lib.qsb_probabilities(self.handle, n, states.handle, first, count, out.handle, out_first), self.handle)
+
+    def probabilities_sum(self, n, states, first, count, out):
+        _check(self.lib.qsb_probabilities_sum(self.handle, n, states.handle, first, count, out.handle), self.handle)
+
+    def sample_index(self, n, states, first, count, uniforms, out):
+        _check(self.lib.qsb_sample_index(self.handle, n, states.handle, first, count, uniforms.handle, out.handle),
+               self.handle)
+
+    def overlap(self, n, a, a_first, b, b_first, b_stride, count, out):
+        _check(self.lib.qsb_overlap(self.handle, n, a.handle, a_first, b.handle, b_first, b_stride, count, out.handle),
+               self.handle)
+
+    def masked_parity(self, n, states, first, count, masks, out):
+        mk = np.ascontiguousarray(masks, dtype=np.uint64)
+        _check(self.lib.qsb_masked_parity(self.handle, n, states.handle, first, count, _hostptr(mk), len(mk),
+                                          out.handle), self.handle)
+
+    def rdm_all(self, n, states, first, count, rdm1, rdm2):
+        _check(self.lib.qsb_rdm_all(self.handle, n, states.handle, first, count,
+                                    rdm1.handle if rdm1 is not None else None,
+                                    rdm2.handle if rdm2 is not None else None), self.handle)
+
+    def rho_accumulate(self, n, states, first, count, scale, rho):
+        _check(self.lib.qsb_rho_accumulate(self.handle, n, states.handle, first, count, scale, rho.handle), self.handle)
+
+    def readout_transform(self, n, probs, count, p01, p10):
+        _check(self.lib.qsb_readout_transform(self.handle, n, probs.handle, count, p01, p10), self.handle)
+
+    def close(self):
+        if self.handle is not None:
+            self.lib.qsb_ctx_destroy(self.handle)
+            self.handle = None
+
+
+class _Pinned:
+    def __init__(self, lib, ptr):
+        self.lib, self.ptr = lib, ptr
+
+    def __del__(self):
+        try:
+            self.lib.qsb_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+class PinnedArray(np.ndarray):
+    """ndarray over cudaHostAlloc memory; views share `_owner`, which frees the block."""
+
+    def __array_finalize__(self, obj):
+        self._owner = getattr(obj, "_owner", None)
+
+
+_tls = threading.local()
+
+
+def default_device():
+    for key in ("QSB_DEVICE", "LOCAL_RANK"):
+        if os.environ.get(key, "") != "":
+            return int(os.environ[key])
+    return 0
+
+
+def get_context(device=None):
+    """Per-thread, per-device Context (the reference's engine is called from Qt worker threads,
+    controller/simulation_controller.py:228-256; a ctx is single-threaded by contract)."""
+    dev = default_device() if device is None else device
+    cache = getattr(_tls, "ctx", None)
+    if cache is None:
+        cache = _tls.ctx = {}
+    if dev not in cache:
+        cache[dev] = Context(dev)
+    return cache[dev]

@@ -1,7 +1,8 @@
-"""Executor + host compiler vs the oracle, on the test-only host emulator (CPU, no GPU).
+"""Executor + host compiler vs the oracle and the reference's golden vectors.
 
-Same `qsb_exec.cuh` op loop the CUDA kernel runs, same `qsb_op` programs; what this cannot see is
-the CUDA-only glue (DeviceEnv barriers/reductions, launch config, C ABI) -- that is tests/test_gpu_*."""
+Every case runs twice: `emu` = the test-only host emulator (CPU; same `qsb_exec.cuh` op loop, same
+`qsb_op` programs, OS threads instead of CUDA threads) and `gpu` = the real CUDA path through the
+C ABI of libqsb.so (marked gpu)."""
 
 import numpy as np
 import pytest
@@ -15,8 +16,16 @@ from qsb.workloads import layered_circuit, config3_noise
 from quantum_sim.engine.circuit import QuantumCircuit, GateInstance
 from quantum_sim.engine.gate_registry import GateRegistry
 
-TOL = 1e-12
+TOL = 1e-12     # complex128 amplitude tolerance of BASELINE.json's north_star
 REG = GateRegistry.instance()
+
+
+@pytest.fixture(params=["emu", pytest.param("gpu", marks=pytest.mark.gpu)])
+def run(request):
+    if request.param == "emu":
+        return emu_run
+    from gpu_util import gpu_run
+    return gpu_run
 
 
 def make_circuit(n, gates, initial=None):
@@ -40,7 +49,7 @@ def basis_index(initial):
 
 
 @pytest.mark.parametrize("gbits", [0, 1, 2, 3])
-def test_random_circuits_vs_oracle(golden, gbits):
+def test_random_circuits_vs_oracle(run, golden, gbits):
     j, a = golden
     for rec in j["random_circuits"]:
         n = rec["n"]
@@ -49,14 +58,14 @@ def test_random_circuits_vs_oracle(golden, gbits):
             continue
         qc = make_circuit(n, as_gates(rec["gates"]), rec["initial"])
         prog, _ = lower_circuit(n, qc.get_ordered_gates(), REG, record_steps=True, local_bits=m)
-        out = emu_run(prog, T=[1, 2, 3][n % 3], default_basis=basis_index(rec["initial"]))
+        out = run(prog, T=[1, 2, 3][n % 3], default_basis=basis_index(rec["initial"]))
         assert np.max(np.abs(out["states"][0] - a[rec["tag"]])) < TOL, rec["tag"]
         assert np.max(np.abs(out["snapshots"][0] - a[rec["tag"] + "_steps"])) < TOL, rec["tag"]
         if gbits:
             assert prog.n_remaps >= 0
 
 
-def test_sigma_dense_ops(golden):
+def test_sigma_dense_ops(run, golden):
     j, a = golden
     n = j["sigma"]["n"]
     for i, t in enumerate(j["sigma"]["targets"]):
@@ -65,11 +74,11 @@ def test_sigma_dense_ops(golden):
         for m in (n, n - 2):
             lw = Lowering(n)
             lw.matrix(u, t)
-            out = emu_run(lw.finish(m), T=2, states=a["sigma_in"][i][None])
+            out = run(lw.finish(m), T=2, states=a["sigma_in"][i][None])
             assert np.max(np.abs(out["states"][0] - a["sigma_out"][i])) < TOL, (t, m)
 
 
-def test_kron_string_observable(golden):
+def test_kron_string_observable(run, golden):
     j, a = golden
     rng = np.random.default_rng(3)
     n = 7
@@ -81,7 +90,7 @@ def test_kron_string_observable(golden):
             obs = np.kron(obs, O.gate_matrix(ch))
         lw = Lowering(n)
         lw.matrix(obs, targets)
-        out = emu_run(lw.finish(5), T=2, states=psi[None])
+        out = run(lw.finish(5), T=2, states=psi[None])
         assert np.max(np.abs(out["states"][0] - O.apply_gate(psi, n, obs, targets))) < TOL
     with pytest.raises(NotImplementedError):
         lw = Lowering(n)
@@ -89,7 +98,7 @@ def test_kron_string_observable(golden):
 
 
 @pytest.mark.parametrize("gbits", [0, 2])
-def test_noisy_trajectories_reference_draws(golden, gbits):
+def test_noisy_trajectories_reference_draws(run, golden, gbits):
     j, a = golden
     for rec in j["noisy"]:
         n = rec["n"]
@@ -102,14 +111,14 @@ def test_noisy_trajectories_reference_draws(golden, gbits):
                                 record_steps=True, local_bits=m)
         assert prog.n_draws == O.draw_count(n, g, noise)
         draws = np.random.default_rng(rec["noise_seed"]).random(max(prog.n_draws, 1))
-        out = emu_run(prog, T=2, uniforms=draws[None], want_branches=True)
+        out = run(prog, T=2, uniforms=draws[None], want_branches=True)
         _, _, branches, _ = O.run_state(n, g, None, noise, draws)
         assert out["branches"][0][:len(branches)].tolist() == branches, rec["tag"]
         assert np.max(np.abs(out["states"][0] - a[rec["tag"]])) < TOL, rec["tag"]
         assert np.max(np.abs(out["snapshots"][0] - a[rec["tag"] + "_steps"])) < TOL, rec["tag"]
 
 
-def test_generic_kraus_matches_builtin_channels():
+def test_generic_kraus_matches_builtin_channels(run):
     rng = np.random.default_rng(11)
     n = 5
     gates = layered_circuit(n, 4, 3)
@@ -121,14 +130,14 @@ def test_generic_kraus_matches_builtin_channels():
 
     prog, _ = lower_circuit(n, qc.get_ordered_gates(), REG, generic, local_bits=4)
     draws = rng.random((6, prog.n_draws))
-    out = emu_run(prog, count=6, T=2, uniforms=draws, want_branches=True)
+    out = run(prog, count=6, T=2, uniforms=draws, want_branches=True)
     for t in range(6):
         psi, _, br, _ = O.run_state(n, gates, None, noise, draws[t])
         assert out["branches"][t].tolist() == br
         assert np.max(np.abs(out["states"][t] - psi)) < TOL
 
 
-def test_parameter_batch(golden):
+def test_parameter_batch(run, golden):
     n = 6
     gates = layered_circuit(n, 5, 21)
     qc = make_circuit(n, gates)
@@ -142,19 +151,19 @@ def test_parameter_batch(golden):
     assert off == len(slots)
     prog, _ = lower_circuit(n, qc.get_ordered_gates(), REG, param_offsets=offs, local_bits=4)
     vals = np.random.default_rng(5).uniform(-np.pi, np.pi, (5, off))
-    out = emu_run(prog, count=5, T=3, params=vals)
+    out = run(prog, count=5, T=3, params=vals)
     for t in range(5):
         psi = O.run_state(n, O.bind_values(gates, vals[t]))[0]
         assert np.max(np.abs(out["states"][t] - psi)) < TOL
 
 
-def test_philox_mode_matches_oracle_uniforms():
+def test_philox_mode_matches_oracle_uniforms(run):
     n = 5
     gates = layered_circuit(n, 3, 8)
     noise = {"global": [("depolarizing", 0.3), ("amplitude_damping", 0.4)], "gate": {}}
     qc = make_circuit(n, gates)
     prog, _ = lower_circuit(n, qc.get_ordered_gates(), REG, channels_of_factory(noise), local_bits=3)
-    out = emu_run(prog, count=4, T=2, seed=0xDEADBEEF12345, traj_offset=100, want_branches=True,
+    out = run(prog, count=4, T=2, seed=0xDEADBEEF12345, traj_offset=100, want_branches=True,
                   accum_probs=True)
     acc = np.zeros(2 ** n)
     for t in range(4):
@@ -166,7 +175,7 @@ def test_philox_mode_matches_oracle_uniforms():
     assert np.max(np.abs(out["probs"] - acc)) < 1e-12
 
 
-def test_config3_trajectory_12q(golden):
+def test_config3_trajectory_12q(run, golden):
     j, a = golden
     g, noise = layered_circuit(12, 16, 2026), config3_noise()
     qc = make_circuit(12, g)
@@ -174,17 +183,17 @@ def test_config3_trajectory_12q(golden):
         prog, _ = lower_circuit(12, qc.get_ordered_gates(), REG, channels_of_factory(noise), local_bits=m)
         seed = j["cfg3_traj_seeds"][0]
         draws = np.random.default_rng(seed).random(prog.n_draws)
-        out = emu_run(prog, T=2, uniforms=draws[None])
+        out = run(prog, T=2, uniforms=draws[None])
         assert np.max(np.abs(out["states"][0] - a[f"cfg3_traj_{seed}"])) < TOL
 
 
-def test_layered16_cluster8(golden):
+def test_layered16_cluster8(run, golden):
     j, a = golden
     g = layered_circuit(16, 64, 2026)
     qc = make_circuit(16, g)
     prog, _ = lower_circuit(16, qc.get_ordered_gates(), REG)
     assert (prog.n, prog.m) == (16, 13)
-    out = emu_run(prog, T=1)
+    out = run(prog, T=1)
     psi = out["states"][0]
     assert np.max(np.abs(psi[a["layered16_idx"]] - a["layered16_amps"])) < TOL
     assert int(np.argmax(np.abs(psi))) == j["layered16"]["argmax"]

@@ -1,0 +1,149 @@
+"""Reduction kernels of libqsb.so (probabilities, sampling, overlaps, parities, RDMs, rho, readout)
+against the oracle, through the C ABI.  GPU only."""
+
+import numpy as np
+import pytest
+
+from oracle import qsim_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def rand_states(rng, count, n):
+    v = rng.normal(size=(count, 2 ** n)) + 1j * rng.normal(size=(count, 2 ** n))
+    return v / np.linalg.norm(v, axis=1, keepdims=True)
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from qsb import capi
+    return capi.get_context()
+
+
+@pytest.mark.parametrize("n", [1, 3, 8, 13, 16])
+def test_probabilities_and_sum(ctx, n):
+    rng = np.random.default_rng(n)
+    psi = rand_states(rng, 3, n)
+    s = ctx.to_device(psi)
+    out = ctx.alloc(3 * 2 ** n * 8)
+    ctx.probabilities(n, s, 0, 3, out)
+    p = out.download(np.float64, (3, 2 ** n))
+    assert np.max(np.abs(p - np.abs(psi) ** 2)) < 1e-15
+    acc = ctx.alloc(2 ** n * 8).zero()
+    ctx.probabilities_sum(n, s, 1, 2, acc)
+    assert np.max(np.abs(acc.download(np.float64, (2 ** n,)) - (np.abs(psi[1:]) ** 2).sum(0))) < 1e-14
+
+
+@pytest.mark.parametrize("n", [2, 5, 12, 16])
+def test_sample_index_matches_numpy_choice(ctx, n):
+    rng = np.random.default_rng(100 + n)
+    count = 64
+    psi = rand_states(rng, count, n)
+    psi[0, : 2 ** n // 2] = 0          # leading zero-probability block
+    psi[0] /= np.linalg.norm(psi[0])
+    psi[1] = 0
+    psi[1, 2 ** n - 1] = 1             # all mass on the last index
+    u = rng.random(count)
+    u[2] = 0.0
+    s, ub = ctx.to_device(psi), ctx.to_device(u)
+    out = ctx.alloc(count * 8)
+    ctx.sample_index(n, s, 0, count, ub, out)
+    got = out.download(np.int64, (count,))
+    want = [O.measure_all_index(psi[t], u[t]) for t in range(count)]
+    assert got.tolist() == want
+
+
+@pytest.mark.parametrize("n", [1, 4, 13, 16])
+def test_overlap(ctx, n):
+    rng = np.random.default_rng(200 + n)
+    a, b = rand_states(rng, 5, n), rand_states(rng, 5, n)
+    da, db = ctx.to_device(a), ctx.to_device(b)
+    out = ctx.alloc(5 * 16)
+    ctx.overlap(n, da, 0, db, 0, 1, 5, out)
+    got = out.download(np.complex128, (5,))
+    assert np.max(np.abs(got - np.array([np.vdot(a[t], b[t]) for t in range(5)]))) < 1e-13
+    ctx.overlap(n, da, 1, db, 2, 0, 3, out)           # broadcast one b
+    got = out.download(np.complex128, (5,))[:3]
+    assert np.max(np.abs(got - np.array([np.vdot(a[t], b[2]) for t in (1, 2, 3)]))) < 1e-13
+
+
+def test_masked_parity_steane_checks(ctx):
+    n = 13
+    rng = np.random.default_rng(300)
+    psi = rand_states(rng, 4, n)
+    checks = O.STEANE_CHECKS + [list(range(7))]
+    masks = [sum(1 << (n - 1 - q) for q in c) for c in checks]
+    s = ctx.to_device(psi)
+    out = ctx.alloc(4 * len(masks) * 16)
+    ctx.masked_parity(n, s, 0, 4, masks, out)
+    got = out.download(np.float64, (4, len(masks), 2))
+    for t in range(4):
+        for k, c in enumerate(checks):
+            e, o = O.z_parity_weights(psi[t], n, c)
+            assert abs(got[t, k, 0] - e) < 1e-13 and abs(got[t, k, 1] - o) < 1e-13
+
+
+@pytest.mark.parametrize("n", [2, 5, 12])
+def test_rdm_all_pairs(ctx, n):
+    rng = np.random.default_rng(400 + n)
+    psi = rand_states(rng, 2, n)
+    npairs = n * (n - 1) // 2
+    s = ctx.to_device(psi)
+    r1, r2 = ctx.alloc(2 * n * 4 * 16), ctx.alloc(2 * npairs * 16 * 16)
+    ctx.rdm_all(n, s, 0, 2, r1, r2)
+    g1 = r1.download(np.complex128, (2, n, 2, 2))
+    g2 = r2.download(np.complex128, (2, npairs, 4, 4))
+    for t in range(2):
+        for q in range(n):
+            assert np.max(np.abs(g1[t, q] - O.reduced_density_matrix_1q(psi[t], n, q))) < 1e-13
+        k = 0
+        for i in range(n):
+            for jj in range(i + 1, n):
+                assert np.max(np.abs(g2[t, k] - O.partial_trace(psi[t], n, [i, jj]))) < 1e-13
+                k += 1
+
+
+@pytest.mark.parametrize("n,count", [(3, 7), (6, 33), (8, 100)])
+def test_rho_accumulate(ctx, n, count):
+    rng = np.random.default_rng(500 + n)
+    psi = rand_states(rng, count, n)
+    s = ctx.to_device(psi)
+    rho = ctx.alloc(4 ** n * 16).zero()
+    ctx.rho_accumulate(n, s, 0, count, 1.0 / count, rho)
+    got = rho.download(np.complex128, (2 ** n, 2 ** n))
+    want = (psi.T @ psi.conj()) / count
+    assert np.max(np.abs(got - want)) < 1e-14
+
+
+@pytest.mark.parametrize("n", [1, 3, 8, 16])
+def test_readout_transform(ctx, n):
+    rng = np.random.default_rng(600 + n)
+    p = rng.random((2, 2 ** n))
+    p /= p.sum(1, keepdims=True)
+    buf = ctx.to_device(p)
+    ctx.readout_transform(n, buf, 2, 0.03, 0.11)
+    got = buf.download(np.float64, (2, 2 ** n))
+    for t in range(2):
+        assert np.max(np.abs(got[t] - O.readout_distribution(p[t], n, 0.03, 0.11))) < 1e-15
+
+
+def test_readout_golden(ctx, golden):
+    j, a = golden
+    buf = ctx.to_device(a["readout8_in"])
+    ctx.readout_transform(8, buf, 1, 0.03, 0.11)
+    assert np.max(np.abs(buf.download(np.float64, (256,)) - a["readout8_out"])) < 1e-15
+
+
+def test_argument_errors(ctx):
+    from qsb.compiler import Lowering
+    small = ctx.alloc(64)
+    with pytest.raises(ValueError):
+        ctx.probabilities(8, small, 0, 1, small)
+    with pytest.raises(ValueError):
+        ctx.readout_transform(2, small, 1, 1.5, 0.0)
+    lw = Lowering(3)
+    lw.gate("X", [0])
+    prog = lw.finish()
+    dp = ctx.program(prog)
+    with pytest.raises(ValueError):
+        ctx.run(dp, 4, states=small)           # states buffer too small
