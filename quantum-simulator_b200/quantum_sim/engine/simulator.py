@@ -1,0 +1,202 @@
+"""Simulator -- the reference's run entry points (simulator.py:28-199) as single device launches.
+
+`run`, `run_with_noise` and `ensemble_density_matrix` each lower the whole circuit (and the noise model)
+to one program and execute it for 1 / shots / n_trials states in one launch of the trajectory kernel;
+the per-gate Python loop of the reference disappears.  Random streams are the reference's: Kraus draws
+from `NoiseModel._rng` (one double per draw, gate-major / channel / target order), child seeds via
+`rng.integers(0, 2**63)`, `measure_all` via one `rng.random()` per shot.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Generator
+
+import numpy as np
+
+from qsb import runtime
+from qsb.lowering import lower_circuit
+from .circuit import QuantumCircuit, GateInstance
+from .gate_registry import GateRegistry
+from .gates import GateType
+from .measurement import MeasurementEngine, MeasurementBasis
+from .state_vector import StateVector
+
+_CHUNK_BYTES = 8 << 30          # state bytes resident per launch when batching shots / trials
+
+
+@dataclass
+class SimulationResult:
+    final_state: StateVector
+    measurement_counts: dict
+    step_states: list | None = None
+    num_shots: int = 1024
+    seed: int | None = None
+    reference_state: StateVector | None = None
+
+
+def _circuit_key(circuit):
+    return (circuit.num_qubits,
+            tuple((g.gate_name, tuple(g.target_qubits), tuple(float(p) for p in g.params), g.column)
+                  for g in circuit.gates))
+
+
+class Simulator:
+    """Executes a QuantumCircuit; optional NoiseModel applied after every gate."""
+
+    def __init__(self, noise_model=None):
+        self._gate_registry = GateRegistry.instance()
+        self._noise_model = noise_model
+
+    # ---- lowering ------------------------------------------------------------------------
+    def _program(self, circuit, record_steps=False, with_noise=True):
+        nm = self._noise_model if with_noise else None
+        n = circuit.num_qubits
+        layout = StateVector.layout
+        key = ("circuit", layout, _circuit_key(circuit), record_steps,
+               nm._signature() if nm is not None and hasattr(nm, "_signature") else None)
+        has_meas = [False]
+
+        def build():
+            channels = (lambda name: nm._channel_specs(name)) if nm is not None else None
+            prog, hm = lower_circuit(n, circuit.get_ordered_gates(), self._gate_registry, channels,
+                                     record_steps=record_steps, layout=layout)
+            prog.meta["has_measurement"] = hm
+            return prog
+
+        dp = runtime.cached_program(key, build)
+        return dp, dp.prog.meta["has_measurement"]
+
+    @staticmethod
+    def _basis(circuit) -> int:
+        return StateVector._basis_index(circuit.initial_states)
+
+    # ---- reference API ---------------------------------------------------------------------
+    def run(self, circuit: QuantumCircuit, shots: int = 1024, record_steps: bool = False,
+            seed: int | None = None, rng: np.random.Generator | None = None,
+            measurement_basis: MeasurementBasis = MeasurementBasis.Z) -> SimulationResult:
+        if rng is None:
+            rng = np.random.default_rng(seed)
+        n = circuit.num_qubits
+        if n != len(circuit.initial_states):
+            n = len(circuit.initial_states)       # from_initial_states sizes the register (simulator.py:53)
+        dp, has_meas = self._program(circuit, record_steps)
+        c = runtime.ctx()
+        dim = 2 ** n
+        state_buf = c.alloc(16 * dim)
+        kw = {}
+        if dp.prog.n_draws:
+            draws = self._noise_model._rng.random(dp.prog.n_draws)
+            kw.update(uniforms=c.to_device(draws), uniforms_stride=dp.prog.n_draws)
+        snaps = None
+        if dp.prog.n_snapshots:
+            snaps = c.alloc(dp.prog.n_snapshots * dim * 16)
+            kw.update(snapshots=snaps)
+        c.run(dp, 1, states=state_buf, default_basis=self._basis(circuit), **kw)
+        state = StateVector._from_device(n, state_buf)
+        step_states = None
+        if record_steps:
+            step_states = []
+            if snaps is not None:
+                host = snaps.download(np.complex128, (dp.prog.n_snapshots, dim))
+                step_states = [StateVector._from_host(n, host[i].copy()) for i in range(dp.prog.n_snapshots)]
+
+        if has_meas or shots > 0:
+            readout_err = getattr(self._noise_model, "readout_error", None) if self._noise_model is not None else None
+            counts = MeasurementEngine.sample_with_basis(state, shots, basis=measurement_basis,
+                                                         readout_error=readout_err, rng=rng)
+        else:
+            counts = {}
+        return SimulationResult(final_state=state, measurement_counts=counts, step_states=step_states,
+                                num_shots=shots, seed=seed)
+
+    def run_step_by_step(self, circuit: QuantumCircuit,
+                         rng: np.random.Generator | None = None) -> Generator:
+        """Yields (state, index) after each non-empty column, starting with (initial, -1)."""
+        yield StateVector.from_initial_states(circuit.initial_states), -1
+        n = circuit.num_qubits
+        dp, _ = self._program(circuit, record_steps=True)
+        if dp.prog.n_snapshots == 0:
+            return
+        c = runtime.ctx()
+        dim = 2 ** n
+        kw = {}
+        if dp.prog.n_draws:
+            kw.update(uniforms=c.to_device(self._noise_model._rng.random(dp.prog.n_draws)),
+                      uniforms_stride=dp.prog.n_draws)
+        snaps = c.alloc(dp.prog.n_snapshots * dim * 16)
+        c.run(dp, 1, default_basis=self._basis(circuit), snapshots=snaps, **kw)
+        host = snaps.download(np.complex128, (dp.prog.n_snapshots, dim))
+        for i in range(dp.prog.n_snapshots):
+            yield StateVector._from_host(n, host[i].copy()), i
+
+    def _apply_gate_instance(self, state: StateVector, gate: GateInstance):
+        gate_def = self._gate_registry.get(gate.gate_name)
+        state.apply_gate(gate_def.matrix_func(*gate.params), gate.target_qubits)
+
+    def _trajectory_batch(self, circuit, uniforms, count):
+        """Run `count` trajectories of `circuit` (+ noise) and return (ctx, device states buffer)."""
+        dp, _ = self._program(circuit)
+        c = runtime.ctx()
+        dim = 2 ** circuit.num_qubits
+        states = c.alloc(count * dim * 16)
+        kw = {}
+        if dp.prog.n_draws:
+            kw.update(uniforms=c.to_device(uniforms), uniforms_stride=dp.prog.n_draws)
+        c.run(dp, count, states=states, default_basis=self._basis(circuit), **kw)
+        return c, states
+
+    def run_with_noise(self, circuit: QuantumCircuit, shots: int = 1024, seed: int | None = None,
+                       rng: np.random.Generator | None = None) -> SimulationResult:
+        """`shots` independent noisy trajectories, one basis index each."""
+        if self._noise_model is None:
+            return self.run(circuit, shots, seed=seed, rng=rng)
+        if rng is None:
+            rng = np.random.default_rng(seed)
+        n = circuit.num_qubits
+        dim = 2 ** n
+        dp, _ = self._program(circuit)
+        d = dp.prog.n_draws
+        counts: dict = {}
+        chunk = max(1, min(shots, _CHUNK_BYTES // (16 * dim)))
+        c = runtime.ctx()
+        for lo in range(0, shots, chunk):
+            cnt = min(chunk, shots - lo)
+            # noise generator: d doubles per shot, never reseeded; measurement generator: one per shot
+            uniforms = self._noise_model._rng.random(cnt * d).reshape(cnt, d) if d else None
+            _, states = self._trajectory_batch(circuit, uniforms, cnt)
+            u = c.to_device(rng.random(cnt))
+            out = c.alloc(cnt * 8)
+            c.sample_index(n, states, 0, cnt, u, out)
+            for i in out.download(np.int64, (cnt,)).tolist():
+                key = format(i, f"0{n}b")
+                counts[key] = counts.get(key, 0) + 1
+        final_state = StateVector.from_initial_states(circuit.initial_states)   # placeholder, as in the reference
+        return SimulationResult(final_state=final_state, measurement_counts=counts, num_shots=shots, seed=seed)
+
+    def ensemble_density_matrix(self, circuit: QuantumCircuit, n_trials: int = 50,
+                                seed: int | None = None) -> np.ndarray:
+        """rho = (1/N) sum_i |psi_i><psi_i| over N stochastic trajectories with per-trial child seeds."""
+        rng = np.random.default_rng(seed)
+        n = circuit.num_qubits
+        dim = 2 ** n
+        dp, _ = self._program(circuit)
+        d = dp.prog.n_draws
+        c = runtime.ctx()
+        rho = c.alloc(16 * dim * dim).zero()
+        seeds = [int(rng.integers(0, 2 ** 63)) for _ in range(n_trials)]     # drawn even without noise
+        chunk = max(1, min(n_trials, _CHUNK_BYTES // (16 * dim)))
+        for lo in range(0, n_trials, chunk):
+            cnt = min(chunk, n_trials - lo)
+            uniforms = None
+            if d:
+                uniforms = np.empty((cnt, d), dtype=np.float64)
+                for i in range(cnt):
+                    uniforms[i] = np.random.default_rng(seeds[lo + i]).random(d)
+            _, states = self._trajectory_batch(circuit, uniforms, cnt)
+            c.rho_accumulate(n, states, 0, cnt, 1.0 / n_trials, rho)
+        if self._noise_model is not None and n_trials > 0:
+            self._noise_model.set_seed(seeds[-1])      # the reference leaves the model seeded with the last child seed
+            if d:
+                self._noise_model._rng.random(d)
+        return rho.download(np.complex128, (dim, dim))
