@@ -488,6 +488,7 @@ int qsb_run(qsb_program* p, const qsb_run_args* r) {
   a.n_ops = p->n_ops;
   a.ops_stride = p->ops_stride;
   a.cdata = p->d_cdata;
+  a.n_cdata = p->n_cdata;
   a.idata = p->d_idata;
   a.n = p->n;
   a.m = p->m;

@@ -10,37 +10,35 @@
 namespace cg = cooperative_groups;
 
 #define QSB_TRAJ_THREADS 512
-#define QSB_SMEM_EXTRA (512 * 4 + 16 * 4 * 8 + 2 * 4 * 8)   // perm table + warp partials + cluster partials
+#define QSB_SMEM_EXTRA (sizeof(qsb_ctl) + 16 * 4 * 8 + 2 * 4 * 8)   // control block + warp partials + cluster partials
+
+// the one dynamic shared-memory block of the trajectory kernel: [tile | qsb_ctl | reduction scratch]
+extern __shared__ __align__(16) unsigned char qsb_smem[];
 
 template <int C>
 struct DeviceEnv {
-  int tid, T, rank;
-  c128* tile_;
-  uint32_t* perm_;
-  double* wpart_;
-  double* cl_;
+  int tid, T, rank, m_;
   int parity;
 
-  __device__ DeviceEnv(unsigned char* smem, int m) {
+  __device__ DeviceEnv(int m) {
     tid = threadIdx.x;
     T = blockDim.x;
     rank = (C > 1) ? (int)cg::this_cluster().block_rank() : 0;
-    tile_ = reinterpret_cast<c128*>(smem);
-    unsigned char* p = smem + ((size_t)16 << m);
-    perm_ = reinterpret_cast<uint32_t*>(p);
-    wpart_ = reinterpret_cast<double*>(p + 2048);
-    cl_ = reinterpret_cast<double*>(p + 2048 + 512);
+    m_ = m;
     parity = 0;
   }
-  __device__ __forceinline__ c128* tile() { return tile_; }
-  __device__ __forceinline__ uint32_t* perm_table() { return perm_; }
+  // pointers are re-derived from the shared symbol at every use so that loads/stores stay LDS/STS
+  __device__ __forceinline__ c128* tile() { return reinterpret_cast<c128*>(qsb_smem); }
+  __device__ __forceinline__ qsb_ctl* ctl() { return reinterpret_cast<qsb_ctl*>(qsb_smem + ((size_t)16 << m_)); }
+  __device__ __forceinline__ double* wpart() { return reinterpret_cast<double*>(qsb_smem + ((size_t)16 << m_) + sizeof(qsb_ctl)); }
+  __device__ __forceinline__ double* clred() { return wpart() + 64; }
   __device__ __forceinline__ void sync_block() { __syncthreads(); }
   __device__ __forceinline__ void sync_cluster() {
     if (C > 1) cg::this_cluster().sync(); else __syncthreads();
   }
   __device__ __forceinline__ const c128* peer_tile(int r) {
-    if (C > 1) return cg::this_cluster().map_shared_rank(tile_, r);
-    return tile_;
+    if (C > 1) return cg::this_cluster().map_shared_rank(tile(), r);
+    return tile();
   }
   __device__ __forceinline__ void atomic_add(double* p, double v) { atomicAdd(p, v); }
 
@@ -51,22 +49,22 @@ struct DeviceEnv {
     for (int k = 0; k < nv; ++k) {
       double x = v[k];
       for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
-      if (lane == 0) wpart_[warp * 4 + k] = x;
+      if (lane == 0) wpart()[warp * 4 + k] = x;
     }
     __syncthreads();
     for (int k = 0; k < nv; ++k) {
       double s = 0.0;
-      for (int w = 0; w < nw; ++w) s += wpart_[w * 4 + k];
+      for (int w = 0; w < nw; ++w) s += wpart()[w * 4 + k];
       v[k] = s;
     }
     if (C > 1) {
       cg::cluster_group cl = cg::this_cluster();
       if (tid == 0)
-        for (int k = 0; k < nv; ++k) cl_[parity * 4 + k] = v[k];
+        for (int k = 0; k < nv; ++k) clred()[parity * 4 + k] = v[k];
       cl.sync();
       for (int k = 0; k < nv; ++k) {
         double s = 0.0;
-        for (int r = 0; r < C; ++r) s += cl.map_shared_rank(cl_, r)[parity * 4 + k];
+        for (int r = 0; r < C; ++r) s += cl.map_shared_rank(clred(), r)[parity * 4 + k];
         v[k] = s;
       }
       parity ^= 1;   // the buffer of reduction k is rewritten at k+2, after everyone passed barrier k+1
@@ -76,8 +74,7 @@ struct DeviceEnv {
 
 template <int C>
 __global__ void __launch_bounds__(QSB_TRAJ_THREADS, 1) qsb_traj_kernel(const __grid_constant__ qsb_exec_args a) {
-  extern __shared__ __align__(16) unsigned char qsb_smem[];
-  DeviceEnv<C> env(qsb_smem, a.m);
+  DeviceEnv<C> env(a.m);
   const int64_t cluster_id = blockIdx.x / C, n_clusters = gridDim.x / C;
   for (int64_t t = cluster_id; t < a.count; t += n_clusters) qsb_exec_trajectory(env, a, t);
   if (C > 1) cg::this_cluster().sync();   // no CTA may exit while a peer can still read its shared memory

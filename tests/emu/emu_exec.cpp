@@ -17,7 +17,7 @@
 struct Shared {
   int C, T, m;
   std::vector<std::vector<c128>> tiles;
-  std::vector<std::vector<uint32_t>> perm;
+  std::vector<qsb_ctl> ctls;
   std::vector<std::unique_ptr<std::barrier<>>> block_bar;
   std::unique_ptr<std::barrier<>> cluster_bar;
   std::vector<double> red;   // [C*T][4]
@@ -28,7 +28,7 @@ struct HostEnv {
   int tid, T, rank;
   Shared* sh;
   c128* tile() { return sh->tiles[rank].data(); }
-  uint32_t* perm_table() { return sh->perm[rank].data(); }
+  qsb_ctl* ctl() { return &sh->ctls[rank]; }
   void sync_block() { sh->block_bar[rank]->arrive_and_wait(); }
   void sync_cluster() { sh->cluster_bar->arrive_and_wait(); }
   const c128* peer_tile(int r) { return sh->tiles[r].data(); }
@@ -46,7 +46,7 @@ struct HostEnv {
   }
 };
 
-extern "C" int emu_run(int n, int m, int T, const qsb_op* ops, int64_t n_ops, int64_t ops_stride, const double* cdata,
+extern "C" int emu_run(int n, int m, int T, const qsb_op* ops, int64_t n_ops, int64_t ops_stride, const double* cdata, int64_t n_cdata,
                        const int32_t* idata, int load_perm, int store_perm, int n_snapshots, int flags, void* states,
                        int64_t count, const double* params, int64_t params_stride, const double* uniforms,
                        int64_t uniforms_stride, uint64_t seed, int64_t traj_offset, const int64_t* init_basis,
@@ -58,14 +58,14 @@ extern "C" int emu_run(int n, int m, int T, const qsb_op* ops, int64_t n_ops, in
   sh.T = T;
   sh.m = m;
   sh.tiles.assign(sh.C, std::vector<c128>((size_t)1 << m));
-  sh.perm.assign(sh.C, std::vector<uint32_t>(512));
+  sh.ctls.resize(sh.C);
   for (int r = 0; r < sh.C; ++r) sh.block_bar.emplace_back(new std::barrier<>(T));
   sh.cluster_bar.reset(new std::barrier<>(sh.C * T));
   sh.red.assign((size_t)sh.C * T * 4, 0.0);
 
   qsb_exec_args a;
   memset(&a, 0, sizeof a);
-  a.ops = ops; a.n_ops = n_ops; a.ops_stride = ops_stride; a.cdata = cdata; a.idata = idata;
+  a.ops = ops; a.n_ops = n_ops; a.ops_stride = ops_stride; a.cdata = cdata; a.n_cdata = n_cdata; a.idata = idata;
   a.n = n; a.m = m; a.load_perm = load_perm; a.store_perm = store_perm; a.n_snapshots = n_snapshots;
   a.flags = flags; a.states = (c128*)states; a.count = count;
   a.params = params; a.params_stride = params_stride;
