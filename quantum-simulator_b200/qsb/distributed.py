@@ -1,0 +1,86 @@
+"""Sharding of independent units (trajectories, parameter sets, sweep points) over ranks.
+
+One process per GPU, launched by torchrun; `torch.distributed` is only plumbing.  The path has no
+exchange step: every rank runs a contiguous slice of the units on its own device and the results meet in
+ONE collective at the end (sum of rho / histograms, or a gather of per-shot indices).  Random streams are
+positioned, not replayed: PCG64 `advance(k)` jumps a generator over the doubles earlier ranks consume, so
+a sharded run draws exactly what the reference's single loop draws (simulator.py:134-145, :175-182).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_bounds(n_items: int, world: int, rank: int):
+    """Contiguous [lo, hi) of `n_items` for `rank`; the first n_items % world ranks get one more."""
+    base, extra = divmod(n_items, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def positioned_rng(seed_or_rng, skip_doubles: int):
+    """Generator whose next `random()` is draw number `skip_doubles` of the given stream.
+
+    Accepts a seed (fresh default_rng) or a Generator (copied, the caller's is not advanced)."""
+    if isinstance(seed_or_rng, np.random.Generator):
+        bg = type(seed_or_rng.bit_generator)()
+        bg.state = seed_or_rng.bit_generator.state
+    else:
+        bg = np.random.default_rng(seed_or_rng).bit_generator
+    if skip_doubles:
+        bg.advance(int(skip_doubles))          # one 64-bit output per random() double
+    return np.random.Generator(bg)
+
+
+def child_seeds(seed, n: int):
+    """The sequential child-seed chain `int(rng.integers(0, 2**63))` (simulator.py:180, qec.py:585);
+    every rank computes the whole chain (it is tiny) and slices it."""
+    rng = np.random.default_rng(seed)
+    return [int(rng.integers(0, 2 ** 63)) for _ in range(n)]
+
+
+def world_info():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(), dist.get_rank()
+    return 1, 0
+
+
+def allreduce_sum_(tensor):
+    """In-place sum over ranks (NCCL on device tensors, gloo on CPU tensors); no-op for one rank."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(tensor)
+    return tensor
+
+
+def gather_concat(array: np.ndarray, device=None):
+    """Concatenate equal-dtype 1-D arrays of all ranks in rank order (lengths may differ by one)."""
+    import torch
+    import torch.distributed as dist
+    world, rank = world_info()
+    if world == 1:
+        return array
+    t = torch.from_numpy(np.ascontiguousarray(array))
+    if device is not None:
+        t = t.to(device)
+    sizes = torch.zeros(world, dtype=torch.int64, device=t.device)
+    sizes[rank] = t.numel()
+    dist.all_reduce(sizes)
+    cap = int(sizes.max().item())
+    pad = torch.zeros(cap, dtype=t.dtype, device=t.device)
+    pad[: t.numel()] = t
+    out = [torch.zeros_like(pad) for _ in range(world)]
+    dist.all_gather(out, pad)
+    return np.concatenate([o[: int(sizes[r].item())].cpu().numpy() for r, o in enumerate(out)])
+
+
+def merge_counts_in_shot_order(indices: np.ndarray, n: int) -> dict:
+    """{bitstring: count} with keys inserted in order of first occurrence, as the reference's per-shot
+    loop builds them (simulator.py:144-145)."""
+    out: dict = {}
+    for i in indices.tolist():
+        key = format(i, f"0{n}b")
+        out[key] = out.get(key, 0) + 1
+    return out

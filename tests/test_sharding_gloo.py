@@ -1,0 +1,90 @@
+"""Host-side sharding logic on CPU: world_size-2 gloo processes reproduce the single-process streams,
+child seeds and count merge.  The per-shot work is done by the oracle here (the GPU path is covered by
+tests/test_gpu_*); what is under test is the partitioning / RNG positioning / collectives."""
+
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import qsim_oracle as O
+from qsb import distributed as D
+from qsb.workloads import ghz
+
+
+def test_shard_bounds_cover_everything():
+    for n in (0, 1, 7, 500, 4096):
+        for world in (1, 2, 3, 8):
+            spans = [D.shard_bounds(n, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def test_positioned_rng_equals_sequential_stream():
+    full = np.random.default_rng(99).random(1000)
+    for skip in (0, 1, 333, 999):
+        assert np.array_equal(D.positioned_rng(99, skip).random(1000 - skip), full[skip:])
+    g = np.random.default_rng(5)
+    g.random(10)
+    want = np.random.default_rng(5).random(40)[10:]
+    assert np.array_equal(D.positioned_rng(g, 7).random(23), want[7:])
+    assert np.array_equal(g.random(30), want)          # the caller's generator was not advanced
+
+
+def test_child_seeds_match_reference_chain():
+    assert D.child_seeds(42, 5) == O.trial_seeds(42, 5)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, shots, out_q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n, gates = 3, ghz(3)
+    noise = {"global": [("depolarizing", 0.1)], "gate": {}}
+    d = O.draw_count(n, gates, noise)
+    lo, hi = D.shard_bounds(shots, world, rank)
+    nrng = D.positioned_rng(7, lo * d)          # noise generator: d doubles per shot
+    mrng = D.positioned_rng(42, lo)             # measurement generator: one double per shot
+    idx = np.empty(hi - lo, dtype=np.int64)
+    hist = torch.zeros(2 ** n, dtype=torch.float64)
+    for i in range(hi - lo):
+        psi = O.run_state(n, gates, None, noise, nrng.random(d))[0]
+        idx[i] = O.measure_all_index(psi, mrng.random())
+        hist += torch.from_numpy(np.abs(psi) ** 2)
+    D.allreduce_sum_(hist)
+    allidx = D.gather_concat(idx)
+    if rank == 0:
+        out_q.put((D.merge_counts_in_shot_order(allidx, n), hist.numpy().copy()))
+    dist.destroy_process_group()
+
+
+def test_world2_gloo_matches_single_process(golden):
+    j, _ = golden
+    shots = 200
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, shots, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    counts, hist = q.get()
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    # same counts, same insertion order as the reference's single loop (golden from the real reference)
+    assert counts == j["ghz3"]["run_with_noise"]
+    assert list(counts) == list(j["ghz3"]["run_with_noise"])
+    assert abs(hist.sum() - shots) < 1e-9
