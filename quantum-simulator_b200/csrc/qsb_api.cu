@@ -20,6 +20,8 @@ struct qsb_ctx {
   int64_t launches;
   std::string err;
   uint64_t* d_masks;      // scratch for qsb_masked_parity
+  unsigned long long* d_prof;   // cycle counters of the last qsb_run (qsb_debug_profile), or NULL
+  int prof_ctas;
 };
 
 struct qsb_buffer {
@@ -40,6 +42,7 @@ struct qsb_program {
   int64_t n_idata, n_cdata;
   int32_t max_param, max_draw;   // highest parameter / draw index any op touches (argument checks)
   bool has_param;
+  int32_t tile_bits;             // > 0: streaming mode (one CTA per 2^m-amplitude tile of a state in HBM)
 };
 
 static thread_local std::string g_err;
@@ -98,6 +101,8 @@ int qsb_ctx_create(int device, qsb_ctx** out) {
   c->total_mem = prop.totalGlobalMem;
   c->launches = 0;
   c->d_masks = nullptr;
+  c->d_prof = nullptr;
+  c->prof_ctas = 0;
   cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
@@ -118,6 +123,7 @@ int qsb_ctx_destroy(qsb_ctx* ctx) {
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   cudaFree(ctx->d_masks);
+  cudaFree(ctx->d_prof);
   delete ctx;
   return QSB_OK;
 }
@@ -278,11 +284,16 @@ int qsb_program_create(qsb_ctx* ctx, int32_t n, int32_t m, const qsb_op* ops, in
   if (!ctx || !out) return fail(ctx, QSB_E_INVAL, "qsb_program_create: NULL argument");
   *out = nullptr;
   if (n < 1) return fail(ctx, QSB_E_INVAL, "num_qubits must be >= 1, got %d", n);
-  if (n > QSB_MAX_QUBITS)
-    return fail(ctx, QSB_E_UNSUPPORTED, "resident executor holds n <= %d qubits, got %d", QSB_MAX_QUBITS, n);
-  if (m < 1 || m > n || m > QSB_MAX_LOCAL_BITS || n - m > 3)
-    return fail(ctx, QSB_E_INVAL, "local_bits %d invalid for n = %d (need n-3 <= m <= min(n, %d))", m, n,
+  if (n > 30)
+    return fail(ctx, QSB_E_UNSUPPORTED, "executor holds n <= 30 qubits per device, got %d", n);
+  if (m < 1 || m > n || m > QSB_MAX_LOCAL_BITS)
+    return fail(ctx, QSB_E_INVAL, "local_bits %d invalid for n = %d (need 1 <= m <= min(n, %d))", m, n,
                 QSB_MAX_LOCAL_BITS);
+  // n - m <= 3 and n <= 16: the state is resident in a cluster of 2^(n-m) CTAs; otherwise it is streamed
+  // through shared memory tile by tile (one pass over HBM per program)
+  const bool streaming = (n - m > 3) || n > QSB_MAX_QUBITS;
+  if (streaming && n_snapshots > 0)
+    return fail(ctx, QSB_E_UNSUPPORTED, "snapshots are not available in streaming mode (n - local_bits > 3)");
   if (n_ops < 0 || (n_ops > 0 && !ops) || n_programs < 1 || (ops_stride != 0 && ops_stride < n_ops))
     return fail(ctx, QSB_E_INVAL, "bad op list");
   if (n_idata < 0 || load_perm < 0 || store_perm < 0 || load_perm + n > n_idata || store_perm + n > n_idata)
@@ -292,10 +303,14 @@ int qsb_program_create(qsb_ctx* ctx, int32_t n, int32_t m, const qsb_op* ops, in
   const int64_t total_ops = ops_stride ? ops_stride * n_programs : n_ops;
   int32_t max_param = -1, max_draw = -1;
   bool has_param = false;
-  const int gbits = n - m;
+  const int gbits = streaming ? 0 : n - m;
   for (int64_t i = 0; i < total_ops; ++i) {
     const qsb_op& o = ops[i];
     int nb = 0, need = 0;
+    if (streaming && (o.kind == QSB_OP_KRAUS_AD || o.kind == QSB_OP_KRAUS_GEN || o.kind == QSB_OP_REMAP ||
+                      o.kind == QSB_OP_SNAPSHOT))
+      return fail(ctx, QSB_E_UNSUPPORTED, "op %lld: kind %d needs the whole state resident (streaming mode)",
+                  (long long)i, o.kind);
     switch (o.kind) {
       case QSB_OP_NOP: break;
       case QSB_OP_U1: nb = 1; need = 8; break;
@@ -327,8 +342,12 @@ int qsb_program_create(qsb_ctx* ctx, int32_t n, int32_t m, const qsb_op* ops, in
     }
     const int bits[3] = {o.b0, o.b1, o.b2};
     if (o.kind != QSB_OP_REMAP && o.kind != QSB_OP_SNAPSHOT) {
+      // 1-qubit gates and Pauli / amplitude-damping draws only touch the pending matrix of their slot, which
+      // may be a cluster-rank slot; everything that sweeps the tile needs local slots
+      const bool deferred = nb == 1 && o.kind != QSB_OP_KRAUS_GEN;
+      const int limit = deferred ? m + gbits : m;
       for (int k = 0; k < nb; ++k) {
-        if (bits[k] < 0 || bits[k] >= m)
+        if (bits[k] < 0 || bits[k] >= limit)
           return fail(ctx, QSB_E_INVAL, "op %lld: target bit %d not resident (local_bits = %d)", (long long)i, bits[k], m);
         for (int l = 0; l < k; ++l)
           if (bits[l] == bits[k]) return fail(ctx, QSB_E_INVAL, "op %lld: repeated target bit", (long long)i);
@@ -365,6 +384,7 @@ int qsb_program_create(qsb_ctx* ctx, int32_t n, int32_t m, const qsb_op* ops, in
   p->max_param = max_param;
   p->max_draw = max_draw;
   p->has_param = has_param;
+  p->tile_bits = streaming ? n - m : 0;
   p->d_ops = nullptr;
   p->d_cdata = nullptr;
   p->d_idata = nullptr;
@@ -435,7 +455,8 @@ static cudaError_t launch_traj(qsb_ctx* ctx, const qsb_exec_args& a, int threads
     if (per_sm < 1) return cudaErrorLaunchOutOfResources;
     max_units = (int64_t)per_sm * ctx->sm_count;
   }
-  int64_t units = a.count < max_units ? a.count : max_units;
+  const int64_t total_units = a.count << a.tile_bits;
+  int64_t units = total_units < max_units ? total_units : max_units;
   cfg.gridDim = dim3((unsigned)(units * C), 1, 1);
   *grid_out = (int)(units * C);
   return cudaLaunchKernelEx(&cfg, kern, a);
@@ -511,11 +532,21 @@ int qsb_run(qsb_program* p, const qsb_run_args* r) {
   a.snapshots = (p->n_snapshots > 0 && r->snapshots) ? (c128*)r->snapshots->ptr : nullptr;
   a.probs_accum = (r->flags & QSB_RUN_ACCUM_PROBS) ? (double*)r->probs_accum->ptr : nullptr;
 
+  a.prof = ctx->d_prof;
+  a.tile_bits = p->tile_bits;
+  if (p->tile_bits) {
+    if (r->flags & QSB_RUN_NORMALIZE)
+      return fail(ctx, QSB_E_UNSUPPORTED, "qsb_run: normalisation needs the whole state resident (streaming mode)");
+    if ((r->flags & QSB_RUN_ACCUM_PROBS) || a.branches)
+      return fail(ctx, QSB_E_UNSUPPORTED, "qsb_run: probs_accum / branches are not available in streaming mode");
+  }
+
   CU(ctx, cudaSetDevice(ctx->device));
-  const int C = 1 << (p->n - p->m);
-  int threads = 1 << (p->m > 4 ? p->m - 4 : 1);       // 16 amplitudes per thread per pass
-  if (threads < 32) threads = 32;
-  if (threads > QSB_TRAJ_THREADS) threads = QSB_TRAJ_THREADS;
+  const int C = p->tile_bits ? 1 : 1 << (p->n - p->m);
+  int workers = 1 << (p->m > 4 ? p->m - 4 : 1);       // 16 amplitudes per worker per pass
+  if (workers < 32) workers = 32;
+  if (workers > QSB_MAX_WORKERS) workers = QSB_MAX_WORKERS;
+  const int threads = workers + QSB_CTL_THREADS;
   const size_t smem = ((size_t)16 << p->m) + QSB_SMEM_EXTRA;
   int grid = 0;
   cudaError_t e;
@@ -532,8 +563,33 @@ int qsb_run(qsb_program* p, const qsb_run_args* r) {
                 cudaGetErrorString(e));
   }
   ctx->launches += 1;
+  ctx->prof_ctas = grid;
   if (!(r->flags & QSB_RUN_ASYNC)) CU(ctx, cudaStreamSynchronize(ctx->stream));
   return QSB_OK;
+}
+
+// Developer aid: enable (enable != 0) per-CTA cycle counters for subsequent qsb_run calls, and/or read the
+// counters of the last run: out[cta][32] = {worker wait, busy per descriptor kind [8], count per kind [8],
+// control ring-full wait, control total, descriptors}.  Returns the number of CTAs of the last run.
+int qsb_debug_profile(qsb_ctx* ctx, int enable, unsigned long long* out, int64_t max_ctas) {
+  if (!ctx) return fail(nullptr, QSB_E_INVAL, "ctx is NULL");
+  CU(ctx, cudaSetDevice(ctx->device));
+  const int64_t cap = 8 * 148 * 4;
+  if (enable && !ctx->d_prof) {
+    CU(ctx, cudaMalloc(&ctx->d_prof, cap * 32 * sizeof(unsigned long long)));
+    CU(ctx, cudaMemset(ctx->d_prof, 0, cap * 32 * sizeof(unsigned long long)));
+  }
+  int n = 0;
+  if (out && ctx->d_prof) {
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    n = ctx->prof_ctas < max_ctas ? ctx->prof_ctas : (int)max_ctas;
+    CU(ctx, cudaMemcpy(out, ctx->d_prof, (size_t)n * 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  }
+  if (!enable && ctx->d_prof) {
+    cudaFree(ctx->d_prof);
+    ctx->d_prof = nullptr;
+  }
+  return n;
 }
 
 // ---- reductions ------------------------------------------------------------------------

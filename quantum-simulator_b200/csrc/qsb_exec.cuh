@@ -1,20 +1,30 @@
-// qsb_exec.cuh -- the resident-trajectory executor.
+// qsb_exec.cuh -- the resident-tile executor (trajectories for n <= 16, streamed tiles above).
 //
 // One CTA cluster (1, 2, 4 or 8 CTAs) keeps one 2^n statevector in shared memory
 // (2^m amplitudes per CTA, n - m cluster-rank bits) for a whole trajectory: gates,
 // Kraus steps, snapshots and the final store, so a 16-qubit trajectory touches HBM
-// only for its op list, its uniforms and its final state.
+// only for its op list, its uniforms and its final state.  For n > 16 the same code
+// runs one CTA per 2^m-amplitude tile of a state that lives in HBM ("streaming"
+// mode: the high index bits select the tile instead of the cluster rank).
 //
-// Runtime 1-qubit fusion: every 1-qubit operation (gate, Pauli branch, amplitude-damping
-// K0/K1, generic Kraus operator) is multiplied into a pending 2x2 matrix of its slot bit
-// by one thread; the state is only swept when a multi-qubit gate, a cluster remap, a
-// state-dependent Kraus draw or a store needs the affected bits, and that sweep applies the
-// pending matrices of its bits and the gate in one pass over shared memory.
+// Warp specialisation.  Each CTA has W worker threads and one control warp:
+//   * the CONTROL warp walks the op list.  Every 1-qubit operation (gate, Pauli
+//     branch, amplitude-damping K0/K1, generic Kraus operator) is only multiplied
+//     into a pending 2x2 matrix of its slot bit -- no amplitude is touched.  When a
+//     multi-qubit gate, a state-dependent Kraus draw, a cluster remap or a store needs
+//     the data, the control warp publishes a DESCRIPTOR (what to sweep, the pending
+//     matrices to apply on the way, their structure class) into a small ring in
+//     shared memory and runs ahead;
+//   * the WORKERS consume descriptors: one pass over the tile applies the pending
+//     matrices of the touched bits plus the gate.
+// Every CTA of a cluster runs an identical control warp on the same ops and the same
+// uniforms, so all copies take the same decisions without communication.
 //
-// The op loop is written once against an `Env` (thread id, barriers, all-reduce, peer tile):
-//   * DeviceEnv  (qsb_kernels.cuh) -- CUDA: __syncthreads / cluster.sync / DSMEM
-//   * HostEnv    (tests/emu)       -- test-only: a few OS threads + std::barrier, used
-//                                     to check index math and the host compiler on CPU.
+// The code is written once against an `Env` (thread identity, barriers, ring hand-off,
+// peer tiles):
+//   * DeviceEnv  (qsb_kernels.cuh) -- CUDA: named barriers, barrier.cluster, DSMEM
+//   * HostEnv    (tests/emu)       -- test-only: OS threads + std::barrier, used to
+//                                     check protocol, index math and host compiler on CPU.
 //
 // Reference semantics implemented here (file:line in the reference tree):
 //   StateVector.apply_gate      state_vector.py:41-74   (textbook action; the axis
@@ -30,32 +40,38 @@
 
 #if defined(__CUDACC__)
 #define QSB_HD __host__ __device__ __forceinline__
-#define QSB_PASS __device__ __noinline__      // whole-tile sweeps: own register allocation, called from the op loop
+#define QSB_PASS __device__ __forceinline__   // whole-tile sweeps: inlined into the worker loop (an ABI call would leave them ~48 registers)
+#define QSB_CTL __device__ __noinline__       // control-warp helpers: called from many ops, keep one copy
 typedef double2 c128;
 #else
 #define QSB_HD inline
 #define QSB_PASS inline
+#define QSB_CTL inline
 struct alignas(16) c128 { double x, y; };
 #endif
 
-#define QSB_MAX_QUBITS 16
+#define QSB_MAX_QUBITS 16          // resident (cluster) mode
+#define QSB_MAX_STREAM_QUBITS 32   // streaming mode (index arithmetic is 32-bit)
 #define QSB_MAX_LOCAL_BITS 13
 #define QSB_AD_MARGIN 1e-10
 #define QSB_CHUNK 128          // ops staged in shared memory per refill
-#define QSB_REMAP_REGS 8       // amplitudes a thread stages per remap round
+#define QSB_REMAP_REGS 16      // amplitudes a thread stages per remap / rank-bit flush round
+#define QSB_RING 4             // descriptors in flight between control warp and workers
 
 struct qsb_exec_args {
   const qsb_op* ops;
   int64_t n_ops;
-  int64_t ops_stride;     // 0: all trajectories share ops[0..n_ops)
+  int64_t ops_stride;     // 0: all units share ops[0..n_ops)
   const double* cdata;
   int64_t n_cdata;
   const int32_t* idata;
   int32_t n, m;
   int32_t load_perm, store_perm, n_snapshots;
   int32_t flags;
+  int32_t tile_bits;      // streaming mode: n - m index bits select the tile (0 in resident mode)
+  int32_t pad0;
   c128* states;           // already offset to `first`
-  int64_t count;
+  int64_t count;          // resident: trajectories; streaming: states (each 2^tile_bits tiles)
   const double* params;   int64_t params_stride;
   const double* uniforms; int64_t uniforms_stride;
   uint64_t seed;          int64_t traj_offset;
@@ -63,17 +79,50 @@ struct qsb_exec_args {
   int32_t* branches;      int64_t branches_stride;
   c128* snapshots;
   double* probs_accum;
+  unsigned long long* prof;   // optional cycle counters, 32 per CTA (qsb_debug_profile), or NULL
+};
+
+// ---- descriptors: control warp -> workers ---------------------------------------------
+enum { QSB_D_EXIT = 0, QSB_D_INIT, QSB_D_SWEEP, QSB_D_REMAP, QSB_D_GFLUSH, QSB_D_RDM1, QSB_D_STORE };
+// structure class of a pending 2x2: none | diag(1, real s) | diag(d0, d1) | dense
+enum { QSB_CLS_NONE = 0, QSB_CLS_RDIAG = 1, QSB_CLS_DIAG = 2, QSB_CLS_DENSE = 3 };
+// gate applied inside a sweep after the pending matrices of its bits
+enum { QSB_G_NONE = 0, QSB_G_CX, QSB_G_CZ, QSB_G_SWAP, QSB_G_CCX, QSB_G_CSWAP, QSB_G_DENSE };
+
+struct alignas(16) qsb_desc {
+  int32_t kind, gate, k, flags;
+  int32_t b[4];            // slot bits, b[0] = MSB of the gate's matrix index
+  int32_t cls[4];          // class of the pending matrix of b[k]
+  int64_t unit;            // INIT: unit index (trajectory; streaming: state * tiles + tile)
+  int64_t basis;           // INIT: reference-order basis index
+  const int32_t* perm;     // INIT / STORE: n-entry bit permutation (slot bit -> reference-order bit)
+  c128* gptr;              // INIT: source state (LOAD) ; STORE: destination (or NULL)
+  double* probs;           // STORE: |psi|^2 accumulation target (or NULL)
+  int64_t tile;            // INIT / STORE: value of the non-resident index bits (cluster rank or tile id)
+  c128 P[3][4];            // pending matrices (row-major), valid where cls != NONE
+  c128 mat[64];            // dense 4x4 / 8x8 gate of this sweep
+};
+
+// decoded op: what the serial part of the control warp does with it
+enum { QSB_DEC_SKIP = 0, QSB_DEC_MUL = 1, QSB_DEC_SLOW = 2 };
+struct alignas(16) qsb_dec {
+  int32_t type;            // SKIP | MUL: pend[b] <- U pend[b] | SLOW: needs the descriptor ring / the state
+  int32_t b;               // slot bit
+  int32_t ucls;            // structure class of U
+  int32_t pad;
+  c128 U[4];
 };
 
 // per-CTA control block that lives behind the tile in shared memory
 struct qsb_ctl {
-  uint32_t perm[512];          // bit-permutation tables (load / store / snapshot)
-  c128 pend[16][4];            // pending 2x2 per slot bit (row-major), valid where the mask bit is set
-  c128 mat[64];                // dense 4x4 / 8x8 gate staged for the current pass
+  uint32_t perm[1024];         // bit-permutation byte tables (workers: INIT / STORE)
+  c128 pend[32][4];            // pending 2x2 per slot bit (row-major); written by the control warp only
+  qsb_desc ring[QSB_RING];
   qsb_op ops[QSB_CHUNK];       // staged op records ...
   double u[QSB_CHUNK];         // ... the uniform each Kraus op consumes
-  double prm[QSB_CHUNK][3];    // ... the angles each parameterised gate reads
-  double cd[QSB_CHUNK][8];     // ... and the first 8 doubles of each op's cdata
+  qsb_dec dec[QSB_CHUNK];      // ... and their decoded form (control warp, lane-parallel decode)
+  double wpart[32 * 4];        // per-warp partial sums (workers)
+  double red[2][4];            // this CTA's contribution to a cluster reduction, double-buffered
 };
 
 // ---- small helpers ---------------------------------------------------------------
@@ -136,46 +185,24 @@ QSB_HD int qsb_choice(const double* p, int k, double u) {
   return idx < k ? idx : k - 1;
 }
 
-// ---- pending 2x2 matrices (one writer: thread 0 of each CTA; every CTA of the cluster keeps an
-//      identical copy because all of them walk the same ops with the same uniforms) -----------
-// P <- U P, or P <- U when the bit had nothing pending
-QSB_HD void qsb_pend_mul(c128* P, bool has, c128 u00, c128 u01, c128 u10, c128 u11) {
-  if (!has) { P[0] = u00; P[1] = u01; P[2] = u10; P[3] = u11; return; }
-  c128 p00 = P[0], p01 = P[1], p10 = P[2], p11 = P[3];
-  P[0] = qsb_fma(u01, p10, qsb_mul(u00, p00));
-  P[1] = qsb_fma(u01, p11, qsb_mul(u00, p01));
-  P[2] = qsb_fma(u11, p10, qsb_mul(u10, p00));
-  P[3] = qsb_fma(u11, p11, qsb_mul(u10, p01));
-}
-QSB_HD void qsb_pend_diag(c128* P, bool has, c128 d0, c128 d1) {
-  if (!has) { P[0] = d0; P[1] = qsb_c(0, 0); P[2] = qsb_c(0, 0); P[3] = d1; return; }
-  P[0] = qsb_mul(d0, P[0]); P[1] = qsb_mul(d0, P[1]);
-  P[2] = qsb_mul(d1, P[2]); P[3] = qsb_mul(d1, P[3]);
-}
-// Pauli code 1 = X, 2 = Y, 3 = Z (gates.py:39-46)
-QSB_HD void qsb_pend_pauli(c128* P, bool has, int code) {
-  if (!has) { P[0] = qsb_c(1, 0); P[1] = qsb_c(0, 0); P[2] = qsb_c(0, 0); P[3] = qsb_c(1, 0); }
-  c128 p00 = P[0], p01 = P[1], p10 = P[2], p11 = P[3];
-  if (code == 1) { P[0] = p10; P[1] = p11; P[2] = p00; P[3] = p01; }
-  else if (code == 2) {           // Y = [[0,-i],[i,0]]: row0' = -i row1, row1' = i row0
-    P[0] = qsb_c(p10.y, -p10.x); P[1] = qsb_c(p11.y, -p11.x);
-    P[2] = qsb_c(-p00.y, p00.x); P[3] = qsb_c(-p01.y, p01.x);
-  } else { P[2] = qsb_neg(p10); P[3] = qsb_neg(p11); }
+// bit-permutation byte tables: index x (<= 32 bits) -> OR_j bit_j(x) << perm[j]
+QSB_HD uint32_t qsb_permute(const uint32_t* tab, uint32_t x) {
+  return tab[x & 255] | tab[256 + ((x >> 8) & 255)] | tab[512 + ((x >> 16) & 255)] | tab[768 + (x >> 24)];
 }
 
-// gate applied inside a fused pass after the pending matrices of its bits
-enum { QSB_G_NONE = 0, QSB_G_CX, QSB_G_CZ, QSB_G_SWAP, QSB_G_CCX, QSB_G_CSWAP, QSB_G_DENSE };
+// =========================================================================================
+//                                      WORKER SIDE
+// =========================================================================================
 
-// One sweep over the tile for K slot bits (bits[0] = MSB of the local index r): apply the pending 2x2 of
-// every bit in `pmask` (bit k of pmask <-> bits[k]), then gate G.  Each thread owns whole 2^K groups.
+// One sweep over the tile for K slot bits (d->b[0] = MSB of the local index r): apply the pending 2x2 of
+// every bit whose class is not NONE, then gate G.  Each worker owns whole 2^K groups.
 template <int K, int G, class Env>
-QSB_PASS void qsb_pass_fused(Env& env, int m, const int* bits, int pmask) {
+QSB_PASS void qsb_sweep(Env& env, int m, const qsb_desc* d) {
   c128* tile = env.tile();          // re-derived here so device code keeps the shared address space (LDS/STS)
-  const qsb_ctl* ctl = env.ctl();
   constexpr int D = 1 << K;
-  int sb[K];
+  int bits[K], sb[K], cls[K];
 #pragma unroll
-  for (int k = 0; k < K; ++k) sb[k] = bits[k];
+  for (int k = 0; k < K; ++k) { bits[k] = d->b[k]; sb[k] = bits[k]; cls[k] = d->cls[k]; }
   qsb_sort_bits<K>(sb);
   int off[D];
 #pragma unroll
@@ -185,15 +212,15 @@ QSB_PASS void qsb_pass_fused(Env& env, int m, const int* bits, int pmask) {
     for (int k = 0; k < K; ++k) if ((r >> (K - 1 - k)) & 1) o |= 1 << bits[k];
     off[r] = o;
   }
-  c128 P[K][4];
+  c128 P[K][4];                     // always a valid matrix (identity where nothing is pending)
 #pragma unroll
-  for (int k = 0; k < K; ++k)
-    if ((pmask >> k) & 1) {
+  for (int k = 0; k < K; ++k) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) P[k][e] = ctl->pend[bits[k]][e];
-    }
+    for (int e = 0; e < 4; ++e) P[k][e] = d->P[k][e];
+  }
   const int cnt = 1 << (m - K);
-  for (int g = env.tid; g < cnt; g += env.T) {
+#pragma unroll 2
+  for (int g = env.wid; g < cnt; g += env.W) {
     int base = g;
 #pragma unroll
     for (int k = 0; k < K; ++k) base = qsb_ins0(base, sb[k]);
@@ -202,14 +229,22 @@ QSB_PASS void qsb_pass_fused(Env& env, int m, const int* bits, int pmask) {
     for (int r = 0; r < D; ++r) a[r] = tile[qsb_slot(base | off[r])];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      if (!((pmask >> k) & 1)) continue;
       const int bit = 1 << (K - 1 - k);
+      if (cls[k] == QSB_CLS_DENSE) {
 #pragma unroll
-      for (int r = 0; r < D; ++r) {
-        if (r & bit) continue;
-        c128 lo = a[r], hi = a[r | bit];
-        a[r] = qsb_fma(P[k][1], hi, qsb_mul(P[k][0], lo));
-        a[r | bit] = qsb_fma(P[k][3], hi, qsb_mul(P[k][2], lo));
+        for (int r = 0; r < D; ++r) {
+          if (r & bit) continue;
+          c128 lo = a[r], hi = a[r | bit];
+          a[r] = qsb_fma(P[k][1], hi, qsb_mul(P[k][0], lo));
+          a[r | bit] = qsb_fma(P[k][3], hi, qsb_mul(P[k][2], lo));
+        }
+      } else if (cls[k] == QSB_CLS_DIAG) {
+#pragma unroll
+        for (int r = 0; r < D; ++r) a[r] = qsb_mul((r & bit) ? P[k][3] : P[k][0], a[r]);
+      } else if (cls[k] == QSB_CLS_RDIAG) {
+        const double s = P[k][3].x;
+#pragma unroll
+        for (int r = 0; r < D; ++r) if (r & bit) { a[r].x *= s; a[r].y *= s; }
       }
     }
     if (G == QSB_G_DENSE) {
@@ -217,14 +252,14 @@ QSB_PASS void qsb_pass_fused(Env& env, int m, const int* bits, int pmask) {
       // its inputs are already in registers
 #pragma unroll
       for (int r = 0; r < D; ++r) {
-        c128 acc = qsb_mul(ctl->mat[r * D], a[0]);
+        c128 acc = qsb_mul(d->mat[r * D], a[0]);
 #pragma unroll
-        for (int c = 1; c < D; ++c) acc = qsb_fma(ctl->mat[r * D + c], a[c], acc);
+        for (int c = 1; c < D; ++c) acc = qsb_fma(d->mat[r * D + c], a[c], acc);
         tile[qsb_slot(base | off[r])] = acc;
       }
       continue;
     }
-    if (G == QSB_G_CX) { c128 t = a[2]; a[2] = a[3]; a[3] = t; }                  // bits[0] control, bits[1] target
+    if (G == QSB_G_CX) { c128 t = a[2]; a[2] = a[3]; a[3] = t; }                  // b[0] control, b[1] target
     else if (G == QSB_G_CZ) { a[3] = qsb_neg(a[3]); }
     else if (G == QSB_G_SWAP) { c128 t = a[1]; a[1] = a[2]; a[2] = t; }
     else if (G == QSB_G_CCX) { c128 t = a[D - 2]; a[D - 2] = a[D - 1]; a[D - 1] = t; }   // 110 <-> 111
@@ -234,36 +269,55 @@ QSB_PASS void qsb_pass_fused(Env& env, int m, const int* bits, int pmask) {
   }
 }
 
-// apply and clear every pending matrix in `which` (slot-bit mask), three bits per sweep.  Collective.
 template <class Env>
-QSB_PASS void qsb_flush(Env& env, int m, uint32_t& mask, uint32_t which) {
-  uint32_t todo = mask & which;
-  if (!todo) return;
-  env.sync_block();                       // thread 0's pending updates are visible, previous sweep done
-  while (todo) {
-    int bits[3], nb = 0;
-    while (todo && nb < 3) {
-      int b = 15;
-      while (!((todo >> b) & 1u)) --b;
-      bits[nb++] = b;
-      todo &= ~(1u << b);
-    }
-    if (nb == 3) qsb_pass_fused<3, QSB_G_NONE>(env, m, bits, 7);
-    else if (nb == 2) qsb_pass_fused<2, QSB_G_NONE>(env, m, bits, 3);
-    else qsb_pass_fused<1, QSB_G_NONE>(env, m, bits, 1);
-    env.sync_block();
+QSB_HD void qsb_do_sweep(Env& env, int m, const qsb_desc* d) {
+  switch (d->k * 8 + d->gate) {
+    case 1 * 8 + QSB_G_NONE:  qsb_sweep<1, QSB_G_NONE>(env, m, d); break;
+    case 2 * 8 + QSB_G_NONE:  qsb_sweep<2, QSB_G_NONE>(env, m, d); break;
+    case 3 * 8 + QSB_G_NONE:  qsb_sweep<3, QSB_G_NONE>(env, m, d); break;
+    case 2 * 8 + QSB_G_CX:    qsb_sweep<2, QSB_G_CX>(env, m, d); break;
+    case 2 * 8 + QSB_G_CZ:    qsb_sweep<2, QSB_G_CZ>(env, m, d); break;
+    case 2 * 8 + QSB_G_SWAP:  qsb_sweep<2, QSB_G_SWAP>(env, m, d); break;
+    case 2 * 8 + QSB_G_DENSE: qsb_sweep<2, QSB_G_DENSE>(env, m, d); break;
+    case 3 * 8 + QSB_G_CCX:   qsb_sweep<3, QSB_G_CCX>(env, m, d); break;
+    case 3 * 8 + QSB_G_CSWAP: qsb_sweep<3, QSB_G_CSWAP>(env, m, d); break;
+    case 3 * 8 + QSB_G_DENSE: qsb_sweep<3, QSB_G_DENSE>(env, m, d); break;
+    default: break;
   }
-  mask &= ~which;
 }
 
-// partial sums for the 1-qubit reduced density matrix of bit b (unnormalised):
-// v[0] = sum |a0|^2, v[1] = sum |a1|^2, v[2] + i v[3] = sum a0 conj(a1)
+// sum v[0..nv) over the workers of this CTA; every worker gets the bit-identical result
+template <class Env>
+QSB_HD void qsb_block_reduce(Env& env, double* v, int nv) {
+  double* wp = env.ctl()->wpart;
+  env.sync_workers();                         // previous users of wpart are done
+  for (int k = 0; k < nv; ++k) {
+    double x = env.warp_sum(v[k]);
+    if (env.lane == 0) wp[env.warp * 4 + k] = x;
+  }
+  env.sync_workers();
+  for (int k = 0; k < nv; ++k) {
+    double s = 0.0;
+    for (int w = 0; w < env.nwarps; ++w) s += wp[w * 4 + k];
+    v[k] = s;
+  }
+}
+
+// partial sums for the 1-qubit reduced density matrix of slot bit b (unnormalised), this CTA's share:
+// v[0] = sum |a0|^2, v[1] = sum |a1|^2, v[2] + i v[3] = sum a0 conj(a1).  b >= m is a cluster-rank bit:
+// the whole tile belongs to one side (off-diagonal terms are not available there and are not requested).
 template <class Env>
 QSB_PASS void qsb_partial_rdm1(Env& env, int m, int b, double v[4]) {
   const c128* tile = env.tile();
   v[0] = v[1] = v[2] = v[3] = 0.0;
+  if (b >= m) {
+    double s = 0.0;
+    for (int i = env.wid; i < (1 << m); i += env.W) s += qsb_norm2(tile[i]);
+    v[(env.rank >> (b - m)) & 1] = s;
+    return;
+  }
   const int cnt = 1 << (m - 1);
-  for (int g = env.tid; g < cnt; g += env.T) {
+  for (int g = env.wid; g < cnt; g += env.W) {
     int i0 = qsb_ins0(g, b);
     c128 a0 = tile[qsb_slot(i0)], a1 = tile[qsb_slot(i0 | (1 << b))];
     v[0] += qsb_norm2(a0);
@@ -274,299 +328,603 @@ QSB_PASS void qsb_partial_rdm1(Env& env, int m, int b, double v[4]) {
 }
 
 template <class Env>
-QSB_PASS double qsb_norm2_all(Env& env, int m) {
-  const c128* tile = env.tile();
-  double v[4] = {0.0, 0.0, 0.0, 0.0};
-  for (int i = env.tid; i < (1 << m); i += env.T) v[0] += qsb_norm2(tile[i]);   // slot order irrelevant
-  env.allreduce(v, 1);
-  return v[0];
-}
-
-// bit-permutation tables: index x (n <= 16 bits) -> sum_j bit_j(x) << perm[j]
-template <class Env>
-QSB_HD void qsb_build_perm(Env& env, qsb_ctl* ctl, const int32_t* perm, int n) {
-  for (int v = env.tid; v < 512; v += env.T) {
-    int lo = v & 255, hi = v >> 8;       // hi = 0: table for bits 0..7, hi = 1: bits 8..15
+QSB_HD void qsb_build_perm(Env& env, const int32_t* perm, int n) {
+  uint32_t* tab = env.ctl()->perm;
+  for (int v = env.wid; v < 1024; v += env.W) {
+    const int lo = v & 255, byte = v >> 8;
     uint32_t r = 0;
     for (int j = 0; j < 8; ++j) {
-      int bit = hi * 8 + j;
+      const int bit = byte * 8 + j;
       if (bit < n && ((lo >> j) & 1)) r |= 1u << perm[bit];
     }
-    ctl->perm[v] = r;
+    tab[v] = r;
   }
-  env.sync_block();
+  env.sync_workers();
 }
-QSB_HD uint32_t qsb_permute(const uint32_t* tab, uint32_t x) { return tab[x & 255] | tab[256 + (x >> 8)]; }
 
-// write the tile (scaled) to out[perm(x)], x = rank << m | i
 template <class Env>
-QSB_PASS void qsb_store_state(Env& env, const qsb_exec_args& a, const int32_t* perm,
-                            double scale, c128* out, double* probs_accum) {
-  const c128* tile = env.tile();
-  qsb_ctl* ctl = env.ctl();
-  qsb_build_perm(env, ctl, perm, a.n);
+QSB_PASS void qsb_do_init(Env& env, const qsb_exec_args& a, const qsb_desc* d) {
+  c128* tile = env.tile();
+  const uint32_t* tab = env.ctl()->perm;
   const int m = a.m;
-  for (int i = env.tid; i < (1 << m); i += env.T) {
-    uint32_t dst = qsb_permute(ctl->perm, ((uint32_t)env.rank << m) | (uint32_t)i);
+  qsb_build_perm(env, d->perm, a.n);
+  const uint32_t hi = (uint32_t)d->tile << m;
+  const bool hoist = (env.W & 31) == 0 && m >= 5;      // the low 5 index bits are then local and equal to the lane
+  const uint32_t lo = hoist ? qsb_permute(tab, (uint32_t)env.wid & 31u) : 0u;
+  if (d->flags & QSB_RUN_LOAD) {
+    const c128* src = d->gptr;
+    for (int i = env.wid; i < (1 << m); i += env.W) {
+      const uint32_t x = hi | (uint32_t)i;
+      const uint32_t s = hoist ? (qsb_permute(tab, x & ~31u) | lo) : qsb_permute(tab, x);
+      tile[qsb_slot(i)] = src[s];
+    }
+  } else {
+    const uint32_t basis = (uint32_t)d->basis;
+    for (int i = env.wid; i < (1 << m); i += env.W) {
+      const uint32_t x = hi | (uint32_t)i;
+      const uint32_t s = hoist ? (qsb_permute(tab, x & ~31u) | lo) : qsb_permute(tab, x);
+      tile[qsb_slot(i)] = qsb_c(s == basis ? 1.0 : 0.0, 0.0);
+    }
+  }
+}
+
+// write the tile (normalised when asked) to gptr[perm(x)], x = tile << m | i
+template <class Env>
+QSB_PASS void qsb_do_store(Env& env, const qsb_exec_args& a, const qsb_desc* d, int& parity) {
+  const c128* tile = env.tile();
+  const uint32_t* tab = env.ctl()->perm;
+  const int m = a.m;
+  double scale = 1.0;
+  if (d->flags & QSB_RUN_NORMALIZE) {
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int i = env.wid; i < (1 << m); i += env.W) v[0] += qsb_norm2(tile[i]);   // slot order irrelevant
+    qsb_block_reduce(env, v, 1);
+    if (env.C > 1) {
+      if (env.wid == 0) env.ctl()->red[parity][0] = v[0];
+      env.cluster_sync_w();
+      double s = 0.0;
+      for (int r = 0; r < env.C; ++r) s += env.peer_ctl(r)->red[parity][0];
+      v[0] = s;
+    }
+    parity ^= 1;
+    if (v[0] > 1e-30) scale = 1.0 / sqrt(v[0]);
+  }
+  qsb_build_perm(env, d->perm, a.n);
+  const uint32_t hi = (uint32_t)d->tile << m;
+  const bool hoist = (env.W & 31) == 0 && m >= 5;      // the low 5 index bits are then local and equal to the lane
+  const uint32_t lo = hoist ? qsb_permute(tab, (uint32_t)env.wid & 31u) : 0u;
+  c128* out = d->gptr;
+  double* probs = d->probs;
+  for (int i = env.wid; i < (1 << m); i += env.W) {
+    const uint32_t x = hi | (uint32_t)i;
+    const uint32_t dst = hoist ? (qsb_permute(tab, x & ~31u) | lo) : qsb_permute(tab, x);
     c128 v = tile[qsb_slot(i)];
     v.x *= scale; v.y *= scale;
     if (out) out[dst] = v;
-    if (probs_accum) env.atomic_add(probs_accum + dst, qsb_norm2(v));
+    if (probs) env.atomic_add(probs + dst, qsb_norm2(v));
   }
-  env.sync_block();
 }
 
-// ---- one trajectory ------------------------------------------------------------------
+// swap cluster-rank bit gb with local slot bit lb: pull the partner's half, then overwrite ours.
+// Pending matrices travel with their qubits (control-warp bookkeeping), so nothing is flushed here.
 template <class Env>
-QSB_HD void qsb_exec_trajectory(Env& env, const qsb_exec_args& a, int64_t t) {
-  const int m = a.m, n = a.n;
+QSB_PASS void qsb_do_remap(Env& env, int m, const qsb_desc* d) {
   c128* tile = env.tile();
+  const int gb = d->b[0], lb = d->b[1];
+  const int mybit = (env.rank >> gb) & 1;
+  const c128* peer = env.peer_tile(env.rank ^ (1 << gb));
+  c128 val[QSB_REMAP_REGS];
+  const int cnt = 1 << (m - 1);
+  env.cluster_sync_w();                       // every CTA finished the sweeps before the exchange
+  // Round r pulls the partner's groups g and then overwrites OUR groups g (the ones the partner pulls
+  // in the same round), so one cluster barrier between the two halves of a round is enough.
+  for (int base = 0; base < cnt; base += QSB_REMAP_REGS * env.W) {
+#pragma unroll
+    for (int e = 0; e < QSB_REMAP_REGS; ++e) {
+      int g = base + e * env.W + env.wid;
+      if (g < cnt) val[e] = peer[qsb_slot(qsb_ins0(g, lb) | (mybit << lb))];
+    }
+    env.cluster_sync_w();
+#pragma unroll
+    for (int e = 0; e < QSB_REMAP_REGS; ++e) {
+      int g = base + e * env.W + env.wid;
+      if (g < cnt) tile[qsb_slot(qsb_ins0(g, lb) | ((1 - mybit) << lb))] = val[e];
+    }
+  }
+}
+QSB_HD int qsb_remap_syncs(int m, int W) {
+  const int cnt = 1 << (m - 1), per = QSB_REMAP_REGS * W;
+  return 1 + (cnt + per - 1) / per;
+}
+
+// apply the pending 2x2 of cluster-rank bit gb: mine' = P[my][my] mine + P[my][other] partner
+template <class Env>
+QSB_PASS void qsb_do_gflush(Env& env, int m, const qsb_desc* d) {
+  c128* tile = env.tile();
+  const int gb = d->b[0];
+  const int mybit = (env.rank >> gb) & 1;
+  const c128* peer = env.peer_tile(env.rank ^ (1 << gb));
+  const c128 pm = d->P[0][mybit * 2 + mybit], po = d->P[0][mybit * 2 + (1 - mybit)];
+  c128 val[QSB_REMAP_REGS];
+  const int cnt = 1 << m;
+  env.cluster_sync_w();
+  for (int base = 0; base < cnt; base += QSB_REMAP_REGS * env.W) {
+#pragma unroll
+    for (int e = 0; e < QSB_REMAP_REGS; ++e) {
+      int i = base + e * env.W + env.wid;
+      if (i < cnt) val[e] = qsb_fma(po, peer[i], qsb_mul(pm, tile[i]));      // same slot on both sides
+    }
+    env.cluster_sync_w();
+#pragma unroll
+    for (int e = 0; e < QSB_REMAP_REGS; ++e) {
+      int i = base + e * env.W + env.wid;
+      if (i < cnt) tile[i] = val[e];
+    }
+  }
+}
+QSB_HD int qsb_gflush_syncs(int m, int W) {
+  const int cnt = 1 << m, per = QSB_REMAP_REGS * W;
+  return 1 + (cnt + per - 1) / per;
+}
+
+// worker main loop: consume descriptors until EXIT
+template <class Env>
+QSB_HD void qsb_worker_loop(Env& env, const qsb_exec_args& a) {
+  const int m = a.m;
+  int parity = 0;
+  const bool prof = a.prof != nullptr && env.wid == 0;
+  unsigned long long pw = 0, pb[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pn[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t0 = 0, t1 = 0;
+  for (uint32_t seq = 0;; ++seq) {
+    const int slot = (int)(seq % QSB_RING);
+    if (prof) t0 = env.clock();
+    env.ring_wait_full(slot);               // also: every worker finished the previous descriptor
+    if (prof) { t1 = env.clock(); pw += t1 - t0; }
+    const qsb_desc* d = &env.ctl()->ring[slot];
+    const int kind = d->kind;
+    switch (kind) {
+      case QSB_D_INIT: qsb_do_init(env, a, d); break;
+      case QSB_D_SWEEP: qsb_do_sweep(env, m, d); break;
+      case QSB_D_REMAP: qsb_do_remap(env, m, d); break;
+      case QSB_D_GFLUSH: qsb_do_gflush(env, m, d); break;
+      case QSB_D_RDM1: {
+        double v[4];
+        qsb_partial_rdm1(env, m, d->b[0], v);
+        qsb_block_reduce(env, v, 4);
+        if (env.wid == 0)
+          for (int k = 0; k < 4; ++k) env.ctl()->red[parity][k] = v[k];
+        env.handoff_w();                    // control warps gather after this barrier
+        parity ^= 1;
+        break;
+      }
+      case QSB_D_STORE: qsb_do_store(env, a, d, parity); break;
+      default: break;
+    }
+    env.ring_release(slot);
+    if (prof) { pb[kind & 7] += env.clock() - t1; pn[kind & 7] += 1; }
+    if (kind == QSB_D_EXIT) break;
+  }
+  if (prof) {
+    unsigned long long* o = a.prof + (size_t)env.cta_id() * 32;
+    o[0] = pw;
+    for (int k = 0; k < 8; ++k) { o[1 + k] = pb[k]; o[9 + k] = pn[k]; }
+  }
+  if (env.C > 1) env.cluster_sync_w();      // no CTA may exit while a peer can still read its shared memory
+}
+
+// =========================================================================================
+//                                      CONTROL SIDE
+// =========================================================================================
+// Pending matrices are ALWAYS valid 2x2 matrices: a slot with nothing pending holds the exact identity, so
+// folding an op is an unconditional P <- U P.  The class word (2 bits per slot) only tells the workers how
+// much arithmetic a pending matrix needs.
+struct qsb_cstate {
+  uint32_t seq;                    // descriptors published so far
+  uint64_t clsword;                // 2-bit structure class per slot bit
+  int parity;
+  bool cl_wait;                    // a cluster-barrier arrival of this warp has not been waited for yet
+  // per-unit constants
+  int64_t t, tile, dim;
+  bool record;
+  bool prof;
+  unsigned long long ring_wait;    // cycles blocked on a full ring
+};
+
+QSB_HD int qsb_cls_of(uint64_t w, int b) { return (int)((w >> (2 * b)) & 3u); }
+QSB_HD uint64_t qsb_cls_set(uint64_t w, int b, int cls) {
+  return (w & ~((uint64_t)3 << (2 * b))) | ((uint64_t)cls << (2 * b));
+}
+// slot bits (as a bit mask) whose class is not NONE
+QSB_HD uint32_t qsb_cls_mask(uint64_t w) {
+  uint32_t r = 0;
+  for (int b = 0; b < 32; ++b) if ((w >> (2 * b)) & 3u) r |= 1u << b;
+  return r;
+}
+QSB_HD void qsb_pend_identity(c128* P) { P[0] = qsb_c(1, 0); P[1] = qsb_c(0, 0); P[2] = qsb_c(0, 0); P[3] = qsb_c(1, 0); }
+// P <- U P
+QSB_HD void qsb_pend_apply(c128* P, const c128* U) {
+  const c128 p00 = P[0], p01 = P[1], p10 = P[2], p11 = P[3];
+  const c128 u00 = U[0], u01 = U[1], u10 = U[2], u11 = U[3];
+  P[0] = qsb_fma(u01, p10, qsb_mul(u00, p00));
+  P[1] = qsb_fma(u01, p11, qsb_mul(u00, p01));
+  P[2] = qsb_fma(u11, p10, qsb_mul(u10, p00));
+  P[3] = qsb_fma(u11, p11, qsb_mul(u10, p01));
+}
+
+template <class Env>
+QSB_HD qsb_desc* qsb_desc_begin(Env& env, qsb_cstate& st) {
+  const int slot = (int)(st.seq % QSB_RING);
+  if (st.seq >= QSB_RING) {
+    const unsigned long long t0 = st.prof ? env.clock() : 0;
+    env.ring_wait_empty(slot);
+    if (st.prof) st.ring_wait += env.clock() - t0;
+  }
+  return &env.ctl()->ring[slot];
+}
+template <class Env>
+QSB_HD void qsb_desc_end(Env& env, qsb_cstate& st) {
+  env.ring_publish((int)(st.seq % QSB_RING));
+  ++st.seq;
+}
+// one cluster-barrier event the control warp takes part in without waiting for its completion
+template <class Env>
+QSB_HD void qsb_cluster_event(Env& env, qsb_cstate& st) {
+  if (env.C == 1) return;
+  if (st.cl_wait) env.cluster_wait_c();
+  env.cluster_arrive_c();
+  st.cl_wait = true;
+}
+
+// publish one sweep over `nb` local bits (bits[0] = MSB of the gate index) and reset their pending matrices
+template <class Env>
+QSB_CTL void qsb_emit_sweep(Env& env, qsb_cstate& st, int gate, int nb, const int* bits, const c128* mat_src) {
+  qsb_desc* d = qsb_desc_begin(env, st);
   qsb_ctl* ctl = env.ctl();
+  if (env.lead) {
+    d->kind = QSB_D_SWEEP; d->gate = gate; d->k = nb; d->flags = 0;
+    for (int k = 0; k < nb; ++k) {
+      const int b = bits[k], cls = qsb_cls_of(st.clsword, b);
+      d->b[k] = b; d->cls[k] = cls;
+      for (int e = 0; e < 4; ++e) d->P[k][e] = ctl->pend[b][e];
+      if (cls != QSB_CLS_NONE) qsb_pend_identity(ctl->pend[b]);
+    }
+  }
+  if (mat_src) {
+    const int cnt = 1 << (2 * nb);
+    for (int e = env.clane; e < cnt; e += env.CL) d->mat[e] = mat_src[e];
+  }
+  for (int k = 0; k < nb; ++k) st.clsword = qsb_cls_set(st.clsword, bits[k], QSB_CLS_NONE);
+  qsb_desc_end(env, st);
+}
+
+// apply and reset every pending matrix in `which` (slot-bit mask; local bits three per sweep, rank bits
+// one cluster exchange each)
+template <class Env>
+QSB_CTL void qsb_flush(Env& env, qsb_cstate& st, int m, uint32_t which) {
+  const uint32_t pending = qsb_cls_mask(st.clsword) & which;
+  uint32_t todo = pending & ((1u << m) - 1u);
+  while (todo) {
+    int bits[3], nb = 0;
+    while (todo && nb < 3) {
+      int b = 31;
+      while (!((todo >> b) & 1u)) --b;
+      bits[nb++] = b;
+      todo &= ~(1u << b);
+    }
+    qsb_emit_sweep(env, st, QSB_G_NONE, nb, bits, (const c128*)nullptr);
+  }
+  uint32_t gtodo = m >= 32 ? 0u : (pending >> m);
+  for (int gb = 0; gtodo; ++gb, gtodo >>= 1) {
+    if (!(gtodo & 1u)) continue;
+    qsb_desc* d = qsb_desc_begin(env, st);
+    if (env.lead) {
+      d->kind = QSB_D_GFLUSH; d->k = 1; d->b[0] = gb; d->cls[0] = QSB_CLS_DENSE;
+      for (int e = 0; e < 4; ++e) d->P[0][e] = env.ctl()->pend[m + gb][e];
+      qsb_pend_identity(env.ctl()->pend[m + gb]);
+    }
+    st.clsword = qsb_cls_set(st.clsword, m + gb, QSB_CLS_NONE);
+    qsb_desc_end(env, st);
+    const int ns = qsb_gflush_syncs(m, env.W);
+    for (int s = 0; s < ns; ++s) qsb_cluster_event(env, st);
+  }
+}
+
+// (unnormalised) 1-qubit reduced density matrix sums of slot bit b of the CURRENT state, in every control warp
+template <class Env>
+QSB_CTL void qsb_ctl_rdm1(Env& env, qsb_cstate& st, int b, double v[4]) {
+  qsb_desc* d = qsb_desc_begin(env, st);
+  if (env.lead) { d->kind = QSB_D_RDM1; d->k = 1; d->b[0] = b; }
+  qsb_desc_end(env, st);
+  if (env.C > 1 && st.cl_wait) { env.cluster_wait_c(); st.cl_wait = false; }
+  env.handoff_c();
+  for (int k = 0; k < 4; ++k) {
+    double s = 0.0;
+    for (int r = 0; r < env.C; ++r) s += env.peer_ctl(r)->red[st.parity][k];
+    v[k] = s;
+  }
+  st.parity ^= 1;
+}
+
+template <class Env>
+QSB_CTL void qsb_emit_store(Env& env, qsb_cstate& st, const qsb_exec_args& a, const int32_t* perm,
+                            c128* out, double* probs) {
+  qsb_desc* d = qsb_desc_begin(env, st);
+  if (env.lead) {
+    d->kind = QSB_D_STORE; d->flags = a.flags & QSB_RUN_NORMALIZE;
+    d->perm = perm; d->gptr = out; d->probs = probs; d->tile = st.tile;
+  }
+  qsb_desc_end(env, st);
+  if (a.flags & QSB_RUN_NORMALIZE) {
+    qsb_cluster_event(env, st);
+    st.parity ^= 1;
+  }
+}
+
+// ---- lane-parallel decode of one op (any control lane) ------------------------------------------
+// 1-qubit gates, Pauli draws and "certain K0" amplitude-damping draws become MUL records; the rest is SLOW.
+template <class Env>
+QSB_HD void qsb_decode_op(Env& env, const qsb_exec_args& a, const qsb_cstate& st, const qsb_op& op, double u,
+                          const double* prm, qsb_dec* d) {
+  const double* cd = a.cdata + (op.data >= 0 ? op.data : 0);
+  c128 U[4];
+  int type = QSB_DEC_MUL, ucls = QSB_CLS_DENSE;
+  U[0] = qsb_c(1, 0); U[1] = qsb_c(0, 0); U[2] = qsb_c(0, 0); U[3] = qsb_c(1, 0);
+  switch (op.kind) {
+    case QSB_OP_NOP: type = QSB_DEC_SKIP; break;
+    case QSB_OP_U1:
+      U[0] = qsb_c(cd[0], cd[1]); U[1] = qsb_c(cd[2], cd[3]); U[2] = qsb_c(cd[4], cd[5]); U[3] = qsb_c(cd[6], cd[7]);
+      break;
+    case QSB_OP_D1:
+      U[0] = qsb_c(cd[0], cd[1]); U[3] = qsb_c(cd[2], cd[3]);
+      ucls = (U[0].x == 1.0 && U[0].y == 0.0 && U[3].y == 0.0) ? QSB_CLS_RDIAG : QSB_CLS_DIAG;
+      break;
+    case QSB_OP_X: U[0] = qsb_c(0, 0); U[1] = qsb_c(1, 0); U[2] = qsb_c(1, 0); U[3] = qsb_c(0, 0); break;
+    case QSB_OP_Y: U[0] = qsb_c(0, 0); U[1] = qsb_c(0, -1); U[2] = qsb_c(0, 1); U[3] = qsb_c(0, 0); break;
+    case QSB_OP_Z: U[3] = qsb_c(-1, 0); ucls = QSB_CLS_RDIAG; break;
+    case QSB_OP_RX: case QSB_OP_RY: {     // gates.py:66-75
+      double s, c;
+      sincos(prm[op.param] * 0.5, &s, &c);
+      U[0] = qsb_c(c, 0); U[3] = qsb_c(c, 0);
+      if (op.kind == QSB_OP_RX) { U[1] = qsb_c(0, -s); U[2] = qsb_c(0, -s); }
+      else { U[1] = qsb_c(-s, 0); U[2] = qsb_c(s, 0); }
+      break;
+    }
+    case QSB_OP_RZ: {                     // gates.py:78-80
+      double s, c;
+      sincos(prm[op.param] * 0.5, &s, &c);
+      U[0] = qsb_c(c, -s); U[3] = qsb_c(c, s); ucls = QSB_CLS_DIAG;
+      break;
+    }
+    case QSB_OP_PHASE: {                  // gates.py:83-85
+      double s, c;
+      sincos(prm[op.param], &s, &c);
+      U[3] = qsb_c(c, s); ucls = QSB_CLS_DIAG;
+      break;
+    }
+    case QSB_OP_U3: {                     // gates.py:88-94
+      double s, c, sp, cp, sl, cl, spl, cpl;
+      sincos(prm[op.param] * 0.5, &s, &c);
+      sincos(prm[op.param + 1], &sp, &cp);
+      sincos(prm[op.param + 2], &sl, &cl);
+      sincos(prm[op.param + 1] + prm[op.param + 2], &spl, &cpl);
+      U[0] = qsb_c(c, 0); U[1] = qsb_c(-cl * s, -sl * s); U[2] = qsb_c(cp * s, sp * s); U[3] = qsb_c(cpl * c, spl * c);
+      break;
+    }
+    case QSB_OP_KRAUS_PAULI: {
+      // K_i = sqrt(w_i) P_i: ||K_i psi||^2 / sum = w_i / sum(w) for any psi, so the branch needs no
+      // reduction and (with the norm deferred to the store) the update is the bare Pauli.
+      int idx = 0;
+      for (int k = 0; k < 3; ++k) if (cd[k] <= u) ++idx;
+      const int code = (int)cd[3 + idx];
+      if (st.record) a.branches[st.t * a.branches_stride + op.draw] = idx;
+      if (code == 0) type = QSB_DEC_SKIP;
+      else if (code == 1) { U[0] = qsb_c(0, 0); U[1] = qsb_c(1, 0); U[2] = qsb_c(1, 0); U[3] = qsb_c(0, 0); }
+      else if (code == 2) { U[0] = qsb_c(0, 0); U[1] = qsb_c(0, -1); U[2] = qsb_c(0, 1); U[3] = qsb_c(0, 0); }
+      else { U[3] = qsb_c(-1, 0); ucls = QSB_CLS_RDIAG; }
+      break;
+    }
+    case QSB_OP_KRAUS_AD: {
+      // K0 = diag(1, sqrt(1-g)), K1 = sqrt(g)|0><1| (noise.py:98-103).  cdf[0] = p0/(p0+p1) >= 1-g, so a
+      // draw below 1-g is K0 whatever the state; only the rest needs P(q=1) of the actual state.
+      if (u < 1.0 - cd[0] - QSB_AD_MARGIN) {
+        if (st.record) a.branches[st.t * a.branches_stride + op.draw] = 0;
+        U[3] = qsb_c(cd[1], 0); ucls = QSB_CLS_RDIAG;
+      } else type = QSB_DEC_SLOW;
+      break;
+    }
+    default: type = QSB_DEC_SLOW; break;
+  }
+  d->type = type; d->b = op.b0; d->ucls = ucls;
+  if (type == QSB_DEC_MUL)
+    for (int e = 0; e < 4; ++e) d->U[e] = U[e];
+}
+
+// ---- ops that need the descriptor ring or the state (whole control warp) --------------------------
+template <class Env>
+QSB_CTL void qsb_control_slow(Env& env, const qsb_exec_args& a, qsb_cstate& st, int i) {
+  qsb_ctl* ctl = env.ctl();
+  const int m = a.m, n = a.n;
+  const qsb_op op = ctl->ops[i];
+  const uint32_t all_bits = n >= 32 ? 0xffffffffu : ((1u << n) - 1u);
+  const int b = op.b0;
+  switch (op.kind) {
+    case QSB_OP_KRAUS_AD: {               // the draw fell in [1-g, 1): the branch depends on P(q=1)
+      const double* cd = a.cdata + op.data;
+      const double u = ctl->u[i], gam = cd[0];
+      double v[4];
+      qsb_flush(env, st, m, all_bits);
+      qsb_ctl_rdm1(env, st, b, v);
+      double p[2] = {v[0] + (1.0 - gam) * v[1], gam * v[1]};
+      const int idx = qsb_choice(p, 2, u);
+      if (st.record) a.branches[st.t * a.branches_stride + op.draw] = idx;
+      if (env.lead) {
+        c128* P = ctl->pend[b];
+        if (idx == 0) { P[0] = qsb_c(1, 0); P[1] = qsb_c(0, 0); P[2] = qsb_c(0, 0); P[3] = qsb_c(cd[1], 0); }
+        else { P[0] = qsb_c(0, 0); P[1] = qsb_c(1, 0); P[2] = qsb_c(0, 0); P[3] = qsb_c(0, 0); }   // a0 <- a1, a1 <- 0
+      }
+      st.clsword = qsb_cls_set(st.clsword, b, idx == 0 ? QSB_CLS_RDIAG : QSB_CLS_DENSE);
+      break;
+    }
+    case QSB_OP_KRAUS_GEN: {              // target is a local bit (host compiler remaps it in)
+      const double u = ctl->u[i];
+      const double* g = a.cdata + op.data;
+      const int nk = (int)g[0];
+      double v[4], p[8];
+      qsb_flush(env, st, m, all_bits);
+      qsb_ctl_rdm1(env, st, b, v);
+      for (int k = 0; k < nk; ++k) {
+        const double* e = g + 1 + k * 12 + 8;       // e00, e11, re e01, im e01 ; rho10 = conj(v2 + i v3)
+        p[k] = e[0] * v[0] + e[1] * v[1] + 2.0 * (e[2] * v[2] + e[3] * v[3]);
+      }
+      const int idx = qsb_choice(p, nk, u);
+      if (st.record) a.branches[st.t * a.branches_stride + op.draw] = idx;
+      const double* kk = g + 1 + idx * 12;
+      if (env.lead) {
+        c128* P = ctl->pend[b];
+        P[0] = qsb_c(kk[0], kk[1]); P[1] = qsb_c(kk[2], kk[3]); P[2] = qsb_c(kk[4], kk[5]); P[3] = qsb_c(kk[6], kk[7]);
+      }
+      st.clsword = qsb_cls_set(st.clsword, b, QSB_CLS_DENSE);
+      break;
+    }
+    // ---------------- multi-qubit gates: one sweep = pending matrices of the bits + the gate
+    case QSB_OP_CX: case QSB_OP_CZ: case QSB_OP_SWAP: case QSB_OP_U2: {
+      int bits[2] = {op.b0, op.b1};
+      const int g = op.kind == QSB_OP_CX ? QSB_G_CX : op.kind == QSB_OP_CZ ? QSB_G_CZ :
+                    op.kind == QSB_OP_SWAP ? QSB_G_SWAP : QSB_G_DENSE;
+      qsb_emit_sweep(env, st, g, 2, bits, op.kind == QSB_OP_U2 ? (const c128*)(a.cdata + op.data) : (const c128*)nullptr);
+      break;
+    }
+    case QSB_OP_CCX: case QSB_OP_CSWAP: case QSB_OP_U3Q: {
+      int bits[3] = {op.b0, op.b1, op.b2};
+      const int g = op.kind == QSB_OP_CCX ? QSB_G_CCX : op.kind == QSB_OP_CSWAP ? QSB_G_CSWAP : QSB_G_DENSE;
+      qsb_emit_sweep(env, st, g, 3, bits, op.kind == QSB_OP_U3Q ? (const c128*)(a.cdata + op.data) : (const c128*)nullptr);
+      break;
+    }
+    case QSB_OP_REMAP: {
+      // swap cluster-rank bit b0 with local slot bit b1; the pending matrices move with their qubits
+      const int gb = op.b0, lb = op.b1;
+      qsb_desc* d = qsb_desc_begin(env, st);
+      if (env.lead) { d->kind = QSB_D_REMAP; d->k = 2; d->b[0] = gb; d->b[1] = lb; }
+      qsb_desc_end(env, st);
+      const int ns = qsb_remap_syncs(m, env.W);
+      for (int s = 0; s < ns; ++s) qsb_cluster_event(env, st);
+      const int ca = qsb_cls_of(st.clsword, lb), cb = qsb_cls_of(st.clsword, m + gb);
+      if (env.lead)
+        for (int e = 0; e < 4; ++e) { c128 x = ctl->pend[lb][e]; ctl->pend[lb][e] = ctl->pend[m + gb][e]; ctl->pend[m + gb][e] = x; }
+      st.clsword = qsb_cls_set(qsb_cls_set(st.clsword, lb, cb), m + gb, ca);
+      break;
+    }
+    case QSB_OP_SNAPSHOT: {
+      qsb_flush(env, st, m, all_bits);
+      qsb_emit_store(env, st, a, a.idata + op.aux,
+                     a.snapshots ? a.snapshots + (st.t * a.n_snapshots + op.b0) * st.dim : nullptr, nullptr);
+      break;
+    }
+    default:
+      break;
+  }
+}
+
+// ---- one unit (trajectory, or tile of a streamed state) on the control warp ----------------
+template <class Env>
+QSB_HD void qsb_control_unit(Env& env, qsb_cstate& st, const qsb_exec_args& a, int64_t unit) {
+  const int n = a.n;
+  qsb_ctl* ctl = env.ctl();
+  const int64_t t = unit >> a.tile_bits;                          // state / trajectory index
+  st.t = t;
+  st.tile = a.tile_bits ? (unit & (((int64_t)1 << a.tile_bits) - 1)) : (int64_t)env.rank;
+  st.dim = (int64_t)1 << n;
+  st.record = a.branches != nullptr && env.rank == 0;
+  st.clsword = 0;
   const qsb_op* ops = a.ops + t * a.ops_stride;
   const double* prm = a.params ? a.params + t * a.params_stride : nullptr;
   const double* uni = a.uniforms ? a.uniforms + t * a.uniforms_stride : nullptr;
   const uint64_t tglob = (uint64_t)(a.traj_offset + t);
-  const int64_t dim = (int64_t)1 << n;
-  const uint32_t all_local = (1u << m) - 1u;
-  const bool lead = env.tid == 0;
-  const bool record = a.branches && lead && env.rank == 0;
-  uint32_t mask = 0;                 // slot bits with a pending matrix; every thread keeps the same value
+  const uint32_t all_bits = n >= 32 ? 0xffffffffu : ((1u << n) - 1u);
+  const bool lead = env.lead;
 
-  // ---- initial state
-  {
-    qsb_build_perm(env, ctl, a.idata + a.load_perm, n);
-    if (a.flags & QSB_RUN_LOAD) {
-      const c128* src = a.states + t * dim;
-      for (int i = env.tid; i < (1 << m); i += env.T)
-        tile[qsb_slot(i)] = src[qsb_permute(ctl->perm, ((uint32_t)env.rank << m) | (uint32_t)i)];
-    } else {
-      const uint32_t basis = (uint32_t)(a.init_basis ? a.init_basis[t] : a.default_basis);
-      for (int i = env.tid; i < (1 << m); i += env.T)
-        tile[qsb_slot(i)] = qsb_c(qsb_permute(ctl->perm, ((uint32_t)env.rank << m) | (uint32_t)i) == basis ? 1.0 : 0.0, 0.0);
+  {  // ---- initial state; every pending matrix starts as the identity
+    for (int e = env.clane; e < 32; e += env.CL) qsb_pend_identity(ctl->pend[e]);
+    qsb_desc* d = qsb_desc_begin(env, st);
+    if (lead) {
+      d->kind = QSB_D_INIT; d->flags = a.flags & QSB_RUN_LOAD;
+      d->unit = unit; d->tile = st.tile;
+      d->basis = a.init_basis ? a.init_basis[t] : a.default_basis;
+      d->perm = a.idata + a.load_perm;
+      d->gptr = a.states ? a.states + t * st.dim : nullptr;
     }
-    env.sync_block();
+    qsb_desc_end(env, st);
   }
 
   for (int64_t pc0 = 0; pc0 < a.n_ops; pc0 += QSB_CHUNK) {
     const int len = (int)((a.n_ops - pc0) < QSB_CHUNK ? (a.n_ops - pc0) : QSB_CHUNK);
-    // ---- stage a chunk: op records, their uniforms / angles / leading cdata (one latency per chunk)
-    env.sync_block();
-    for (int i = env.tid; i < len; i += env.T) {
+    // ---- phase A: the lanes decode a chunk in parallel (op records, uniforms, angles, matrices)
+    env.sync_control();
+    for (int i = env.clane; i < len; i += env.CL) {
       const qsb_op op = ops[pc0 + i];
+      double u = 0.0;
+      if (op.draw >= 0) u = uni ? uni[op.draw] : qsb_philox_uniform(a.seed, tglob, (uint32_t)op.draw);
       ctl->ops[i] = op;
-      if (op.draw >= 0) ctl->u[i] = uni ? uni[op.draw] : qsb_philox_uniform(a.seed, tglob, (uint32_t)op.draw);
-      if (op.param >= 0 && prm) {
-        const int np = op.kind == QSB_OP_U3 ? 3 : 1;
-        for (int k = 0; k < np; ++k) ctl->prm[i][k] = prm[op.param + k];
-      }
-      if (op.data >= 0)
-        for (int k = 0; k < 8; ++k) ctl->cd[i][k] = (op.data + k < a.n_cdata) ? a.cdata[op.data + k] : 0.0;
+      ctl->u[i] = u;
+      qsb_decode_op(env, a, st, op, u, prm, &ctl->dec[i]);
     }
-    env.sync_block();
+    env.sync_control();
 
-    for (int i = 0; i < len; ++i) {
-      const qsb_op op = ctl->ops[i];
-      const double* cd = ctl->cd[i];
-      const int b = op.b0;
-      const bool has = (mask >> b) & 1u;
-      switch (op.kind) {
-        case QSB_OP_NOP:
-          break;
-        // ---------------- 1-qubit operations: fold into the pending matrix of bit b
-        case QSB_OP_U1:
-          if (lead) qsb_pend_mul(ctl->pend[b], has, qsb_c(cd[0], cd[1]), qsb_c(cd[2], cd[3]), qsb_c(cd[4], cd[5]), qsb_c(cd[6], cd[7]));
-          mask |= 1u << b;
-          break;
-        case QSB_OP_D1:
-          if (lead) qsb_pend_diag(ctl->pend[b], has, qsb_c(cd[0], cd[1]), qsb_c(cd[2], cd[3]));
-          mask |= 1u << b;
-          break;
-        case QSB_OP_X: case QSB_OP_Y: case QSB_OP_Z:
-          if (lead) qsb_pend_pauli(ctl->pend[b], has, op.kind - QSB_OP_X + 1);
-          mask |= 1u << b;
-          break;
-        case QSB_OP_RX: case QSB_OP_RY: {     // gates.py:66-75
-          if (lead) {
-            double s, c;
-            sincos(ctl->prm[i][0] * 0.5, &s, &c);
-            if (op.kind == QSB_OP_RX) qsb_pend_mul(ctl->pend[b], has, qsb_c(c, 0), qsb_c(0, -s), qsb_c(0, -s), qsb_c(c, 0));
-            else qsb_pend_mul(ctl->pend[b], has, qsb_c(c, 0), qsb_c(-s, 0), qsb_c(s, 0), qsb_c(c, 0));
+    // ---- phase B: fold the MUL records in order (one lane, a tight loop), stop at every SLOW op
+    int i = 0;
+    while (i < len) {
+      uint64_t w = st.clsword;
+      if (lead) {
+        while (i < len) {
+          const qsb_dec* d = &ctl->dec[i];
+          const int type = d->type;
+          if (type == QSB_DEC_SLOW) break;
+          if (type == QSB_DEC_MUL) {
+            const int b = d->b & 31;
+            qsb_pend_apply(ctl->pend[b], d->U);
+            const int c = qsb_cls_of(w, b), uc = d->ucls;
+            w = qsb_cls_set(w, b, c > uc ? c : uc);
           }
-          mask |= 1u << b;
-          break;
+          ++i;
         }
-        case QSB_OP_RZ: {                     // gates.py:78-80
-          if (lead) {
-            double s, c;
-            sincos(ctl->prm[i][0] * 0.5, &s, &c);
-            qsb_pend_diag(ctl->pend[b], has, qsb_c(c, -s), qsb_c(c, s));
-          }
-          mask |= 1u << b;
-          break;
-        }
-        case QSB_OP_PHASE: {                  // gates.py:83-85
-          if (lead) {
-            double s, c;
-            sincos(ctl->prm[i][0], &s, &c);
-            qsb_pend_diag(ctl->pend[b], has, qsb_c(1, 0), qsb_c(c, s));
-          }
-          mask |= 1u << b;
-          break;
-        }
-        case QSB_OP_U3: {                     // gates.py:88-94
-          if (lead) {
-            double s, c, sp, cp, sl, cl, spl, cpl;
-            sincos(ctl->prm[i][0] * 0.5, &s, &c);
-            sincos(ctl->prm[i][1], &sp, &cp);
-            sincos(ctl->prm[i][2], &sl, &cl);
-            sincos(ctl->prm[i][1] + ctl->prm[i][2], &spl, &cpl);
-            qsb_pend_mul(ctl->pend[b], has, qsb_c(c, 0), qsb_c(-cl * s, -sl * s), qsb_c(cp * s, sp * s), qsb_c(cpl * c, spl * c));
-          }
-          mask |= 1u << b;
-          break;
-        }
-        case QSB_OP_KRAUS_PAULI: {
-          // K_i = sqrt(w_i) P_i: ||K_i psi||^2 / sum = w_i / sum(w) for any psi, so the branch needs no
-          // reduction and (with the norm deferred to the store) the update is the bare Pauli.
-          const double u = ctl->u[i];
-          int idx = 0;
-          for (int k = 0; k < 3; ++k) if (cd[k] <= u) ++idx;
-          const int code = (int)cd[3 + idx];
-          if (record) a.branches[t * a.branches_stride + op.draw] = idx;
-          if (code != 0) {
-            if (lead) qsb_pend_pauli(ctl->pend[b], has, code);
-            mask |= 1u << b;
-          }
-          break;
-        }
-        case QSB_OP_KRAUS_AD: {
-          // K0 = diag(1, sqrt(1-g)), K1 = sqrt(g)|0><1| (noise.py:98-103).  cdf[0] = p0/(p0+p1) >= 1-g, so a
-          // draw below 1-g is K0 whatever the state; only the rest needs P(q=1) of the actual state.
-          const double u = ctl->u[i];
-          const double gam = cd[0];
-          int idx = 0;
-          bool had = has;
-          if (!(u < 1.0 - gam - QSB_AD_MARGIN)) {
-            qsb_flush(env, m, mask, all_local);
-            had = false;
-            double v[4];
-            qsb_partial_rdm1(env, m, b, v);
-            env.allreduce(v, 2);
-            double p[2] = {v[0] + (1.0 - gam) * v[1], gam * v[1]};
-            idx = qsb_choice(p, 2, u);
-          }
-          if (record) a.branches[t * a.branches_stride + op.draw] = idx;
-          if (lead) {
-            if (idx == 0) qsb_pend_diag(ctl->pend[b], had, qsb_c(1, 0), qsb_c(cd[1], 0));
-            else qsb_pend_mul(ctl->pend[b], had, qsb_c(0, 0), qsb_c(1, 0), qsb_c(0, 0), qsb_c(0, 0));   // a0 <- a1, a1 <- 0
-          }
-          mask |= 1u << b;
-          break;
-        }
-        case QSB_OP_KRAUS_GEN: {
-          const double u = ctl->u[i];
-          const double* g = a.cdata + op.data;
-          const int nk = (int)g[0];
-          double v[4], p[8];
-          qsb_flush(env, m, mask, all_local);
-          qsb_partial_rdm1(env, m, b, v);
-          env.allreduce(v, 4);
-          for (int k = 0; k < nk; ++k) {
-            const double* e = g + 1 + k * 12 + 8;       // e00, e11, re e01, im e01 ; rho10 = conj(v2 + i v3)
-            p[k] = e[0] * v[0] + e[1] * v[1] + 2.0 * (e[2] * v[2] + e[3] * v[3]);
-          }
-          const int idx = qsb_choice(p, nk, u);
-          if (record) a.branches[t * a.branches_stride + op.draw] = idx;
-          const double* kk = g + 1 + idx * 12;
-          if (lead) qsb_pend_mul(ctl->pend[b], false, qsb_c(kk[0], kk[1]), qsb_c(kk[2], kk[3]), qsb_c(kk[4], kk[5]), qsb_c(kk[6], kk[7]));
-          mask |= 1u << b;
-          break;
-        }
-        // ---------------- multi-qubit gates: one sweep = pending matrices of the bits + the gate
-        case QSB_OP_CX: case QSB_OP_CZ: case QSB_OP_SWAP: case QSB_OP_U2: {
-          int bits[2] = {op.b0, op.b1};
-          const int pm = (int)((mask >> op.b0) & 1u) | (int)(((mask >> op.b1) & 1u) << 1);
-          env.sync_block();
-          if (op.kind == QSB_OP_U2) {
-            for (int k = env.tid; k < 16; k += env.T) ctl->mat[k] = ((const c128*)(a.cdata + op.data))[k];
-            env.sync_block();
-            qsb_pass_fused<2, QSB_G_DENSE>(env, m, bits, pm);
-          } else if (op.kind == QSB_OP_CX) qsb_pass_fused<2, QSB_G_CX>(env, m, bits, pm);
-          else if (op.kind == QSB_OP_CZ) qsb_pass_fused<2, QSB_G_CZ>(env, m, bits, pm);
-          else qsb_pass_fused<2, QSB_G_SWAP>(env, m, bits, pm);
-          env.sync_block();
-          mask &= ~((1u << op.b0) | (1u << op.b1));
-          break;
-        }
-        case QSB_OP_CCX: case QSB_OP_CSWAP: case QSB_OP_U3Q: {
-          int bits[3] = {op.b0, op.b1, op.b2};
-          const int pm = (int)((mask >> op.b0) & 1u) | (int)(((mask >> op.b1) & 1u) << 1) | (int)(((mask >> op.b2) & 1u) << 2);
-          env.sync_block();
-          if (op.kind == QSB_OP_U3Q) {
-            for (int k = env.tid; k < 64; k += env.T) ctl->mat[k] = ((const c128*)(a.cdata + op.data))[k];
-            env.sync_block();
-            qsb_pass_fused<3, QSB_G_DENSE>(env, m, bits, pm);
-          } else if (op.kind == QSB_OP_CCX) qsb_pass_fused<3, QSB_G_CCX>(env, m, bits, pm);
-          else qsb_pass_fused<3, QSB_G_CSWAP>(env, m, bits, pm);
-          env.sync_block();
-          mask &= ~((1u << op.b0) | (1u << op.b1) | (1u << op.b2));
-          break;
-        }
-        case QSB_OP_REMAP: {
-          // swap cluster-rank bit b0 with local slot bit b1: pull the partner's half, then overwrite ours
-          const int gb = op.b0, lb = op.b1;
-          qsb_flush(env, m, mask, 1u << lb);      // the outgoing qubit takes no pending matrix along
-          const int mybit = (env.rank >> gb) & 1;
-          const c128* peer = env.peer_tile(env.rank ^ (1 << gb));
-          c128 val[QSB_REMAP_REGS];
-          const int cnt = 1 << (m - 1);
-          env.sync_cluster();                       // everyone finished the ops before the exchange
-          // Round r pulls the partner's groups g and then overwrites OUR groups g (the ones the partner pulls
-          // in the same round), so one cluster barrier between the two halves of a round is enough.
-          for (int base = 0; base < cnt; base += QSB_REMAP_REGS * env.T) {
-            for (int e = 0; e < QSB_REMAP_REGS; ++e) {
-              int g = base + e * env.T + env.tid;
-              if (g < cnt) val[e] = peer[qsb_slot(qsb_ins0(g, lb) | (mybit << lb))];
-            }
-            env.sync_cluster();
-            for (int e = 0; e < QSB_REMAP_REGS; ++e) {
-              int g = base + e * env.T + env.tid;
-              if (g < cnt) tile[qsb_slot(qsb_ins0(g, lb) | ((1 - mybit) << lb))] = val[e];
-            }
-          }
-          env.sync_block();
-          break;
-        }
-        case QSB_OP_SNAPSHOT: {
-          qsb_flush(env, m, mask, all_local);
-          double scale = 1.0;
-          if (a.flags & QSB_RUN_NORMALIZE) {
-            double nn = qsb_norm2_all(env, m);
-            if (nn > 1e-30) scale = 1.0 / sqrt(nn);
-          }
-          if (a.snapshots)
-            qsb_store_state(env, a, a.idata + op.aux, scale,
-                            a.snapshots + (t * a.n_snapshots + op.b0) * dim, nullptr);
-          break;
-        }
-        default:
-          break;
+      }
+      i = env.bcast_i(i);
+      st.clsword = env.bcast_u64(w);
+      if (i < len) {
+        qsb_control_slow(env, a, st, i);
+        ++i;
       }
     }
   }
 
   // ---- epilogue
-  qsb_flush(env, m, mask, all_local);
-  env.sync_block();
-  if (a.flags & (QSB_RUN_STORE | QSB_RUN_ACCUM_PROBS)) {
-    double scale = 1.0;
-    if (a.flags & QSB_RUN_NORMALIZE) {
-      double nn = qsb_norm2_all(env, m);
-      if (nn > 1e-30) scale = 1.0 / sqrt(nn);
-    }
-    qsb_store_state(env, a, a.idata + a.store_perm, scale,
-                    (a.flags & QSB_RUN_STORE) ? a.states + t * dim : nullptr,
-                    (a.flags & QSB_RUN_ACCUM_PROBS) ? a.probs_accum : nullptr);
+  env.sync_control();
+  qsb_flush(env, st, a.m, all_bits);
+  if (a.flags & (QSB_RUN_STORE | QSB_RUN_ACCUM_PROBS))
+    qsb_emit_store(env, st, a, a.idata + a.store_perm,
+                   (a.flags & QSB_RUN_STORE) ? a.states + t * st.dim : nullptr,
+                   (a.flags & QSB_RUN_ACCUM_PROBS) ? a.probs_accum : nullptr);
+}
+
+// control main loop over the units [first, total) of this CTA (stride = number of resident clusters / CTAs)
+template <class Env>
+QSB_HD void qsb_control_loop(Env& env, const qsb_exec_args& a, int64_t first, int64_t stride) {
+  qsb_cstate st;
+  st.seq = 0; st.clsword = 0; st.parity = 0; st.cl_wait = false;
+  st.prof = a.prof != nullptr; st.ring_wait = 0;
+  const unsigned long long c0 = st.prof ? env.clock() : 0;
+  const int64_t total = a.count << a.tile_bits;
+  for (int64_t u = first; u < total; u += stride) qsb_control_unit(env, st, a, u);
+  if (st.prof && env.lead) {
+    unsigned long long* o = a.prof + (size_t)env.cta_id() * 32;
+    o[17] = st.ring_wait;
+    o[18] = env.clock() - c0;
+    o[19] = st.seq;
   }
-  env.sync_block();
+  qsb_desc* d = qsb_desc_begin(env, st);
+  if (env.lead) d->kind = QSB_D_EXIT;
+  qsb_desc_end(env, st);
+  if (env.C > 1) {
+    qsb_cluster_event(env, st);
+    env.cluster_wait_c();
+  }
 }

@@ -9,75 +9,114 @@
 
 namespace cg = cooperative_groups;
 
-#define QSB_TRAJ_THREADS 512
-#define QSB_SMEM_EXTRA (sizeof(qsb_ctl) + 16 * 4 * 8 + 2 * 4 * 8)   // control block + warp partials + cluster partials
+#define QSB_MAX_WORKERS 256
+#define QSB_CTL_THREADS 32
+#define QSB_SMEM_EXTRA (sizeof(qsb_ctl))
 
-// the one dynamic shared-memory block of the trajectory kernel: [tile | qsb_ctl | reduction scratch]
+// the one dynamic shared-memory block of the executor kernel: [tile | qsb_ctl]
 extern __shared__ __align__(16) unsigned char qsb_smem[];
 
-template <int C>
+// named barriers (id 0 is left to __syncthreads, which the executor never uses)
+#define QSB_BAR_FULL 1                    // + ring slot: control arrives, workers sync
+#define QSB_BAR_EMPTY (1 + QSB_RING)      // + ring slot: workers arrive, control syncs
+#define QSB_BAR_WORKERS (1 + 2 * QSB_RING)
+#define QSB_BAR_ALL (2 + 2 * QSB_RING)
+
+__device__ __forceinline__ void qsb_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void qsb_bar_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void qsb_cluster_arrive() {
+  asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+}
+__device__ __forceinline__ void qsb_cluster_wait() {
+  asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+}
+
+// threads [0, W) are workers, [W, W + 32) is the control warp
+template <int CS>
 struct DeviceEnv {
-  int tid, T, rank, m_;
-  int parity;
+  static constexpr int C = CS;
+  static constexpr int CL = QSB_CTL_THREADS;
+  int wid, W, rank, m_;
+  int lane, warp, nwarps;      // worker warp geometry
+  int clane;                   // lane inside the control warp
+  bool lead;                   // the control lane that writes shared state
 
   __device__ DeviceEnv(int m) {
-    tid = threadIdx.x;
-    T = blockDim.x;
-    rank = (C > 1) ? (int)cg::this_cluster().block_rank() : 0;
+    W = (int)blockDim.x - QSB_CTL_THREADS;
+    const int tid = threadIdx.x;
+    wid = tid < W ? tid : -1;
+    lane = tid & 31;
+    warp = tid >> 5;
+    nwarps = W >> 5;
+    clane = tid - W;
+    lead = clane == 0;
+    rank = (CS > 1) ? (int)cg::this_cluster().block_rank() : 0;
     m_ = m;
-    parity = 0;
   }
   // pointers are re-derived from the shared symbol at every use so that loads/stores stay LDS/STS
   __device__ __forceinline__ c128* tile() { return reinterpret_cast<c128*>(qsb_smem); }
   __device__ __forceinline__ qsb_ctl* ctl() { return reinterpret_cast<qsb_ctl*>(qsb_smem + ((size_t)16 << m_)); }
-  __device__ __forceinline__ double* wpart() { return reinterpret_cast<double*>(qsb_smem + ((size_t)16 << m_) + sizeof(qsb_ctl)); }
-  __device__ __forceinline__ double* clred() { return wpart() + 64; }
-  __device__ __forceinline__ void sync_block() { __syncthreads(); }
-  __device__ __forceinline__ void sync_cluster() {
-    if (C > 1) cg::this_cluster().sync(); else __syncthreads();
-  }
   __device__ __forceinline__ const c128* peer_tile(int r) {
-    if (C > 1) return cg::this_cluster().map_shared_rank(tile(), r);
+    if (CS > 1) return cg::this_cluster().map_shared_rank(tile(), r);
     return tile();
   }
+  __device__ __forceinline__ const qsb_ctl* peer_ctl(int r) {
+    if (CS > 1) return cg::this_cluster().map_shared_rank(ctl(), r);
+    return ctl();
+  }
   __device__ __forceinline__ void atomic_add(double* p, double v) { atomicAdd(p, v); }
-
-  // sum v[0..nv) over every thread of the cluster; all threads get bit-identical results
-  __device__ void allreduce(double* v, int nv) {
-    const int lane = tid & 31, warp = tid >> 5, nw = (T + 31) >> 5;
-    __syncthreads();
-    for (int k = 0; k < nv; ++k) {
-      double x = v[k];
-      for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
-      if (lane == 0) wpart()[warp * 4 + k] = x;
-    }
-    __syncthreads();
-    for (int k = 0; k < nv; ++k) {
-      double s = 0.0;
-      for (int w = 0; w < nw; ++w) s += wpart()[w * 4 + k];
-      v[k] = s;
-    }
-    if (C > 1) {
-      cg::cluster_group cl = cg::this_cluster();
-      if (tid == 0)
-        for (int k = 0; k < nv; ++k) clred()[parity * 4 + k] = v[k];
-      cl.sync();
-      for (int k = 0; k < nv; ++k) {
-        double s = 0.0;
-        for (int r = 0; r < C; ++r) s += cl.map_shared_rank(clred(), r)[parity * 4 + k];
-        v[k] = s;
-      }
-      parity ^= 1;   // the buffer of reduction k is rewritten at k+2, after everyone passed barrier k+1
-    }
+  __device__ __forceinline__ double warp_sum(double x) {
+    for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+    return x;
+  }
+  __device__ __forceinline__ unsigned long long clock() { return (unsigned long long)clock64(); }
+  __device__ __forceinline__ int cta_id() { return (int)blockIdx.x; }
+  // lane 0 of the control warp -> every lane
+  __device__ __forceinline__ int bcast_i(int x) { return __shfl_sync(0xffffffffu, x, 0); }
+  __device__ __forceinline__ uint64_t bcast_u64(uint64_t x) {
+    const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)x, 0), hi = __shfl_sync(0xffffffffu, (uint32_t)(x >> 32), 0);
+    return ((uint64_t)hi << 32) | lo;
+  }
+  // ---- descriptor ring
+  __device__ __forceinline__ void ring_wait_empty(int s) { __syncwarp(); qsb_bar_sync(QSB_BAR_EMPTY + s, W + QSB_CTL_THREADS); }
+  __device__ __forceinline__ void ring_publish(int s) {
+    __syncwarp();
+    __threadfence_block();
+    qsb_bar_arrive(QSB_BAR_FULL + s, W + QSB_CTL_THREADS);
+  }
+  __device__ __forceinline__ void ring_wait_full(int s) { qsb_bar_sync(QSB_BAR_FULL + s, W + QSB_CTL_THREADS); }
+  __device__ __forceinline__ void ring_release(int s) { qsb_bar_arrive(QSB_BAR_EMPTY + s, W + QSB_CTL_THREADS); }
+  // ---- barriers
+  __device__ __forceinline__ void sync_workers() { qsb_bar_sync(QSB_BAR_WORKERS, W); }
+  __device__ __forceinline__ void sync_control() { __syncwarp(); }
+  __device__ __forceinline__ void cluster_sync_w() { qsb_cluster_arrive(); qsb_cluster_wait(); }
+  __device__ __forceinline__ void cluster_arrive_c() { __syncwarp(); qsb_cluster_arrive(); }
+  __device__ __forceinline__ void cluster_wait_c() { qsb_cluster_wait(); }
+  // workers -> control hand-off of a reduction (every CTA of the cluster takes part)
+  __device__ __forceinline__ void handoff_w() {
+    if (CS > 1) cluster_sync_w(); else qsb_bar_sync(QSB_BAR_ALL, W + QSB_CTL_THREADS);
+  }
+  __device__ __forceinline__ void handoff_c() {
+    __syncwarp();
+    if (CS > 1) { qsb_cluster_arrive(); qsb_cluster_wait(); } else qsb_bar_sync(QSB_BAR_ALL, W + QSB_CTL_THREADS);
   }
 };
 
-template <int C>
-__global__ void __launch_bounds__(QSB_TRAJ_THREADS, 1) qsb_traj_kernel(const __grid_constant__ qsb_exec_args a) {
-  DeviceEnv<C> env(a.m);
-  const int64_t cluster_id = blockIdx.x / C, n_clusters = gridDim.x / C;
-  for (int64_t t = cluster_id; t < a.count; t += n_clusters) qsb_exec_trajectory(env, a, t);
-  if (C > 1) cg::this_cluster().sync();   // no CTA may exit while a peer can still read its shared memory
+template <int CS>
+__global__ void __launch_bounds__(QSB_MAX_WORKERS + QSB_CTL_THREADS, 1)
+qsb_traj_kernel(const __grid_constant__ qsb_exec_args a) {
+  DeviceEnv<CS> env(a.m);
+  if (env.wid >= 0) {
+    qsb_worker_loop(env, a);
+  } else {
+    const int64_t first = a.tile_bits ? (int64_t)blockIdx.x : (int64_t)(blockIdx.x / CS);
+    const int64_t stride = a.tile_bits ? (int64_t)gridDim.x : (int64_t)(gridDim.x / CS);
+    qsb_control_loop(env, a, first, stride);
+  }
 }
 
 // ---------------------------------------------------------------------------------------

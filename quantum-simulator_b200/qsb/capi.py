@@ -26,6 +26,7 @@ SYMBOLS = [
     "qsb_launch_count", "qsb_buffer_alloc", "qsb_buffer_wrap", "qsb_buffer_free", "qsb_buffer_upload",
     "qsb_buffer_download", "qsb_buffer_zero", "qsb_buffer_copy", "qsb_buffer_ptr", "qsb_buffer_bytes",
     "qsb_host_alloc", "qsb_host_free", "qsb_program_create", "qsb_program_free", "qsb_run",
+    "qsb_debug_profile",
     "qsb_probabilities", "qsb_probabilities_sum", "qsb_sample_index", "qsb_overlap",
     "qsb_masked_parity", "qsb_rdm_all", "qsb_rho_accumulate", "qsb_readout_transform",
 ]
@@ -87,6 +88,7 @@ def load_library():
             "qsb_program_create": (C.c_int, [vp, i32, i32, vp, i64, i64, i64, vp, i64, vp, i64, i32, i32, i32, P(vp)]),
             "qsb_program_free": (C.c_int, [vp]),
             "qsb_run": (C.c_int, [vp, P(RunArgs)]),
+            "qsb_debug_profile": (C.c_int, [vp, C.c_int, vp, i64]),
             "qsb_probabilities": (C.c_int, [vp, i32, vp, i64, i64, vp, i64]),
             "qsb_probabilities_sum": (C.c_int, [vp, i32, vp, i64, i64, vp]),
             "qsb_sample_index": (C.c_int, [vp, i32, vp, i64, i64, vp, vp]),
@@ -250,6 +252,15 @@ class Context:
                    (RUN_NORMALIZE if norm else 0) | (RUN_ASYNC if async_ else 0) |
                    (RUN_ACCUM_PROBS if probs_accum is not None else 0))
         _check(self.lib.qsb_run(dprog.handle, C.byref(a)), self.handle)
+
+    def profile(self, enable=True, read=False):
+        """Developer aid: executor cycle counters (see qsb_debug_profile); returns uint64[ctas][32] when read."""
+        out = np.zeros((8 * 148 * 4, 32), dtype=np.uint64) if read else None
+        n = self.lib.qsb_debug_profile(self.handle, 1 if enable else 0, _hostptr(out) if read else None,
+                                       out.shape[0] if read else 0)
+        if n < 0:
+            _check(n, self.handle)
+        return out[:n] if read else None
 
     def sync(self):
         _check(self.lib.qsb_ctx_sync(self.handle), self.handle)

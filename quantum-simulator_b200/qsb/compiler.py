@@ -292,10 +292,15 @@ class Lowering:
             raise ValueError(f"local_bits {m} invalid for n = {n}")
         g = n - m
         items = self.items
-        uses = [[] for _ in range(n)]          # op indices touching each physical bit
+        # 1-qubit gates and Pauli / amplitude-damping draws only update the pending 2x2 of their slot,
+        # which may be a cluster-rank slot; only ops that sweep the tile need their bits resident
+        def needs_local(kind, pbits):
+            return len(pbits) > 1 or kind == KRAUS_GEN
+        uses = [[] for _ in range(n)]          # indices of the sweeping ops touching each physical bit
         for i, it in enumerate(items):
-            for b in it[1]:
-                uses[b].append(i)
+            if it[0] != SNAPSHOT and needs_local(it[0], it[1]):
+                for b in it[1]:
+                    uses[b].append(i)
         for it in items:
             if len(it[1]) > m:
                 raise ValueError(f"a {len(it[1])}-qubit op does not fit {m} resident bits")
@@ -336,7 +341,7 @@ class Lowering:
                 ops.append((SNAPSHOT, data, 0, 0, -1, -1, -1, off))
                 continue
             for b in pbits:
-                if slot_of[b] >= m:
+                if slot_of[b] >= m and needs_local(kind, pbits):
                     cand = [c for c in range(n) if slot_of[c] < m and c not in pbits]
                     victim = max(cand, key=lambda c: (next_use(c, i), -slot_of[c]))
                     ops.append((REMAP, slot_of[b] - m, slot_of[victim], 0, -1, -1, -1, 0))

@@ -1,49 +1,66 @@
-// emu_exec.cpp -- TEST-ONLY host emulation of the resident-trajectory executor.
+// emu_exec.cpp -- TEST-ONLY host emulation of the resident-tile executor.
 //
-// Compiles quantum-simulator_b200/csrc/qsb_exec.cuh with g++ against a HostEnv made of a few
-// OS threads and std::barrier, so the op loop, the index math and the host compiler
-// (qsb/compiler.py) can be checked against the oracle on a machine without a GPU.  It exports one
-// symbol (emu_run) that libqsb.so does not have; the product package never loads this library and
-// has no switch that could route to it.
+// Compiles quantum-simulator_b200/csrc/qsb_exec.cuh with g++ against a HostEnv made of OS
+// threads and std::barrier, so the control/worker protocol, the op loop, the index math and the
+// host compiler (qsb/compiler.py) can be checked against the oracle on a machine without a GPU.
+// It exports one symbol (emu_run) that libqsb.so does not have; the product package never loads
+// this library and has no switch that could route to it.
 #include <barrier>
+#include <cstring>
 #include <memory>
 #include <mutex>
+#include <optional>
 #include <thread>
 #include <vector>
-#include <cstring>
 
 #include "qsb_exec.cuh"
 
+// One emulated CTA = W worker threads + 1 control thread; the barriers mirror the CUDA named barriers
+// (std::barrier::arrive() = bar.arrive, arrive_and_wait() = bar.sync).
+struct Cta {
+  std::vector<c128> tile;
+  qsb_ctl ctl;
+  std::unique_ptr<std::barrier<>> full[QSB_RING], empty[QSB_RING], workers, all;
+};
+
 struct Shared {
-  int C, T, m;
-  std::vector<std::vector<c128>> tiles;
-  std::vector<qsb_ctl> ctls;
-  std::vector<std::unique_ptr<std::barrier<>>> block_bar;
-  std::unique_ptr<std::barrier<>> cluster_bar;
-  std::vector<double> red;   // [C*T][4]
+  int C, W, m;
+  std::vector<std::unique_ptr<Cta>> cta;
+  std::unique_ptr<std::barrier<>> cluster;    // every thread of every CTA of the cluster, like barrier.cluster
   std::mutex mu;
 };
 
 struct HostEnv {
-  int tid, T, rank;
+  static constexpr int CL = 1;
+  int wid, W, rank, C;
+  int cta;                      // index of this CTA's storage (== rank in cluster mode)
+  int lane, warp, nwarps, clane;
+  bool lead;
   Shared* sh;
-  c128* tile() { return sh->tiles[rank].data(); }
-  qsb_ctl* ctl() { return &sh->ctls[rank]; }
-  void sync_block() { sh->block_bar[rank]->arrive_and_wait(); }
-  void sync_cluster() { sh->cluster_bar->arrive_and_wait(); }
-  const c128* peer_tile(int r) { return sh->tiles[r].data(); }
+  std::optional<std::barrier<>::arrival_token> tok;
+
+  Cta& me() { return *sh->cta[cta]; }
+  c128* tile() { return me().tile.data(); }
+  qsb_ctl* ctl() { return &me().ctl; }
+  const c128* peer_tile(int r) { return sh->cta[r]->tile.data(); }
+  const qsb_ctl* peer_ctl(int r) { return C > 1 ? &sh->cta[r]->ctl : &me().ctl; }
   void atomic_add(double* p, double v) { std::lock_guard<std::mutex> g(sh->mu); *p += v; }
-  void allreduce(double* v, int nv) {
-    double* mine = &sh->red[(rank * T + tid) * 4];
-    for (int k = 0; k < nv; ++k) mine[k] = v[k];
-    sync_cluster();
-    for (int k = 0; k < nv; ++k) {
-      double s = 0.0;
-      for (int i = 0; i < sh->C * T; ++i) s += sh->red[i * 4 + k];
-      v[k] = s;
-    }
-    sync_cluster();
-  }
+  double warp_sum(double x) { return x; }     // one-lane "warps"
+  unsigned long long clock() { return 0; }
+  int cta_id() { return cta; }
+  int bcast_i(int x) { return x; }
+  uint64_t bcast_u64(uint64_t x) { return x; }
+  void ring_wait_empty(int s) { me().empty[s]->arrive_and_wait(); }
+  void ring_publish(int s) { (void)me().full[s]->arrive(); }
+  void ring_wait_full(int s) { me().full[s]->arrive_and_wait(); }
+  void ring_release(int s) { (void)me().empty[s]->arrive(); }
+  void sync_workers() { me().workers->arrive_and_wait(); }
+  void sync_control() {}
+  void cluster_sync_w() { sh->cluster->arrive_and_wait(); }
+  void cluster_arrive_c() { tok.emplace(sh->cluster->arrive()); }
+  void cluster_wait_c() { sh->cluster->wait(std::move(*tok)); tok.reset(); }
+  void handoff_w() { if (C > 1) sh->cluster->arrive_and_wait(); else me().all->arrive_and_wait(); }
+  void handoff_c() { if (C > 1) sh->cluster->arrive_and_wait(); else me().all->arrive_and_wait(); }
 };
 
 extern "C" int emu_run(int n, int m, int T, const qsb_op* ops, int64_t n_ops, int64_t ops_stride, const double* cdata, int64_t n_cdata,
@@ -52,22 +69,34 @@ extern "C" int emu_run(int n, int m, int T, const qsb_op* ops, int64_t n_ops, in
                        int64_t uniforms_stride, uint64_t seed, int64_t traj_offset, const int64_t* init_basis,
                        int64_t default_basis, int32_t* branches, int64_t branches_stride, void* snapshots,
                        double* probs_accum) {
-  if (n < 1 || n > QSB_MAX_QUBITS || m < 1 || m > n || n - m > 3 || T < 1) return -1;
+  if (n < 1 || n > 30 || m < 1 || m > n || m > QSB_MAX_LOCAL_BITS || T < 1) return -1;
+  const bool streaming = (n - m > 3) || n > QSB_MAX_QUBITS;
   Shared sh;
-  sh.C = 1 << (n - m);
-  sh.T = T;
+  sh.C = streaming ? 1 : 1 << (n - m);
+  sh.W = T;
   sh.m = m;
-  sh.tiles.assign(sh.C, std::vector<c128>((size_t)1 << m));
-  sh.ctls.resize(sh.C);
-  for (int r = 0; r < sh.C; ++r) sh.block_bar.emplace_back(new std::barrier<>(T));
-  sh.cluster_bar.reset(new std::barrier<>(sh.C * T));
-  sh.red.assign((size_t)sh.C * T * 4, 0.0);
+  // streaming mode: two independent "CTAs" stride over the tiles (no cluster)
+  const int n_cta = streaming ? 2 : sh.C;
+  for (int r = 0; r < n_cta; ++r) {
+    sh.cta.emplace_back(new Cta());
+    Cta& c = *sh.cta.back();
+    c.tile.assign((size_t)1 << m, c128{0.0, 0.0});
+    memset(&c.ctl, 0, sizeof c.ctl);
+    for (int s = 0; s < QSB_RING; ++s) {
+      c.full[s].reset(new std::barrier<>(T + 1));
+      c.empty[s].reset(new std::barrier<>(T + 1));
+    }
+    c.workers.reset(new std::barrier<>(T));
+    c.all.reset(new std::barrier<>(T + 1));
+  }
+  sh.cluster.reset(new std::barrier<>(sh.C * (T + 1)));
 
   qsb_exec_args a;
   memset(&a, 0, sizeof a);
   a.ops = ops; a.n_ops = n_ops; a.ops_stride = ops_stride; a.cdata = cdata; a.n_cdata = n_cdata; a.idata = idata;
   a.n = n; a.m = m; a.load_perm = load_perm; a.store_perm = store_perm; a.n_snapshots = n_snapshots;
   a.flags = flags; a.states = (c128*)states; a.count = count;
+  a.tile_bits = streaming ? n - m : 0;
   a.params = params; a.params_stride = params_stride;
   a.uniforms = uniforms; a.uniforms_stride = uniforms_stride;
   a.seed = seed; a.traj_offset = traj_offset;
@@ -76,11 +105,16 @@ extern "C" int emu_run(int n, int m, int T, const qsb_op* ops, int64_t n_ops, in
   a.snapshots = (c128*)snapshots; a.probs_accum = probs_accum;
 
   std::vector<std::thread> th;
-  for (int r = 0; r < sh.C; ++r)
-    for (int t = 0; t < T; ++t)
-      th.emplace_back([&sh, &a, r, t, T]() {
-        HostEnv env{t, T, r, &sh};
-        for (int64_t j = 0; j < a.count; ++j) qsb_exec_trajectory(env, a, j);
+  for (int r = 0; r < n_cta; ++r)
+    for (int t = 0; t <= T; ++t)
+      th.emplace_back([&sh, &a, r, t, T, streaming, n_cta]() {
+        HostEnv env;
+        env.sh = &sh; env.cta = r; env.rank = streaming ? 0 : r; env.C = sh.C; env.W = T;
+        env.wid = t < T ? t : -1;
+        env.lane = 0; env.warp = t; env.nwarps = T; env.clane = 0; env.lead = true;
+        if (env.wid >= 0) qsb_worker_loop(env, a);
+        else if (streaming) qsb_control_loop(env, a, r, n_cta);
+        else qsb_control_loop(env, a, 0, 1);
       });
   for (auto& x : th) x.join();
   return 0;

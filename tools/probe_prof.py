@@ -1,0 +1,39 @@
+"""Executor cycle-counter probe (developer tool): where do workers / the control warp spend their cycles?"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "quantum-simulator_b200"), os.path.join(ROOT, "tests")]
+import numpy as np
+from qsb import capi
+from tools.probe_traj import prog_for, ctx   # noqa  (runs its table first)
+from qsb.workloads import config3_noise
+
+KINDS = ["exit", "init", "sweep", "remap", "gflush", "rdm1", "store", "?"]
+
+
+def prof(label, prog, T):
+    dim = 1 << prog.n
+    dp = ctx.program(prog)
+    states = ctx.alloc(T * dim * 16)
+    kw = {}
+    if prog.n_draws:
+        u = np.random.default_rng(0).random((T, prog.n_draws))
+        kw.update(uniforms=ctx.to_device(u), uniforms_stride=prog.n_draws)
+    ctx.profile(True)
+    ctx.run(dp, T, states=states, **kw)
+    p = ctx.profile(True, read=True).astype(np.float64)
+    ctx.profile(False)
+    C = 1 << (prog.n - prog.m)
+    units = max(1, T // (len(p) // C))
+    p0 = p[0] / units
+    print(f"--- {label}: CTAs={len(p)} units/cluster={units}  per unit, CTA 0 (cycles):")
+    print(f"   control total {p0[18]:10.0f}   ring-full wait {p0[17]:10.0f}   descriptors {p0[19]:7.1f}")
+    print(f"   worker wait   {p0[0]:10.0f}")
+    for k, name in enumerate(KINDS):
+        if p0[9 + k]:
+            print(f"   {name:7s} n={p0[9 + k]:7.1f}  busy {p0[1 + k]:10.0f}  ({p0[1 + k] / p0[9 + k]:8.0f} / desc)")
+
+
+noise = config3_noise()
+prof("16q noisy", prog_for(16, 64, noise), 150)
+prof("16q noiseless", prog_for(16, 64, None), 150)
+prof("13q noisy", prog_for(13, 64, noise), 1480)
