@@ -166,7 +166,7 @@ int qsb_program_free(qsb_program* prog);
 int qsb_run(qsb_program* prog, const qsb_run_args* args);
 /* developer aid: per-CTA cycle counters of the executor kernel (worker wait / busy per descriptor kind,
  * control-warp stalls); enable != 0 switches them on for later qsb_run calls; out (may be NULL) receives
- * unsigned long long[ctas][32] of the last run; returns the number of CTAs copied or a negative error */
+ * unsigned long long[ctas][128] of the last run; returns the number of CTAs copied or a negative error */
 int qsb_debug_profile(qsb_ctx* ctx, int enable, unsigned long long* out, int64_t max_ctas);
 
 /* ---- reductions over stored (reference-order) states ---------------------------- */

@@ -533,6 +533,7 @@ int qsb_run(qsb_program* p, const qsb_run_args* r) {
   a.probs_accum = (r->flags & QSB_RUN_ACCUM_PROBS) ? (double*)r->probs_accum->ptr : nullptr;
 
   a.prof = ctx->d_prof;
+  if (ctx->d_prof) CU(ctx, cudaMemsetAsync(ctx->d_prof, 0, (size_t)8 * 148 * 4 * QSB_PROF_WORDS * sizeof(unsigned long long), ctx->stream));
   a.tile_bits = p->tile_bits;
   if (p->tile_bits) {
     if (r->flags & QSB_RUN_NORMALIZE)
@@ -576,14 +577,14 @@ int qsb_debug_profile(qsb_ctx* ctx, int enable, unsigned long long* out, int64_t
   CU(ctx, cudaSetDevice(ctx->device));
   const int64_t cap = 8 * 148 * 4;
   if (enable && !ctx->d_prof) {
-    CU(ctx, cudaMalloc(&ctx->d_prof, cap * 32 * sizeof(unsigned long long)));
-    CU(ctx, cudaMemset(ctx->d_prof, 0, cap * 32 * sizeof(unsigned long long)));
+    CU(ctx, cudaMalloc(&ctx->d_prof, cap * QSB_PROF_WORDS * sizeof(unsigned long long)));
+    CU(ctx, cudaMemset(ctx->d_prof, 0, cap * QSB_PROF_WORDS * sizeof(unsigned long long)));
   }
   int n = 0;
   if (out && ctx->d_prof) {
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     n = ctx->prof_ctas < max_ctas ? ctx->prof_ctas : (int)max_ctas;
-    CU(ctx, cudaMemcpy(out, ctx->d_prof, (size_t)n * 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CU(ctx, cudaMemcpy(out, ctx->d_prof, (size_t)n * QSB_PROF_WORDS * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   }
   if (!enable && ctx->d_prof) {
     cudaFree(ctx->d_prof);

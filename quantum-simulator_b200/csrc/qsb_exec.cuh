@@ -56,6 +56,10 @@ struct alignas(16) c128 { double x, y; };
 #define QSB_AD_MARGIN 1e-10
 #define QSB_CHUNK 128          // ops staged in shared memory per refill
 #define QSB_REMAP_REGS 16      // amplitudes a thread stages per remap / rank-bit flush round
+#ifndef QSB_GROUP_POS
+#define QSB_GROUP_POS 1        // 1: bank-conflict-free group order (qsb_group_order), 0: ascending free bits
+#endif
+#define QSB_PROF_WORDS 128
 #define QSB_RING 4             // descriptors in flight between control warp and workers
 
 struct qsb_exec_args {
@@ -79,7 +83,7 @@ struct qsb_exec_args {
   int32_t* branches;      int64_t branches_stride;
   c128* snapshots;
   double* probs_accum;
-  unsigned long long* prof;   // optional cycle counters, 32 per CTA (qsb_debug_profile), or NULL
+  unsigned long long* prof;   // optional cycle counters, QSB_PROF_WORDS per CTA (qsb_debug_profile), or NULL
 };
 
 // ---- descriptors: control warp -> workers ---------------------------------------------
@@ -99,6 +103,9 @@ struct alignas(16) qsb_desc {
   c128* gptr;              // INIT: source state (LOAD) ; STORE: destination (or NULL)
   double* probs;           // STORE: |psi|^2 accumulation target (or NULL)
   int64_t tile;            // INIT / STORE: value of the non-resident index bits (cluster rank or tile id)
+  int8_t pos[16];          // SWEEP: index bit that bit t of the group number lands on (bank-conflict-free order)
+  int32_t hmask;           // SWEEP: index bits the group-number bits above log2(W) land on (ascending)
+  int32_t pad1[3];
   c128 P[3][4];            // pending matrices (row-major), valid where cls != NONE
   c128 mat[64];            // dense 4x4 / 8x8 gate of this sweep
 };
@@ -185,6 +192,32 @@ QSB_HD int qsb_choice(const double* p, int k, double u) {
   return idx < k ? idx : k - 1;
 }
 
+// Order in which the bits of a group number are laid onto the non-target index bits of the tile.
+// The swizzled slot of index i has 16-byte bank group (i0^i3, i1^i4, i2^i5); the 8 lanes of a
+// quarter-warp differ in group bits 0..2, so these go to one free position out of each pair
+// {0,3}, {1,4}, {2,5}: every LDS.128 / STS.128 of a sweep is then conflict-free whatever the targets
+// (unless the targets cover both members of a pair).  The remaining positions follow in ascending order.
+QSB_HD void qsb_group_order(int m, int nb, const int* bits, int8_t* pos) {
+  uint32_t used = 0;
+  for (int k = 0; k < nb; ++k) used |= 1u << bits[k];
+  int cnt = 0;
+  for (int j = 0; j < 3; ++j) {
+    int q = -1;
+    if (j < m && !((used >> j) & 1u)) q = j;
+    else if (j + 3 < m && !((used >> (j + 3)) & 1u)) q = j + 3;
+    if (q >= 0) { pos[cnt++] = (int8_t)q; used |= 1u << q; }
+  }
+  for (int q = 0; q < m; ++q)
+    if (!((used >> q) & 1u)) pos[cnt++] = (int8_t)q;
+  for (; cnt < 16; ++cnt) pos[cnt] = 0;
+}
+// deposit the low `nbits` bits of g onto the positions pos[0..nbits)
+QSB_HD int qsb_deposit(int g, const int8_t* pos, int nbits) {
+  int r = 0;
+  for (int t = 0; t < nbits; ++t) r |= ((g >> t) & 1) << pos[t];
+  return r;
+}
+
 // bit-permutation byte tables: index x (<= 32 bits) -> OR_j bit_j(x) << perm[j]
 QSB_HD uint32_t qsb_permute(const uint32_t* tab, uint32_t x) {
   return tab[x & 255] | tab[256 + ((x >> 8) & 255)] | tab[512 + ((x >> 16) & 255)] | tab[768 + (x >> 24)];
@@ -195,15 +228,33 @@ QSB_HD uint32_t qsb_permute(const uint32_t* tab, uint32_t x) {
 // =========================================================================================
 
 // One sweep over the tile for K slot bits (d->b[0] = MSB of the local index r): apply the pending 2x2 of
-// every bit whose class is not NONE, then gate G.  Each worker owns whole 2^K groups.
-template <int K, int G, class Env>
+// every bit whose class is not NONE, then gate G.  Each worker owns whole 2^K groups and keeps 16
+// amplitudes (NG groups) in registers per step: all loads are issued before the arithmetic, and the
+// (CTA-uniform) class branches are taken once per step instead of once per group.
+// amplitudes a worker keeps in registers per step: 16 (all loads in flight before the arithmetic); 8 for K = 3,
+// where 16 amplitudes plus three dense pending matrices would spill (measured: profiles/README.md)
+template <int K, bool DG, class Env>
 QSB_PASS void qsb_sweep(Env& env, int m, const qsb_desc* d) {
   c128* tile = env.tile();          // re-derived here so device code keeps the shared address space (LDS/STS)
   constexpr int D = 1 << K;
-  int bits[K], sb[K], cls[K];
+  constexpr int NG = DG ? (K == 2 ? 2 : 1) : (K == 3 ? 1 : 16 / D);
+  const int G = d->gate;
+  int bits[K], cls[K];
 #pragma unroll
-  for (int k = 0; k < K; ++k) { bits[k] = d->b[k]; sb[k] = bits[k]; cls[k] = d->cls[k]; }
+  for (int k = 0; k < K; ++k) { bits[k] = d->b[k]; cls[k] = d->cls[k]; }
+  // group g = wid + j W (W = 2^wbits): the bits of wid are laid onto the tile index once per sweep; the
+  // bits of j land on `hmask` in ascending order, so consecutive j are a masked increment
+#if QSB_GROUP_POS
+  const int wbits = env.wbits;
+  const int lo_base = qsb_deposit(env.wid, d->pos, wbits < m - K ? wbits : m - K);
+  const int hmask = d->hmask;
+  int hi = 0;
+#else
+  int sb[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) sb[k] = bits[k];
   qsb_sort_bits<K>(sb);
+#endif
   int off[D];
 #pragma unroll
   for (int r = 0; r < D; ++r) {
@@ -219,71 +270,89 @@ QSB_PASS void qsb_sweep(Env& env, int m, const qsb_desc* d) {
     for (int e = 0; e < 4; ++e) P[k][e] = d->P[k][e];
   }
   const int cnt = 1 << (m - K);
-#pragma unroll 2
-  for (int g = env.wid; g < cnt; g += env.W) {
-    int base = g;
+  for (int g0 = env.wid; g0 < cnt; g0 += NG * env.W) {
+    c128 a[NG][D];
+    int base[NG];
 #pragma unroll
-    for (int k = 0; k < K; ++k) base = qsb_ins0(base, sb[k]);
-    c128 a[D];
+    for (int j = 0; j < NG; ++j) {
+#if QSB_GROUP_POS
+      const int bs = lo_base | hi;        // out-of-range groups of a short tile wrap onto valid ones (never stored)
+      hi = ((hi | ~hmask) + 1) & hmask;
+#else
+      const int g = g0 + j * env.W;
+      int bs = g < cnt ? g : g0;          // out-of-range groups of the last step alias a valid one (never stored)
 #pragma unroll
-    for (int r = 0; r < D; ++r) a[r] = tile[qsb_slot(base | off[r])];
+      for (int k = 0; k < K; ++k) bs = qsb_ins0(bs, sb[k]);
+#endif
+      base[j] = bs;
+#pragma unroll
+      for (int r = 0; r < D; ++r) a[j][r] = tile[qsb_slot(bs | off[r])];
+    }
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       const int bit = 1 << (K - 1 - k);
-      if (cls[k] == QSB_CLS_DENSE) {
+      if (cls[k] >= QSB_CLS_DIAG) {          // complex-diagonal matrices take the dense path (keeps the code small)
 #pragma unroll
-        for (int r = 0; r < D; ++r) {
-          if (r & bit) continue;
-          c128 lo = a[r], hi = a[r | bit];
-          a[r] = qsb_fma(P[k][1], hi, qsb_mul(P[k][0], lo));
-          a[r | bit] = qsb_fma(P[k][3], hi, qsb_mul(P[k][2], lo));
-        }
-      } else if (cls[k] == QSB_CLS_DIAG) {
+        for (int j = 0; j < NG; ++j)
 #pragma unroll
-        for (int r = 0; r < D; ++r) a[r] = qsb_mul((r & bit) ? P[k][3] : P[k][0], a[r]);
+          for (int r = 0; r < D; ++r) {
+            if (r & bit) continue;
+            c128 lo = a[j][r], hi = a[j][r | bit];
+            a[j][r] = qsb_fma(P[k][1], hi, qsb_mul(P[k][0], lo));
+            a[j][r | bit] = qsb_fma(P[k][3], hi, qsb_mul(P[k][2], lo));
+          }
       } else if (cls[k] == QSB_CLS_RDIAG) {
-        const double s = P[k][3].x;
+        const double sc = P[k][3].x;
 #pragma unroll
-        for (int r = 0; r < D; ++r) if (r & bit) { a[r].x *= s; a[r].y *= s; }
+        for (int j = 0; j < NG; ++j)
+#pragma unroll
+          for (int r = 0; r < D; ++r) if (r & bit) { a[j][r].x *= sc; a[j][r].y *= sc; }
       }
     }
-    if (G == QSB_G_DENSE) {
+    if (DG) {
       // every output row is written straight to the tile: the group is owned by this thread and all of
       // its inputs are already in registers
 #pragma unroll
       for (int r = 0; r < D; ++r) {
-        c128 acc = qsb_mul(d->mat[r * D], a[0]);
+        c128 acc[NG];
 #pragma unroll
-        for (int c = 1; c < D; ++c) acc = qsb_fma(d->mat[r * D + c], a[c], acc);
-        tile[qsb_slot(base | off[r])] = acc;
+        for (int c = 0; c < D; ++c) {
+          const c128 mv = d->mat[r * D + c];
+#pragma unroll
+          for (int j = 0; j < NG; ++j) acc[j] = c == 0 ? qsb_mul(mv, a[j][0]) : qsb_fma(mv, a[j][c], acc[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < NG; ++j)
+          if (g0 + j * env.W < cnt) tile[qsb_slot(base[j] | off[r])] = acc[j];
       }
       continue;
     }
-    if (G == QSB_G_CX) { c128 t = a[2]; a[2] = a[3]; a[3] = t; }                  // b[0] control, b[1] target
-    else if (G == QSB_G_CZ) { a[3] = qsb_neg(a[3]); }
-    else if (G == QSB_G_SWAP) { c128 t = a[1]; a[1] = a[2]; a[2] = t; }
-    else if (G == QSB_G_CCX) { c128 t = a[D - 2]; a[D - 2] = a[D - 1]; a[D - 1] = t; }   // 110 <-> 111
-    else if (G == QSB_G_CSWAP) { c128 t = a[(D >> 1) | 1]; a[(D >> 1) | 1] = a[(D >> 1) | 2]; a[(D >> 1) | 2] = t; }  // 101 <-> 110
 #pragma unroll
-    for (int r = 0; r < D; ++r) tile[qsb_slot(base | off[r])] = a[r];
+    for (int j = 0; j < NG; ++j) {
+      c128* x = a[j];
+      // the gate is a CTA-uniform run-time choice: one sweep body per K keeps the instruction footprint small
+      if (K == 2) {
+        if (G == QSB_G_CX) { c128 t = x[2]; x[2] = x[3]; x[3] = t; }                // b[0] control, b[1] target
+        else if (G == QSB_G_CZ) { x[3] = qsb_neg(x[3]); }
+        else if (G == QSB_G_SWAP) { c128 t = x[1]; x[1] = x[2]; x[2] = t; }
+      } else if (K == 3) {
+        if (G == QSB_G_CCX) { c128 t = x[D - 2]; x[D - 2] = x[D - 1]; x[D - 1] = t; }   // 110 <-> 111
+        else if (G == QSB_G_CSWAP) { c128 t = x[(D >> 1) | 1]; x[(D >> 1) | 1] = x[(D >> 1) | 2]; x[(D >> 1) | 2] = t; }  // 101 <-> 110
+      }
+      if (g0 + j * env.W < cnt) {
+#pragma unroll
+        for (int r = 0; r < D; ++r) tile[qsb_slot(base[j] | off[r])] = x[r];
+      }
+    }
   }
 }
 
 template <class Env>
 QSB_HD void qsb_do_sweep(Env& env, int m, const qsb_desc* d) {
-  switch (d->k * 8 + d->gate) {
-    case 1 * 8 + QSB_G_NONE:  qsb_sweep<1, QSB_G_NONE>(env, m, d); break;
-    case 2 * 8 + QSB_G_NONE:  qsb_sweep<2, QSB_G_NONE>(env, m, d); break;
-    case 3 * 8 + QSB_G_NONE:  qsb_sweep<3, QSB_G_NONE>(env, m, d); break;
-    case 2 * 8 + QSB_G_CX:    qsb_sweep<2, QSB_G_CX>(env, m, d); break;
-    case 2 * 8 + QSB_G_CZ:    qsb_sweep<2, QSB_G_CZ>(env, m, d); break;
-    case 2 * 8 + QSB_G_SWAP:  qsb_sweep<2, QSB_G_SWAP>(env, m, d); break;
-    case 2 * 8 + QSB_G_DENSE: qsb_sweep<2, QSB_G_DENSE>(env, m, d); break;
-    case 3 * 8 + QSB_G_CCX:   qsb_sweep<3, QSB_G_CCX>(env, m, d); break;
-    case 3 * 8 + QSB_G_CSWAP: qsb_sweep<3, QSB_G_CSWAP>(env, m, d); break;
-    case 3 * 8 + QSB_G_DENSE: qsb_sweep<3, QSB_G_DENSE>(env, m, d); break;
-    default: break;
-  }
+  const bool dg = d->gate == QSB_G_DENSE;
+  if (d->k == 1) qsb_sweep<1, false>(env, m, d);
+  else if (d->k == 2) { if (dg) qsb_sweep<2, true>(env, m, d); else qsb_sweep<2, false>(env, m, d); }
+  else if (d->k == 3) { if (dg) qsb_sweep<3, true>(env, m, d); else qsb_sweep<3, false>(env, m, d); }
 }
 
 // sum v[0..nv) over the workers of this CTA; every worker gets the bit-identical result
@@ -358,6 +427,9 @@ QSB_PASS void qsb_do_init(Env& env, const qsb_exec_args& a, const qsb_desc* d) {
       const uint32_t s = hoist ? (qsb_permute(tab, x & ~31u) | lo) : qsb_permute(tab, x);
       tile[qsb_slot(i)] = src[s];
     }
+    // LOAD + STORE run in place and the two bit permutations differ, so a CTA's stores land on addresses
+    // another CTA of the cluster loads from: nobody may go on before every CTA has its tile
+    if (env.C > 1) env.cluster_sync_w();
   } else {
     const uint32_t basis = (uint32_t)d->basis;
     for (int i = env.wid; i < (1 << m); i += env.W) {
@@ -415,7 +487,9 @@ QSB_PASS void qsb_do_remap(Env& env, int m, const qsb_desc* d) {
   const c128* peer = env.peer_tile(env.rank ^ (1 << gb));
   c128 val[QSB_REMAP_REGS];
   const int cnt = 1 << (m - 1);
+  const unsigned long long pt0 = env.prof_on() ? env.clock() : 0;
   env.cluster_sync_w();                       // every CTA finished the sweeps before the exchange
+  if (env.prof_on()) env.prof_add(120, env.clock() - pt0);
   // Round r pulls the partner's groups g and then overwrites OUR groups g (the ones the partner pulls
   // in the same round), so one cluster barrier between the two halves of a round is enough.
   for (int base = 0; base < cnt; base += QSB_REMAP_REGS * env.W) {
@@ -473,11 +547,15 @@ QSB_HD void qsb_worker_loop(Env& env, const qsb_exec_args& a) {
   const int m = a.m;
   int parity = 0;
   const bool prof = a.prof != nullptr && env.wid == 0;
+  const bool wprof = a.prof != nullptr && env.lane == 0;      // per-warp busy / wait cycles
+  unsigned long long wb = 0, ww = 0, w0 = 0, w1 = 0;
   unsigned long long pw = 0, pb[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pn[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t0 = 0, t1 = 0;
   for (uint32_t seq = 0;; ++seq) {
     const int slot = (int)(seq % QSB_RING);
     if (prof) t0 = env.clock();
+    if (wprof) w0 = env.clock();
     env.ring_wait_full(slot);               // also: every worker finished the previous descriptor
+    if (wprof) { w1 = env.clock(); ww += w1 - w0; }
     if (prof) { t1 = env.clock(); pw += t1 - t0; }
     const qsb_desc* d = &env.ctl()->ring[slot];
     const int kind = d->kind;
@@ -500,11 +578,27 @@ QSB_HD void qsb_worker_loop(Env& env, const qsb_exec_args& a) {
       default: break;
     }
     env.ring_release(slot);
-    if (prof) { pb[kind & 7] += env.clock() - t1; pn[kind & 7] += 1; }
+    if (wprof) wb += env.clock() - w1;
+    if (prof) {
+      const unsigned long long dt = env.clock() - t1;
+      pb[kind & 7] += dt; pn[kind & 7] += 1;
+      if (kind == QSB_D_SWEEP) {          // per sweep variant (k * 8 + gate) and per number of dense pending matrices
+        unsigned long long* o = a.prof + (size_t)env.cta_id() * QSB_PROF_WORDS;
+        const int key = (d->k * 8 + d->gate) & 31;
+        int nd = 0;
+        for (int k = 0; k < d->k; ++k) nd += d->cls[k] == QSB_CLS_DENSE;
+        o[32 + key] += dt; o[64 + key] += 1;
+        o[96 + nd] += dt; o[100 + nd] += 1;
+      }
+    }
     if (kind == QSB_D_EXIT) break;
   }
+  if (wprof && env.warp < 8) {
+    unsigned long long* o = a.prof + (size_t)env.cta_id() * QSB_PROF_WORDS;
+    o[104 + env.warp] = wb; o[112 + env.warp] = ww;
+  }
   if (prof) {
-    unsigned long long* o = a.prof + (size_t)env.cta_id() * 32;
+    unsigned long long* o = a.prof + (size_t)env.cta_id() * QSB_PROF_WORDS;
     o[0] = pw;
     for (int k = 0; k < 8; ++k) { o[1 + k] = pb[k]; o[9 + k] = pn[k]; }
   }
@@ -576,7 +670,7 @@ QSB_HD void qsb_cluster_event(Env& env, qsb_cstate& st) {
 
 // publish one sweep over `nb` local bits (bits[0] = MSB of the gate index) and reset their pending matrices
 template <class Env>
-QSB_CTL void qsb_emit_sweep(Env& env, qsb_cstate& st, int gate, int nb, const int* bits, const c128* mat_src) {
+QSB_CTL void qsb_emit_sweep(Env& env, qsb_cstate& st, int m, int gate, int nb, const int* bits, const c128* mat_src) {
   qsb_desc* d = qsb_desc_begin(env, st);
   qsb_ctl* ctl = env.ctl();
   if (env.lead) {
@@ -587,6 +681,10 @@ QSB_CTL void qsb_emit_sweep(Env& env, qsb_cstate& st, int gate, int nb, const in
       for (int e = 0; e < 4; ++e) d->P[k][e] = ctl->pend[b][e];
       if (cls != QSB_CLS_NONE) qsb_pend_identity(ctl->pend[b]);
     }
+    qsb_group_order(m, nb, bits, d->pos);
+    int hm = 0;
+    for (int t = env.wbits; t < m - nb; ++t) hm |= 1 << d->pos[t];
+    d->hmask = hm;
   }
   if (mat_src) {
     const int cnt = 1 << (2 * nb);
@@ -610,7 +708,7 @@ QSB_CTL void qsb_flush(Env& env, qsb_cstate& st, int m, uint32_t which) {
       bits[nb++] = b;
       todo &= ~(1u << b);
     }
-    qsb_emit_sweep(env, st, QSB_G_NONE, nb, bits, (const c128*)nullptr);
+    qsb_emit_sweep(env, st, m, QSB_G_NONE, nb, bits, (const c128*)nullptr);
   }
   uint32_t gtodo = m >= 32 ? 0u : (pending >> m);
   for (int gb = 0; gtodo; ++gb, gtodo >>= 1) {
@@ -790,13 +888,13 @@ QSB_CTL void qsb_control_slow(Env& env, const qsb_exec_args& a, qsb_cstate& st, 
       int bits[2] = {op.b0, op.b1};
       const int g = op.kind == QSB_OP_CX ? QSB_G_CX : op.kind == QSB_OP_CZ ? QSB_G_CZ :
                     op.kind == QSB_OP_SWAP ? QSB_G_SWAP : QSB_G_DENSE;
-      qsb_emit_sweep(env, st, g, 2, bits, op.kind == QSB_OP_U2 ? (const c128*)(a.cdata + op.data) : (const c128*)nullptr);
+      qsb_emit_sweep(env, st, m, g, 2, bits, op.kind == QSB_OP_U2 ? (const c128*)(a.cdata + op.data) : (const c128*)nullptr);
       break;
     }
     case QSB_OP_CCX: case QSB_OP_CSWAP: case QSB_OP_U3Q: {
       int bits[3] = {op.b0, op.b1, op.b2};
       const int g = op.kind == QSB_OP_CCX ? QSB_G_CCX : op.kind == QSB_OP_CSWAP ? QSB_G_CSWAP : QSB_G_DENSE;
-      qsb_emit_sweep(env, st, g, 3, bits, op.kind == QSB_OP_U3Q ? (const c128*)(a.cdata + op.data) : (const c128*)nullptr);
+      qsb_emit_sweep(env, st, m, g, 3, bits, op.kind == QSB_OP_U3Q ? (const c128*)(a.cdata + op.data) : (const c128*)nullptr);
       break;
     }
     case QSB_OP_REMAP: {
@@ -853,6 +951,7 @@ QSB_HD void qsb_control_unit(Env& env, qsb_cstate& st, const qsb_exec_args& a, i
       d->gptr = a.states ? a.states + t * st.dim : nullptr;
     }
     qsb_desc_end(env, st);
+    if (a.flags & QSB_RUN_LOAD) qsb_cluster_event(env, st);     // matches the barrier at the end of a LOAD
   }
 
   for (int64_t pc0 = 0; pc0 < a.n_ops; pc0 += QSB_CHUNK) {
@@ -915,7 +1014,7 @@ QSB_HD void qsb_control_loop(Env& env, const qsb_exec_args& a, int64_t first, in
   const int64_t total = a.count << a.tile_bits;
   for (int64_t u = first; u < total; u += stride) qsb_control_unit(env, st, a, u);
   if (st.prof && env.lead) {
-    unsigned long long* o = a.prof + (size_t)env.cta_id() * 32;
+    unsigned long long* o = a.prof + (size_t)env.cta_id() * QSB_PROF_WORDS;
     o[17] = st.ring_wait;
     o[18] = env.clock() - c0;
     o[19] = st.seq;

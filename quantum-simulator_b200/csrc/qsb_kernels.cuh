@@ -40,13 +40,14 @@ template <int CS>
 struct DeviceEnv {
   static constexpr int C = CS;
   static constexpr int CL = QSB_CTL_THREADS;
-  int wid, W, rank, m_;
+  int wid, W, wbits, rank, m_;
   int lane, warp, nwarps;      // worker warp geometry
   int clane;                   // lane inside the control warp
   bool lead;                   // the control lane that writes shared state
 
   __device__ DeviceEnv(int m) {
-    W = (int)blockDim.x - QSB_CTL_THREADS;
+    W = (int)blockDim.x - QSB_CTL_THREADS;      // a power of two >= 32
+    wbits = 31 - __clz(W);
     const int tid = threadIdx.x;
     wid = tid < W ? tid : -1;
     lane = tid & 31;
@@ -74,6 +75,9 @@ struct DeviceEnv {
     return x;
   }
   __device__ __forceinline__ unsigned long long clock() { return (unsigned long long)clock64(); }
+  unsigned long long* prof_;
+  __device__ __forceinline__ bool prof_on() { return prof_ != nullptr && threadIdx.x == 0; }
+  __device__ __forceinline__ void prof_add(int slot, unsigned long long v) { prof_[(size_t)blockIdx.x * QSB_PROF_WORDS + slot] += v; }
   __device__ __forceinline__ int cta_id() { return (int)blockIdx.x; }
   // lane 0 of the control warp -> every lane
   __device__ __forceinline__ int bcast_i(int x) { return __shfl_sync(0xffffffffu, x, 0); }
@@ -110,6 +114,7 @@ template <int CS>
 __global__ void __launch_bounds__(QSB_MAX_WORKERS + QSB_CTL_THREADS, 1)
 qsb_traj_kernel(const __grid_constant__ qsb_exec_args a) {
   DeviceEnv<CS> env(a.m);
+  env.prof_ = a.prof;
   if (env.wid >= 0) {
     qsb_worker_loop(env, a);
   } else {

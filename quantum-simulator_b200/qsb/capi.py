@@ -255,7 +255,7 @@ class Context:
 
     def profile(self, enable=True, read=False):
         """Developer aid: executor cycle counters (see qsb_debug_profile); returns uint64[ctas][32] when read."""
-        out = np.zeros((8 * 148 * 4, 32), dtype=np.uint64) if read else None
+        out = np.zeros((8 * 148 * 4, 128), dtype=np.uint64) if read else None
         n = self.lib.qsb_debug_profile(self.handle, 1 if enable else 0, _hostptr(out) if read else None,
                                        out.shape[0] if read else 0)
         if n < 0:

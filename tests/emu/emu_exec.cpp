@@ -32,7 +32,7 @@ struct Shared {
 
 struct HostEnv {
   static constexpr int CL = 1;
-  int wid, W, rank, C;
+  int wid, W, wbits, rank, C;
   int cta;                      // index of this CTA's storage (== rank in cluster mode)
   int lane, warp, nwarps, clane;
   bool lead;
@@ -47,6 +47,8 @@ struct HostEnv {
   void atomic_add(double* p, double v) { std::lock_guard<std::mutex> g(sh->mu); *p += v; }
   double warp_sum(double x) { return x; }     // one-lane "warps"
   unsigned long long clock() { return 0; }
+  bool prof_on() { return false; }
+  void prof_add(int, unsigned long long) {}
   int cta_id() { return cta; }
   int bcast_i(int x) { return x; }
   uint64_t bcast_u64(uint64_t x) { return x; }
@@ -69,7 +71,7 @@ extern "C" int emu_run(int n, int m, int T, const qsb_op* ops, int64_t n_ops, in
                        int64_t uniforms_stride, uint64_t seed, int64_t traj_offset, const int64_t* init_basis,
                        int64_t default_basis, int32_t* branches, int64_t branches_stride, void* snapshots,
                        double* probs_accum) {
-  if (n < 1 || n > 30 || m < 1 || m > n || m > QSB_MAX_LOCAL_BITS || T < 1) return -1;
+  if (n < 1 || n > 30 || m < 1 || m > n || m > QSB_MAX_LOCAL_BITS || T < 8 || T > 32 || (T & (T - 1))) return -1;   // W: power of two >= 8
   const bool streaming = (n - m > 3) || n > QSB_MAX_QUBITS;
   Shared sh;
   sh.C = streaming ? 1 : 1 << (n - m);
@@ -109,7 +111,7 @@ extern "C" int emu_run(int n, int m, int T, const qsb_op* ops, int64_t n_ops, in
     for (int t = 0; t <= T; ++t)
       th.emplace_back([&sh, &a, r, t, T, streaming, n_cta]() {
         HostEnv env;
-        env.sh = &sh; env.cta = r; env.rank = streaming ? 0 : r; env.C = sh.C; env.W = T;
+        env.sh = &sh; env.cta = r; env.rank = streaming ? 0 : r; env.C = sh.C; env.W = T; env.wbits = T == 8 ? 3 : T == 16 ? 4 : 5;
         env.wid = t < T ? t : -1;
         env.lane = 0; env.warp = t; env.nwarps = T; env.clane = 0; env.lead = true;
         if (env.wid >= 0) qsb_worker_loop(env, a);

@@ -71,7 +71,7 @@ def emu_run(prog, count=1, T=2, states=None, params=None, uniforms=None, seed=0,
     branches = np.full((count, max(prog.n_draws, 1)), -1, dtype=np.int32) if want_branches else None
     snaps = np.zeros((count, max(prog.n_snapshots, 1), dim), dtype=np.complex128) if prog.n_snapshots else None
     rc = lib().emu_run(
-        ctypes.c_int(prog.n), ctypes.c_int(prog.m), ctypes.c_int(T), _p(ops), ctypes.c_int64(len(ops)),
+        ctypes.c_int(prog.n), ctypes.c_int(prog.m), ctypes.c_int(8 if T < 3 else 16), _p(ops), ctypes.c_int64(len(ops)),
         ctypes.c_int64(prog.ops_stride), _p(cdata), ctypes.c_int64(len(cdata)), _p(idata), ctypes.c_int(prog.load_perm),
         ctypes.c_int(prog.store_perm), ctypes.c_int(prog.n_snapshots), ctypes.c_int(flags), _p(states),
         ctypes.c_int64(count), _p(params), ctypes.c_int64(params.shape[1] if params is not None else 0),

@@ -25,6 +25,10 @@ def run(label, n, build, T, reps=3, m=None, nops=None):
         ctx.timer_start()
         ctx.run(dp, T, states=states, async_=True, **kw)
         best = min(best, ctx.timer_stop())
+    ctx.profile(True)
+    ctx.run(dp, T, states=states, **kw)
+    pr = ctx.profile(True, read=True).astype(np.float64)[0]
+    ctx.profile(False)
     C = 1 << (prog.n - prog.m)
     units = min(T, (148 // C) if C > 1 else 148)
     if C == 8: units = min(T, 15)
@@ -32,7 +36,8 @@ def run(label, n, build, T, reps=3, m=None, nops=None):
     per_traj = best * 1e-3 / rounds
     k = nops or len(prog.ops)
     print(f"{label:40s} n={n} C={C} ops={len(prog.ops):5d} remaps={prog.n_remaps:4d} {best:8.3f} ms  "
-          f"{per_traj * 1e6:9.1f} us/traj  {per_traj / k * CLK:9.0f} cyc/op", flush=True)
+          f"{per_traj * 1e6:9.1f} us/traj  {per_traj / k * CLK:9.0f} cyc/op | sweep busy/desc "
+          f"{pr[3] / max(pr[11], 1):7.0f} n={pr[11]:5.0f} wwait {pr[0]:9.0f} ctl {pr[18]:9.0f} ringwait {pr[17]:9.0f}", flush=True)
 
 
 N = 400

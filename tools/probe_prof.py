@@ -4,7 +4,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "quantum-simulator_b200"), os.path.join(ROOT, "tests")]
 import numpy as np
 from qsb import capi
-from tools.probe_traj import prog_for, ctx   # noqa  (runs its table first)
+import tools.probe_traj as _pt
+prog_for, ctx = _pt.prog_for, _pt.ctx
 from qsb.workloads import config3_noise
 
 KINDS = ["exit", "init", "sweep", "remap", "gflush", "rdm1", "store", "?"]
@@ -31,9 +32,18 @@ def prof(label, prog, T):
     for k, name in enumerate(KINDS):
         if p0[9 + k]:
             print(f"   {name:7s} n={p0[9 + k]:7.1f}  busy {p0[1 + k]:10.0f}  ({p0[1 + k] / p0[9 + k]:8.0f} / desc)")
+    G = ["none", "cx", "cz", "swap", "ccx", "cswap", "dense", "?"]
+    for key in range(32):
+        if p0[64 + key]:
+            print(f"      sweep k={key // 8} gate={G[key % 8]:6s} n={p0[64 + key]:7.1f}  {p0[32 + key] / p0[64 + key]:8.0f} / desc")
+    print(f"      remap: first cluster barrier {p0[120] / max(p0[12], 1):8.0f} / remap")
+    print("      per-warp busy:", " ".join(f"{p0[104 + w]:9.0f}" for w in range(8)))
+    print("      per-warp wait:", " ".join(f"{p0[112 + w]:9.0f}" for w in range(8)))
+    for nd in range(4):
+        if p0[100 + nd]:
+            print(f"      sweeps with {nd} dense pending: n={p0[100 + nd]:7.1f}  {p0[96 + nd] / p0[100 + nd]:8.0f} / desc")
 
 
 noise = config3_noise()
 prof("16q noisy", prog_for(16, 64, noise), 150)
 prof("16q noiseless", prog_for(16, 64, None), 150)
-prof("13q noisy", prog_for(13, 64, noise), 1480)
