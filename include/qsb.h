@@ -118,6 +118,10 @@ typedef struct qsb_run_args {
   qsb_buffer* probs_accum;   /* double[2^n] or NULL                                         */
   int32_t flags;
   int32_t reserved;
+  qsb_buffer* states_out;    /* STORE destination (same layout as states); NULL = in place.  Needed when a
+                                streamed pass (n - local_bits > 3) stores with a bit permutation other than
+                                the one it loaded with: tiles then read and write different addresses      */
+  int64_t out_first;
 } qsb_run_args;
 
 /* ---- lifecycle --------------------------------------------------------------- */
@@ -152,9 +156,14 @@ int qsb_host_free(void* p);
 /* ---- programs ------------------------------------------------------------------
  * Replaces the per-gate loop of Simulator.run (simulator.py:57-71), NoiseModel.apply
  * (noise.py:212-260) and StateVector.apply_gate (state_vector.py:41-74).
- *   n_qubits <= 16, local_bits = bits resident per CTA (cluster size = 2^(n-local_bits) <= 8,
- *   local_bits <= 13);  load_perm/store_perm = idata offsets of n-entry bit permutations
- *   (slot bit j -> reference-order bit).                                              */
+ *   local_bits = index bits resident per CTA (<= 13).
+ *   RESIDENT mode (n_qubits <= 16 and n_qubits - local_bits <= 3): a cluster of 2^(n-local_bits)
+ *     CTAs holds the whole state in shared memory for the whole program.
+ *   STREAMING mode (otherwise, n_qubits <= 30): the state lives in HBM; one launch = one pass that
+ *     loads every 2^local_bits-amplitude tile, applies the program (all op bits < local_bits) and stores
+ *     it.  No state-dependent Kraus draws, snapshots or normalisation in this mode.
+ *   load_perm/store_perm = idata offsets of n-entry bit permutations (slot bit j -> bit of the
+ *   amplitude index in memory).                                                        */
 int qsb_program_create(qsb_ctx* ctx, int32_t n_qubits, int32_t local_bits,
                        const qsb_op* ops, int64_t n_ops, int64_t ops_stride /*0 = shared*/,
                        int64_t n_programs /*1 if shared*/,

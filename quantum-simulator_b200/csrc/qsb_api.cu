@@ -20,6 +20,7 @@ struct qsb_ctx {
   int64_t launches;
   std::string err;
   uint64_t* d_masks;      // scratch for qsb_masked_parity
+  c128* d_part;                 // partial sums of the large-state reductions
   unsigned long long* d_prof;   // cycle counters of the last qsb_run (qsb_debug_profile), or NULL
   int prof_ctas;
 };
@@ -102,6 +103,7 @@ int qsb_ctx_create(int device, qsb_ctx** out) {
   c->launches = 0;
   c->d_masks = nullptr;
   c->d_prof = nullptr;
+  c->d_part = nullptr;
   c->prof_ctas = 0;
   cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
@@ -124,6 +126,7 @@ int qsb_ctx_destroy(qsb_ctx* ctx) {
   cudaEventDestroy(ctx->ev1);
   cudaFree(ctx->d_masks);
   cudaFree(ctx->d_prof);
+  cudaFree(ctx->d_part);
   delete ctx;
   return QSB_OK;
 }
@@ -478,7 +481,7 @@ int qsb_run(qsb_program* p, const qsb_run_args* r) {
   if (r->count == 0) return QSB_OK;
   const int64_t dim = (int64_t)1 << p->n;
   int rc;
-  if (r->flags & (QSB_RUN_LOAD | QSB_RUN_STORE))
+  if ((r->flags & QSB_RUN_LOAD) || ((r->flags & QSB_RUN_STORE) && !r->states_out))
     if ((rc = need(ctx, r->states, (r->first + r->count) * dim * 16, "states"))) return rc;
   if (p->ops_stride && r->count > p->n_programs)
     return fail(ctx, QSB_E_INVAL, "qsb_run: %lld trajectories but only %lld per-trajectory programs",
@@ -518,6 +521,12 @@ int qsb_run(qsb_program* p, const qsb_run_args* r) {
   a.n_snapshots = p->n_snapshots;
   a.flags = r->flags;
   a.states = r->states ? (c128*)r->states->ptr + r->first * dim : nullptr;
+  a.states_out = a.states;
+  if (r->states_out) {
+    if (r->out_first < 0) return fail(ctx, QSB_E_INVAL, "qsb_run: negative out_first");
+    if ((rc = need(ctx, r->states_out, (r->out_first + r->count) * dim * 16, "states_out"))) return rc;
+    a.states_out = (c128*)r->states_out->ptr + r->out_first * dim;
+  }
   a.count = r->count;
   a.params = r->params ? (const double*)r->params->ptr : nullptr;
   a.params_stride = r->params_stride;
@@ -668,6 +677,20 @@ int qsb_overlap(qsb_ctx* ctx, int32_t n, qsb_buffer* a, int64_t a_first, qsb_buf
   if ((rc = need(ctx, b, (b_first + (b_stride_states ? count : 1)) * dim * 16, "states b"))) return rc;
   if ((rc = need(ctx, out, count * 16, "overlap output"))) return rc;
   CU(ctx, cudaSetDevice(ctx->device));
+  if (dim >= ((int64_t)1 << 18)) {
+    // big states: two-stage reduction over many CTAs, one state pair at a time
+    const int n_part = ctx->sm_count * 8;
+    const int64_t per = (dim + n_part - 1) / n_part;
+    if (!ctx->d_part) CU(ctx, cudaMalloc(&ctx->d_part, sizeof(c128) * 148 * 16));
+    for (int64_t t = 0; t < count; ++t) {
+      const c128* x = (const c128*)a->ptr + (a_first + t) * dim;
+      const c128* y = (const c128*)b->ptr + (b_first + t * b_stride_states) * dim;
+      qsb_overlap_partial_kernel<<<n_part, 256, 0, ctx->stream>>>(x, y, dim, per, ctx->d_part);
+      qsb_overlap_final_kernel<<<1, 256, 0, ctx->stream>>>(ctx->d_part, n_part, (c128*)out->ptr + t);
+      ctx->launches += 1;
+    }
+    return after_launch(ctx, "overlap");
+  }
   qsb_overlap_kernel<<<(unsigned)count, 256, 0, ctx->stream>>>((const c128*)a->ptr + a_first * dim,
                                                                (const c128*)b->ptr + b_first * dim,
                                                                b_stride_states * dim, (c128*)out->ptr, dim);

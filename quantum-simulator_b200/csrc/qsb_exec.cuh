@@ -75,6 +75,7 @@ struct qsb_exec_args {
   int32_t tile_bits;      // streaming mode: n - m index bits select the tile (0 in resident mode)
   int32_t pad0;
   c128* states;           // already offset to `first`
+  c128* states_out;       // STORE destination, already offset (== states when in place)
   int64_t count;          // resident: trajectories; streaming: states (each 2^tile_bits tiles)
   const double* params;   int64_t params_stride;
   const double* uniforms; int64_t uniforms_stride;
@@ -422,10 +423,24 @@ QSB_PASS void qsb_do_init(Env& env, const qsb_exec_args& a, const qsb_desc* d) {
   const uint32_t lo = hoist ? qsb_permute(tab, (uint32_t)env.wid & 31u) : 0u;
   if (d->flags & QSB_RUN_LOAD) {
     const c128* src = d->gptr;
-    for (int i = env.wid; i < (1 << m); i += env.W) {
-      const uint32_t x = hi | (uint32_t)i;
-      const uint32_t s = hoist ? (qsb_permute(tab, x & ~31u) | lo) : qsb_permute(tab, x);
-      tile[qsb_slot(i)] = src[s];
+    // 8 loads in flight per worker: addresses first (the table look-ups and the tile stores are both shared
+    // memory, so the compiler will not reorder them itself), then the global loads, then the stores
+    for (int i0 = env.wid; i0 < (1 << m); i0 += 8 * env.W) {
+      uint32_t s[8];
+      c128 v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int i = i0 + e * env.W;
+        const uint32_t x = hi | (uint32_t)(i < (1 << m) ? i : i0);
+        s[e] = hoist ? (qsb_permute(tab, x & ~31u) | lo) : qsb_permute(tab, x);
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = src[s[e]];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int i = i0 + e * env.W;
+        if (i < (1 << m)) tile[qsb_slot(i)] = v[e];
+      }
     }
     // LOAD + STORE run in place and the two bit permutations differ, so a CTA's stores land on addresses
     // another CTA of the cluster loads from: nobody may go on before every CTA has its tile
@@ -467,13 +482,26 @@ QSB_PASS void qsb_do_store(Env& env, const qsb_exec_args& a, const qsb_desc* d, 
   const uint32_t lo = hoist ? qsb_permute(tab, (uint32_t)env.wid & 31u) : 0u;
   c128* out = d->gptr;
   double* probs = d->probs;
-  for (int i = env.wid; i < (1 << m); i += env.W) {
-    const uint32_t x = hi | (uint32_t)i;
-    const uint32_t dst = hoist ? (qsb_permute(tab, x & ~31u) | lo) : qsb_permute(tab, x);
-    c128 v = tile[qsb_slot(i)];
-    v.x *= scale; v.y *= scale;
-    if (out) out[dst] = v;
-    if (probs) env.atomic_add(probs + dst, qsb_norm2(v));
+  for (int i0 = env.wid; i0 < (1 << m); i0 += 8 * env.W) {
+    uint32_t dst[8];
+    c128 v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int i = i0 + e * env.W;
+      const int ii = i < (1 << m) ? i : i0;
+      const uint32_t x = hi | (uint32_t)ii;
+      dst[e] = hoist ? (qsb_permute(tab, x & ~31u) | lo) : qsb_permute(tab, x);
+      v[e] = tile[qsb_slot(ii)];
+      v[e].x *= scale; v[e].y *= scale;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int i = i0 + e * env.W;
+      if (i < (1 << m)) {
+        if (out) out[dst[e]] = v[e];
+        if (probs) env.atomic_add(probs + dst[e], qsb_norm2(v[e]));
+      }
+    }
   }
 }
 
@@ -1000,7 +1028,7 @@ QSB_HD void qsb_control_unit(Env& env, qsb_cstate& st, const qsb_exec_args& a, i
   qsb_flush(env, st, a.m, all_bits);
   if (a.flags & (QSB_RUN_STORE | QSB_RUN_ACCUM_PROBS))
     qsb_emit_store(env, st, a, a.idata + a.store_perm,
-                   (a.flags & QSB_RUN_STORE) ? a.states + t * st.dim : nullptr,
+                   (a.flags & QSB_RUN_STORE) ? a.states_out + t * st.dim : nullptr,
                    (a.flags & QSB_RUN_ACCUM_PROBS) ? a.probs_accum : nullptr);
 }
 

@@ -218,6 +218,29 @@ __global__ void qsb_overlap_kernel(const c128* __restrict__ a, const c128* __res
   if (threadIdx.x == 0) out[blockIdx.x] = make_double2(v[0], v[1]);
 }
 
+// large states: stage 1, CTA c sums the slice [c * per, (c + 1) * per) of one state pair into part[c];
+// stage 2 (one CTA) adds the partials in index order, so the result does not depend on scheduling
+__global__ void qsb_overlap_partial_kernel(const c128* __restrict__ x, const c128* __restrict__ y, int64_t dim,
+                                           int64_t per, c128* __restrict__ part) {
+  __shared__ double scratch[64];
+  const int64_t lo = blockIdx.x * per, hi = (lo + per < dim) ? lo + per : dim;
+  double v[2] = {0.0, 0.0};
+  for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    c128 p = x[i], q = y[i];
+    v[0] += p.x * q.x + p.y * q.y;
+    v[1] += p.x * q.y - p.y * q.x;
+  }
+  qsb_block_sum<2>(v, scratch);
+  if (threadIdx.x == 0) part[blockIdx.x] = make_double2(v[0], v[1]);
+}
+__global__ void qsb_overlap_final_kernel(const c128* __restrict__ part, int n_part, c128* __restrict__ out) {
+  __shared__ double scratch[64];
+  double v[2] = {0.0, 0.0};
+  for (int i = threadIdx.x; i < n_part; i += blockDim.x) { v[0] += part[i].x; v[1] += part[i].y; }
+  qsb_block_sum<2>(v, scratch);
+  if (threadIdx.x == 0) out[0] = make_double2(v[0], v[1]);
+}
+
 // (p_even, p_odd) per mask (qec.py:466-484); up to 8 masks per launch
 __global__ void qsb_parity_kernel(const c128* __restrict__ psi, int64_t dim, const uint64_t* __restrict__ masks,
                                   int n_masks, double* __restrict__ out) {

@@ -282,6 +282,51 @@ class Lowering:
         self.items.append([SNAPSHOT, [], slot, -1, -1, list(self.bit_of_axis)])
         return slot
 
+    # -- streaming (state in HBM): passes of resident tiles -------------------------------
+    def finish_stream(self, local_bits=None, low_bits=5, reorder=True):
+        """Lower to a StreamPlan.  Between passes the state rests in PHYSICAL order (the order it was loaded
+        in); with `reorder` the last pass stores it back in reference order (out of place when the
+        reference's axis scramble left a non-trivial permutation)."""
+        n = self.n
+        m = min(n, MAX_LOCAL_BITS) if local_bits is None else int(local_bits)
+        if not 1 <= m <= min(n, MAX_LOCAL_BITS):
+            raise ValueError(f"local_bits {m} invalid for n = {n}")
+        low = max(0, min(low_bits, m - 3))      # keep room for a 3-qubit gate on arbitrary bits
+        for it in self.items:
+            if it[0] in (SNAPSHOT, KRAUS_AD, KRAUS_GEN):
+                raise NotImplementedError("snapshots and state-dependent Kraus draws need the whole state "
+                                          "resident (n <= 16)")
+        packed = plan_passes(self.items, n, m, low)
+        final_perm_phys = [0] * n                  # physical bit -> reference-order bit
+        for axis in range(n):
+            final_perm_phys[self.bit_of_axis[axis]] = n - 1 - axis
+        needs_reorder = reorder and any(final_perm_phys[b] != b for b in range(n))
+        if not packed and needs_reorder:
+            packed = [(list(range(m)), [])]
+        if not packed:
+            packed = [(list(range(m)), [])]
+        cdata = self.pool.array()
+        progs = []
+        for k, (resident, chosen) in enumerate(packed):
+            others = [b for b in range(n) if b not in resident]
+            phys_of_slot = resident + others       # slot j (tile-local first, then the tile-number bits)
+            slot_of = {b: j for j, b in enumerate(phys_of_slot)}
+            ops = []
+            for idx in chosen:
+                kind, pbits, data, param, draw, _ = self.items[idx]
+                sb = [slot_of[b] for b in pbits] + [0, 0, 0]
+                ops.append((kind, sb[0], sb[1], sb[2], data, param, draw, 0))
+            last = k == len(packed) - 1
+            store = [final_perm_phys[b] for b in phys_of_slot] if (last and needs_reorder) else list(phys_of_slot)
+            idata = list(phys_of_slot) + store
+            arr = np.array(ops, dtype=OP_DTYPE) if ops else np.zeros(0, dtype=OP_DTYPE)
+            progs.append(Program(n=n, m=m, ops=arr, cdata=cdata, idata=np.array(idata, dtype=np.int32),
+                                 load_perm=0, store_perm=n, n_snapshots=0, n_draws=self.n_draws,
+                                 n_params=self.n_params, normalize=False, n_gate_ops=0, n_kraus_ops=0,
+                                 meta={"resident": resident}))
+        return StreamPlan(n=n, m=m, passes=progs, final_out_of_place=needs_reorder, n_gate_ops=self.n_gate_ops,
+                          n_draws=self.n_draws, n_params=self.n_params)
+
     # -- slot placement + emission ------------------------------------------------------
     def finish(self, local_bits=None):
         n = self.n
@@ -356,6 +401,60 @@ class Lowering:
                        load_perm=0, store_perm=store_off, n_snapshots=self.n_snapshots, n_draws=self.n_draws,
                        n_params=self.n_params, normalize=self.normalize, n_gate_ops=self.n_gate_ops,
                        n_kraus_ops=self.n_kraus_ops, n_remaps=n_remaps)
+
+
+@dataclass
+class StreamPlan:
+    """A program for a state that lives in HBM (n > 16, or any n with n - m > 3): a list of passes.
+    Every pass but (possibly) the last runs in place; `final_out_of_place` says the last one stores through a
+    different bit permutation (back to reference order) and therefore needs a second buffer."""
+    n: int
+    m: int
+    passes: list                 # [Program]
+    final_out_of_place: bool
+    n_gate_ops: int = 0
+    n_draws: int = 0
+    n_params: int = 0
+
+
+def plan_passes(items, n, m, low, frozen=()):
+    """Greedy packing of ops into passes.  A pass keeps `m` physical bits resident: always the `low`
+    lowest ones (contiguous 16 * 2^low-byte rows in HBM), never those in `frozen` (bits owned by another
+    device), the rest by demand.  An op that does not fit blocks its qubits; later ops on blocked qubits wait
+    for the next pass (ops on other qubits commute past them and are packed now).
+    Returns [(sorted resident bits, [item indices])]."""
+    remaining = list(range(len(items)))
+    passes = []
+    frozen = set(frozen)
+    while remaining:
+        resident = set(range(low))
+        blocked = set()
+        chosen, rest = [], []
+        for idx in remaining:
+            pbits = items[idx][1]
+            if any(b in frozen for b in pbits):
+                raise ValueError("op on a bit that is not addressable on this device")
+            if any(b in blocked for b in pbits):
+                blocked.update(pbits)
+                rest.append(idx)
+                continue
+            need = [b for b in pbits if b not in resident]
+            if len(resident) + len(need) <= m:
+                resident.update(need)
+                chosen.append(idx)
+            else:
+                blocked.update(pbits)
+                rest.append(idx)
+        if not chosen:
+            raise ValueError(f"an op needs more than {m} resident bits")
+        for b in range(n):                       # fill the tile with the lowest free bits
+            if len(resident) >= m:
+                break
+            if b not in resident and b not in frozen:
+                resident.add(b)
+        passes.append((sorted(resident), chosen))
+        remaining = rest
+    return passes
 
 
 def _kron_factors(mat, k):

@@ -70,7 +70,7 @@ extern "C" int emu_run(int n, int m, int T, const qsb_op* ops, int64_t n_ops, in
                        int64_t count, const double* params, int64_t params_stride, const double* uniforms,
                        int64_t uniforms_stride, uint64_t seed, int64_t traj_offset, const int64_t* init_basis,
                        int64_t default_basis, int32_t* branches, int64_t branches_stride, void* snapshots,
-                       double* probs_accum) {
+                       double* probs_accum, void* states_out) {
   if (n < 1 || n > 30 || m < 1 || m > n || m > QSB_MAX_LOCAL_BITS || T < 8 || T > 32 || (T & (T - 1))) return -1;   // W: power of two >= 8
   const bool streaming = (n - m > 3) || n > QSB_MAX_QUBITS;
   Shared sh;
@@ -97,7 +97,7 @@ extern "C" int emu_run(int n, int m, int T, const qsb_op* ops, int64_t n_ops, in
   memset(&a, 0, sizeof a);
   a.ops = ops; a.n_ops = n_ops; a.ops_stride = ops_stride; a.cdata = cdata; a.n_cdata = n_cdata; a.idata = idata;
   a.n = n; a.m = m; a.load_perm = load_perm; a.store_perm = store_perm; a.n_snapshots = n_snapshots;
-  a.flags = flags; a.states = (c128*)states; a.count = count;
+  a.flags = flags; a.states = (c128*)states; a.states_out = states_out ? (c128*)states_out : (c128*)states; a.count = count;
   a.tile_bits = streaming ? n - m : 0;
   a.params = params; a.params_stride = params_stride;
   a.uniforms = uniforms; a.uniforms_stride = uniforms_stride;

@@ -42,7 +42,7 @@ def _p(a):
 
 
 def emu_run(prog, count=1, T=2, states=None, params=None, uniforms=None, seed=0, traj_offset=0,
-            init_basis=None, default_basis=0, want_branches=False, store=True, accum_probs=False):
+            init_basis=None, default_basis=0, want_branches=False, store=True, accum_probs=False, out_of_place=False):
     """Returns dict(states, snapshots, branches, probs)."""
     dim = 1 << prog.n
     flags = 0
@@ -70,6 +70,7 @@ def emu_run(prog, count=1, T=2, states=None, params=None, uniforms=None, seed=0,
         init_basis = np.ascontiguousarray(init_basis, dtype=np.int64)
     branches = np.full((count, max(prog.n_draws, 1)), -1, dtype=np.int32) if want_branches else None
     snaps = np.zeros((count, max(prog.n_snapshots, 1), dim), dtype=np.complex128) if prog.n_snapshots else None
+    out_states = np.zeros_like(states) if out_of_place else None
     rc = lib().emu_run(
         ctypes.c_int(prog.n), ctypes.c_int(prog.m), ctypes.c_int(8 if T < 3 else 16), _p(ops), ctypes.c_int64(len(ops)),
         ctypes.c_int64(prog.ops_stride), _p(cdata), ctypes.c_int64(len(cdata)), _p(idata), ctypes.c_int(prog.load_perm),
@@ -77,6 +78,7 @@ def emu_run(prog, count=1, T=2, states=None, params=None, uniforms=None, seed=0,
         ctypes.c_int64(count), _p(params), ctypes.c_int64(params.shape[1] if params is not None else 0),
         _p(uniforms), ctypes.c_int64(uniforms.shape[1] if uniforms is not None else 0),
         ctypes.c_uint64(seed), ctypes.c_int64(traj_offset), _p(init_basis), ctypes.c_int64(default_basis),
-        _p(branches), ctypes.c_int64(branches.shape[1] if branches is not None else 0), _p(snaps), _p(probs))
+        _p(branches), ctypes.c_int64(branches.shape[1] if branches is not None else 0), _p(snaps), _p(probs),
+        _p(out_states))
     assert rc == 0, rc
-    return dict(states=states, snapshots=snaps, branches=branches, probs=probs)
+    return dict(states=out_states if out_of_place else states, snapshots=snaps, branches=branches, probs=probs)

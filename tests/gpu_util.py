@@ -6,7 +6,7 @@ from qsb import capi
 
 
 def gpu_run(prog, count=1, T=None, states=None, params=None, uniforms=None, seed=0, traj_offset=0,
-            init_basis=None, default_basis=0, want_branches=False, store=True, accum_probs=False):
+            init_basis=None, default_basis=0, want_branches=False, store=True, accum_probs=False, out_of_place=False):
     ctx = capi.get_context()
     dim = 1 << prog.n
     dp = ctx.program(prog)
@@ -36,8 +36,11 @@ def gpu_run(prog, count=1, T=None, states=None, params=None, uniforms=None, seed
     if accum_probs:
         pb = ctx.alloc(dim * 8).zero()
         kw.update(probs_accum=pb)
+    obuf = ctx.alloc(count * dim * 16).zero() if out_of_place else None
     ctx.run(dp, count, states=sbuf, load=load, store=store, seed=seed, traj_offset=traj_offset,
-            default_basis=default_basis, **kw)
+            default_basis=default_basis, states_out=obuf, **kw)
+    if obuf is not None:
+        sbuf = obuf
     return dict(states=sbuf.download(np.complex128, (count, dim)),
                 snapshots=sn.download(np.complex128, (count, prog.n_snapshots, dim)) if sn is not None else None,
                 branches=bbuf.download(np.int32, (count, max(prog.n_draws, 1))) if bbuf is not None else None,

@@ -37,7 +37,7 @@ def _build():
     return BIN
 
 
-def _dump(path, prog, W, count=1, states=None, uniforms=None, params=None):
+def _dump(path, prog, W, count=1, states=None, uniforms=None, params=None, out_of_place=False):
     dim = 1 << prog.n
     flags = 2 | (1 if states is not None else 0) | (4 if prog.normalize else 0)
     st = np.zeros((count, dim), dtype=np.complex128) if states is None else np.ascontiguousarray(states, dtype=np.complex128)
@@ -46,7 +46,7 @@ def _dump(path, prog, W, count=1, states=None, uniforms=None, params=None):
             arr = np.ascontiguousarray(arr)
             f.write(struct.pack("<q", arr.size if arr.dtype != prog.ops.dtype else len(arr)))
             f.write(arr.tobytes())
-        w(np.array([prog.n, prog.m, W, prog.load_perm, prog.store_perm, prog.n_snapshots, flags, count, prog.ops_stride],
+        w(np.array([prog.n, prog.m, W, prog.load_perm, prog.store_perm, prog.n_snapshots, flags, count, prog.ops_stride, int(out_of_place)],
                    dtype=np.int64))
         w(prog.ops)
         w(np.asarray(prog.cdata, dtype=np.float64))

@@ -197,3 +197,40 @@ def test_layered16_cluster8(run, golden):
     psi = out["states"][0]
     assert np.max(np.abs(psi[a["layered16_idx"]] - a["layered16_amps"])) < TOL
     assert int(np.argmax(np.abs(psi))) == j["layered16"]["argmax"]
+
+
+def run_stream(run, plan, psi0):
+    """Run a StreamPlan pass by pass (every pass is one launch over all tiles of the state)."""
+    cur = np.ascontiguousarray(psi0, dtype=np.complex128)[None]
+    for k, prog in enumerate(plan.passes):
+        last = k == len(plan.passes) - 1
+        cur = run(prog, T=2, states=cur, out_of_place=last and plan.final_out_of_place)["states"]
+    return cur[0]
+
+
+@pytest.mark.parametrize("n,m", [(8, 4), (9, 4), (10, 5), (11, 5)])
+def test_streaming_passes_vs_oracle(run, n, m):
+    """n - m > 3: the state stays in memory and is streamed tile by tile, one pass per launch."""
+    rng = np.random.default_rng(n * 31 + m)
+    gates = layered_circuit(n, 6, 100 + n)
+    qc = QuantumCircuit(n)
+    for g in gates:
+        qc.add_gate(GateInstance(g[0], list(g[1]), list(g[2]), g[3]))
+    plan, _ = lower_circuit(n, qc.get_ordered_gates(), REG, local_bits=m, stream=True)
+    assert len(plan.passes) >= 2
+    psi0 = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+    psi0 /= np.linalg.norm(psi0)
+    ordered = [g for col in qc.get_ordered_gates() for g in col]     # the reference's execution order
+    ref = psi0
+    for g in ordered:
+        ref = O.apply_gate(ref, n, O.gate_matrix(g.gate_name, g.params), list(g.target_qubits))
+    got = run_stream(run, plan, psi0)
+    assert np.max(np.abs(got - ref)) < TOL
+    # textbook layout: no final reorder, everything in place
+    plan_t, _ = lower_circuit(n, qc.get_ordered_gates(), REG, local_bits=m, stream=True, layout="textbook")
+    assert not plan_t.final_out_of_place
+    got_t = run_stream(run, plan_t, psi0)
+    ref_t = psi0
+    for g in ordered:
+        ref_t = O.apply_textbook(ref_t, n, O.gate_matrix(g.gate_name, g.params), list(g.target_qubits))
+    assert np.max(np.abs(got_t - ref_t)) < TOL
