@@ -133,6 +133,15 @@ def plan_distributed(lw: Lowering, g: int, local_bits=None, low_bits=4):
     return steps, pos_of
 
 
+def exchange_rank_bits(src, dst, group=None):
+    """Swap the g rank positions with the top g local positions of a sharded state: rank r's chunk c (the
+    shard cut into world-size contiguous chunks) becomes rank c's chunk r.  One all_to_all_single; works on
+    CUDA tensors over NCCL/NVLink and on CPU tensors over gloo (tests)."""
+    import torch.distributed as dist
+    dist.all_to_all_single(dst, src, group=group)
+    return dst
+
+
 class BigState:
     """One n-qubit complex128 state on this rank's GPU (a 2^(n-g) shard when the process group has 2^g ranks)."""
 
@@ -213,10 +222,8 @@ class BigState:
 
     def _exchange(self):
         """Swap the g rank positions with the top g local positions (one all-to-all of contiguous chunks)."""
-        import torch.distributed as dist
         o = self._other()
-        src, dst = self.buf[self.cur], self.buf[o]
-        dist.all_to_all_single(dst, src, group=self.group)
+        exchange_rank_bits(self.buf[self.cur], self.buf[o], self.group)
         self.cur = o
 
     # -- circuits -------------------------------------------------------------------------------

@@ -88,3 +88,60 @@ def test_world2_gloo_matches_single_process(golden):
     assert counts == j["ghz3"]["run_with_noise"]
     assert list(counts) == list(j["ghz3"]["run_with_noise"])
     assert abs(hist.sum() - shots) < 1e-9
+
+
+def _exchange_worker(rank, world, port, n, out_q):
+    """Sharded plan executed with NumPy per rank and a real gloo all_to_all_single for the exchange steps."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from qsb.bigstate import plan_distributed, exchange_rank_bits, Step
+    from qsb.workloads import layered_circuit
+    from test_bigstate import ordered, lower, replay_numpy
+    g = world.bit_length() - 1
+    L = n - g
+    gl = ordered(n, layered_circuit(n, 5, 77))
+    lw = lower(n, gl)
+    steps, pos_of = plan_distributed(lw, g, local_bits=4)
+    rng = np.random.default_rng(3)
+    psi = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+    psi /= np.linalg.norm(psi)
+    shard = psi[rank << L:(rank + 1) << L].copy()
+    n_ex = 0
+    for st in steps:
+        if st.kind == "exchange":
+            src = torch.from_numpy(shard.view(np.float64).copy())
+            dst = torch.empty_like(src)
+            exchange_rank_bits(src, dst)
+            shard = dst.numpy().view(np.complex128).copy()
+            n_ex += 1
+        else:
+            # one local pass: reuse the single-shard NumPy model (g = 0 view of this rank's shard)
+            shard = replay_numpy([st], L, 0, shard, lw.pool.array())
+    parts = [torch.zeros(2 * (1 << L), dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(parts, torch.from_numpy(shard.view(np.float64).copy()))
+    if rank == 0:
+        full = np.concatenate([p.numpy().view(np.complex128) for p in parts])
+        pos = [pos_of[lw.bit_of_axis[j]] for j in range(n)]
+        got = np.ascontiguousarray(full.reshape([2] * n).transpose([n - 1 - pos[j] for j in range(n)])).reshape(-1)
+        ref = psi
+        for name, targets, params in gl:
+            ref = O.apply_gate(ref, n, O.gate_matrix(name, params), targets)
+        out_q.put((float(np.max(np.abs(got - ref))), n_ex))
+    dist.destroy_process_group()
+
+
+def test_world2_gloo_sharded_state_with_qubit_exchanges():
+    """BASELINE config 5's exchange step on CPU: global qubit <-> local qubit swaps as all_to_all_single."""
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_exchange_worker, args=(r, 2, port, 9, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    err, n_ex = q.get()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert n_ex >= 1
+    assert err < 1e-12
