@@ -98,7 +98,8 @@ enum {
   QSB_RUN_STORE = 2,       /* write the final state to states[first+t] in reference order */
   QSB_RUN_NORMALIZE = 4,   /* divide by ||psi|| on store/snapshot (set when Kraus ops ran) */
   QSB_RUN_ASYNC = 8,       /* do not synchronise the ctx stream before returning          */
-  QSB_RUN_ACCUM_PROBS = 16 /* atomically add |psi|^2 (reference order) into probs_accum   */
+  QSB_RUN_ACCUM_PROBS = 16,/* atomically add |psi|^2 (reference order) into probs_accum   */
+  QSB_RUN_LOAD_BROADCAST = 32 /* with LOAD: every unit starts from states[first] (one codeword, many trials) */
 };
 
 typedef struct qsb_run_args {

@@ -481,8 +481,11 @@ int qsb_run(qsb_program* p, const qsb_run_args* r) {
   if (r->count == 0) return QSB_OK;
   const int64_t dim = (int64_t)1 << p->n;
   int rc;
+  if ((r->flags & QSB_RUN_LOAD_BROADCAST) && (r->flags & QSB_RUN_STORE) && !r->states_out)
+    return fail(ctx, QSB_E_INVAL, "qsb_run: LOAD_BROADCAST cannot store in place");
   if ((r->flags & QSB_RUN_LOAD) || ((r->flags & QSB_RUN_STORE) && !r->states_out))
-    if ((rc = need(ctx, r->states, (r->first + r->count) * dim * 16, "states"))) return rc;
+    if ((rc = need(ctx, r->states, (r->first + ((r->flags & QSB_RUN_LOAD_BROADCAST) ? 1 : r->count)) * dim * 16, "states")))
+      return rc;
   if (p->ops_stride && r->count > p->n_programs)
     return fail(ctx, QSB_E_INVAL, "qsb_run: %lld trajectories but only %lld per-trajectory programs",
                 (long long)r->count, (long long)p->n_programs);

@@ -976,7 +976,7 @@ QSB_HD void qsb_control_unit(Env& env, qsb_cstate& st, const qsb_exec_args& a, i
       d->unit = unit; d->tile = st.tile;
       d->basis = a.init_basis ? a.init_basis[t] : a.default_basis;
       d->perm = a.idata + a.load_perm;
-      d->gptr = a.states ? a.states + t * st.dim : nullptr;
+      d->gptr = a.states ? a.states + ((a.flags & QSB_RUN_LOAD_BROADCAST) ? 0 : t * st.dim) : nullptr;
     }
     qsb_desc_end(env, st);
     if (a.flags & QSB_RUN_LOAD) qsb_cluster_event(env, st);     // matches the barrier at the end of a LOAD

@@ -18,7 +18,7 @@ from .compiler import OP_DTYPE, Program
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "libqsb.so")
 
-RUN_LOAD, RUN_STORE, RUN_NORMALIZE, RUN_ASYNC, RUN_ACCUM_PROBS = 1, 2, 4, 8, 16
+RUN_LOAD, RUN_STORE, RUN_NORMALIZE, RUN_ASYNC, RUN_ACCUM_PROBS, RUN_LOAD_BROADCAST = 1, 2, 4, 8, 16, 32
 
 SYMBOLS = [
     "qsb_version", "qsb_device_count", "qsb_ctx_create", "qsb_ctx_destroy", "qsb_ctx_set_stream",
@@ -234,7 +234,7 @@ class Context:
     def run(self, dprog, count, *, states=None, first=0, load=False, store=True, params=None, params_stride=0,
             uniforms=None, uniforms_stride=0, seed=0, traj_offset=0, init_basis=None, default_basis=0,
             branches=None, branches_stride=0, snapshots=None, probs_accum=None, async_=False, normalize=None,
-            states_out=None, out_first=0):
+            states_out=None, out_first=0, load_broadcast=False):
         a = RunArgs()
         a.states = states.handle if states is not None else None
         a.first, a.count = first, count
@@ -254,7 +254,8 @@ class Context:
         norm = dprog.prog.normalize if normalize is None else normalize
         a.flags = ((RUN_LOAD if load else 0) | (RUN_STORE if store and (states is not None or states_out is not None) else 0) |
                    (RUN_NORMALIZE if norm else 0) | (RUN_ASYNC if async_ else 0) |
-                   (RUN_ACCUM_PROBS if probs_accum is not None else 0))
+                   (RUN_ACCUM_PROBS if probs_accum is not None else 0) |
+                   (RUN_LOAD_BROADCAST if load_broadcast else 0))
         _check(self.lib.qsb_run(dprog.handle, C.byref(a)), self.handle)
 
     def profile(self, enable=True, read=False):
