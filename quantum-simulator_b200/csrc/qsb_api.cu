@@ -750,8 +750,8 @@ int qsb_rho_accumulate(qsb_ctx* ctx, int32_t n, qsb_buffer* states, int64_t firs
   if ((rc = need(ctx, rho, dim * dim * 16, "rho"))) return rc;
   CU(ctx, cudaSetDevice(ctx->device));
   const unsigned g = (unsigned)((dim + QSB_RHO_TILE - 1) / QSB_RHO_TILE);
-  qsb_rho_kernel<<<dim3(g, g, 1), 256, 0, ctx->stream>>>((const c128*)states->ptr + first * dim, dim, count, scale,
-                                                         (c128*)rho->ptr);
+  qsb_rho_kernel<<<g * (g + 1) / 2, 256, 0, ctx->stream>>>((const c128*)states->ptr + first * dim, dim, count, scale,
+                                                           (c128*)rho->ptr, (int)g);
   return after_launch(ctx, "rho_accumulate");
 }
 

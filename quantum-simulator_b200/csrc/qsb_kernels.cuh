@@ -347,57 +347,92 @@ __global__ void qsb_rdm2_kernel(const c128* __restrict__ psi, int n, int npairs,
 }
 
 // rho[i][j] += scale * sum_t psi_t[i] conj(psi_t[j])   (simulator.py:195-198)
-// 64x64 tile of rho per CTA (256 threads, 4x4 outputs each), 16 trajectories per shared-memory stage.
+// The one dense contraction of the path: with A = Re Psi, B = Im Psi (dim x N),
+//   Re rho = A A^T + B B^T,   Im rho = B A^T - A B^T
+// i.e. real GEMMs with K = N trajectories, run on the FP64 tensor-core path (DMMA, mma.sync m8n8k4).
+// One CTA = one 64x64 tile of the upper triangle (rho is Hermitian; the mirrored tile is written from the
+// same accumulators); 8 warps, each a 32x16 patch = 4x2 m8n8 tiles x (Re, Im); 16 trajectories per
+// shared-memory stage.
 #define QSB_RHO_TILE 64
 #define QSB_RHO_KC 16
+#define QSB_RHO_PAD 2          // doubles of row padding: the 4 k-rows a fragment load touches hit different banks
+
+__device__ __forceinline__ void qsb_dmma(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
 __global__ void __launch_bounds__(256) qsb_rho_kernel(const c128* __restrict__ psi, int64_t dim, int64_t count,
-                                                       double scale, c128* __restrict__ rho) {
-  __shared__ c128 sa[QSB_RHO_KC][QSB_RHO_TILE];
-  __shared__ c128 sb[QSB_RHO_KC][QSB_RHO_TILE];
-  const int64_t i0 = (int64_t)blockIdx.y * QSB_RHO_TILE, j0 = (int64_t)blockIdx.x * QSB_RHO_TILE;
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  c128 acc[4][4];
+                                                       double scale, c128* __restrict__ rho, int tiles_per_side) {
+  // re / im planes of the two 64-wide panels, [k][x]
+  __shared__ double sa_re[QSB_RHO_KC][QSB_RHO_TILE + QSB_RHO_PAD], sa_im[QSB_RHO_KC][QSB_RHO_TILE + QSB_RHO_PAD];
+  __shared__ double sb_re[QSB_RHO_KC][QSB_RHO_TILE + QSB_RHO_PAD], sb_im[QSB_RHO_KC][QSB_RHO_TILE + QSB_RHO_PAD];
+  // linear tile id -> (ti <= tj) in the upper triangle
+  int ti = 0, rem = blockIdx.x;
+  while (rem >= tiles_per_side - ti) { rem -= tiles_per_side - ti; ++ti; }
+  const int tj = ti + rem;
+  const int64_t i0 = (int64_t)ti * QSB_RHO_TILE, j0 = (int64_t)tj * QSB_RHO_TILE;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wr = (warp >> 2) * 32, wc = (warp & 3) * 16;         // warp patch origin inside the tile
+  const int grp = lane >> 2, tig = lane & 3;                     // fragment coordinates
+  double re[4][2][2], im[4][2][2];
 #pragma unroll
-  for (int r = 0; r < 4; ++r)
+  for (int a = 0; a < 4; ++a)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) acc[r][c] = make_double2(0.0, 0.0);
+    for (int b = 0; b < 2; ++b) { re[a][b][0] = re[a][b][1] = im[a][b][0] = im[a][b][1] = 0.0; }
   for (int64_t t0 = 0; t0 < count; t0 += QSB_RHO_KC) {
     for (int e = threadIdx.x; e < QSB_RHO_KC * QSB_RHO_TILE; e += 256) {
-      int k = e / QSB_RHO_TILE, x = e % QSB_RHO_TILE;
-      c128 z = make_double2(0.0, 0.0);
-      sa[k][x] = (t0 + k < count && i0 + x < dim) ? psi[(t0 + k) * dim + i0 + x] : z;
-      sb[k][x] = (t0 + k < count && j0 + x < dim) ? psi[(t0 + k) * dim + j0 + x] : z;
+      const int k = e / QSB_RHO_TILE, x = e % QSB_RHO_TILE;
+      c128 za = make_double2(0.0, 0.0), zb = za;
+      if (t0 + k < count) {
+        if (i0 + x < dim) za = psi[(t0 + k) * dim + i0 + x];
+        if (j0 + x < dim) zb = psi[(t0 + k) * dim + j0 + x];
+      }
+      sa_re[k][x] = za.x; sa_im[k][x] = za.y;
+      sb_re[k][x] = zb.x; sb_im[k][x] = zb.y;
     }
     __syncthreads();
-#pragma unroll 4
-    for (int k = 0; k < QSB_RHO_KC; ++k) {
-      c128 av[4], bv[4];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) av[r] = sa[k][ty + 16 * r];
+    for (int k0 = 0; k0 < QSB_RHO_KC; k0 += 4) {
+      double ar[4], ai[4], br[2], bi[2];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) bv[c] = sb[k][tx + 16 * c];
+      for (int a = 0; a < 4; ++a) { ar[a] = sa_re[k0 + tig][wr + a * 8 + grp]; ai[a] = sa_im[k0 + tig][wr + a * 8 + grp]; }
 #pragma unroll
-      for (int r = 0; r < 4; ++r)
+      for (int b = 0; b < 2; ++b) { br[b] = sb_re[k0 + tig][wc + b * 8 + grp]; bi[b] = sb_im[k0 + tig][wc + b * 8 + grp]; }
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {   // a * conj(b)
-          acc[r][c].x = fma(av[r].x, bv[c].x, fma(av[r].y, bv[c].y, acc[r][c].x));
-          acc[r][c].y = fma(av[r].y, bv[c].x, fma(-av[r].x, bv[c].y, acc[r][c].y));
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          // psi_i conj(psi_j) = (ar br + ai bi) + i (ai br - ar bi)
+          qsb_dmma(re[a][b][0], re[a][b][1], ar[a], br[b]);
+          qsb_dmma(re[a][b][0], re[a][b][1], ai[a], bi[b]);
+          qsb_dmma(im[a][b][0], im[a][b][1], ai[a], br[b]);
+          qsb_dmma(im[a][b][0], im[a][b][1], -ar[a], bi[b]);
         }
     }
     __syncthreads();
   }
+  // accumulator (row = grp, cols 2 tig, 2 tig + 1) -> rho and, off the diagonal tiles, its mirror image
 #pragma unroll
-  for (int r = 0; r < 4; ++r)
+  for (int a = 0; a < 4; ++a)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      int64_t i = i0 + ty + 16 * r, j = j0 + tx + 16 * c;
-      if (i < dim && j < dim) {
-        c128 o = rho[i * dim + j];
-        o.x += scale * acc[r][c].x;
-        o.y += scale * acc[r][c].y;
-        rho[i * dim + j] = o;
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int64_t i = i0 + wr + a * 8 + grp, j = j0 + wc + b * 8 + 2 * tig + c;
+        if (i < dim && j < dim) {
+          c128 o = rho[i * dim + j];
+          o.x += scale * re[a][b][c];
+          o.y += scale * im[a][b][c];
+          rho[i * dim + j] = o;
+          if (ti != tj) {
+            c128 m = rho[j * dim + i];
+            m.x += scale * re[a][b][c];
+            m.y -= scale * im[a][b][c];
+            rho[j * dim + i] = m;
+          }
+        }
       }
-    }
 }
 
 // one axis of ReadoutError.apply_to_distribution (noise.py:163-169): out[m] = C[m][0] p0 + C[m][1] p1
