@@ -41,6 +41,11 @@ def algorithmic_bytes_per_trajectory(n, gates, k_pauli, k_ad):
     return (gates + k_pauli + 1.5 * k_ad) * sweep + 16 * 2 ** n
 
 
+# DRAM bytes one trajectory really moves (ncu dram__bytes_read.sum + dram__bytes_write.sum of the trajectory
+# kernel divided by its trajectories: profiles/r01c_traj_kernel_ncu_full_traj480.csv, 515.0 MB / 480)
+MEASURED_DRAM_BYTES_PER_TRAJECTORY = 515029248 / 480
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -272,6 +277,9 @@ def run_ours(args):
     e2e_value = world * e2e_T * args.e2e_steps / float(e2e_dt.item())
     assert sum(res.measurement_counts.values()) == e2e_T
 
+    extras = None
+    if rank == 0 and not args.no_extras:
+        extras = measure_other_paths(ctx, sim, qc)
     if rank == 0:
         peak, peak_src = measured_peak()
         kms = float(np.mean(kern_ms))
@@ -286,7 +294,9 @@ def run_ours(args):
                        "histogram_total": hist_total},
             "roofline": {"bound": "hbm", "kernel": f"qsb_traj_kernel<{1 << (prog.n - prog.m)}>",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": MEASURED_DRAM_BYTES_PER_TRAJECTORY * T,
+                         "traffic_source": "ncu dram bytes per trajectory (profiles/r01c_*_traj480.csv) x trajectories per launch",
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes * T, "kernel_ms": kms,
                          "note": "trajectories are resident in cluster shared memory; algorithmic bytes count "
                                  "every gate/Kraus sweep (SURVEY 8d), real DRAM traffic is ~1 MiB/trajectory "
@@ -297,11 +307,87 @@ def run_ours(args):
                     "steps": args.e2e_steps},
             "gpu_launches": launches, "clocks": clocks,
         }
+        if extras is not None:
+            line["other_paths"] = extras
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_sample()
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_other_paths(ctx, sim, qc16):
+    """Short, separately timed runs of the other BASELINE configs (not part of the headline timing):
+    device time by CUDA events on the ctx stream, inputs resident."""
+    import torch
+    from qsb.workloads import layered_circuit, to_gate_instances
+    from quantum_sim.engine.circuit import QuantumCircuit, GateInstance
+    from quantum_sim.engine.noise import NoiseModel, DepolarizingNoise, AmplitudeDampingNoise
+    from quantum_sim.engine.optimizer import ParameterizedCircuitConfig
+    from quantum_sim.engine.qec import QECSimulator, SteaneCode
+    from quantum_sim.engine.simulator import Simulator
+    out = {}
+    # config 2: 16-qubit layered circuit, 4096 parameter sets in one launch (noiseless) -> gate-apps/s
+    cfg = ParameterizedCircuitConfig.auto_detect(qc16)
+    vals = np.random.default_rng(2027).uniform(-np.pi, np.pi, (4096, cfg.num_params))
+    cfg.run_batch(vals[:64])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    cfg.run_batch(vals)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    gates = len(qc16.gates)
+    out["config2_param_batch"] = {"param_sets": 4096, "gates": gates, "seconds": dt, "gate_apps_per_s": 4096 * gates / dt,
+                                  "algorithmic_GBps": 4096 * gates * 2 * 16 * 2 ** 16 / dt / 1e9,
+                                  "includes": "h2d of the 4096x473 parameter matrix"}
+    # config 3: 12 qubits, depolarizing + amplitude damping, 500 trajectories -> rho (DMMA) + all-pairs MI per layer
+    n = 12
+    qc = QuantumCircuit(n)
+    for g in to_gate_instances(layered_circuit(n, 16, 2026), GateInstance):
+        qc.add_gate(g)
+    nm = NoiseModel()
+    nm.add_global_noise(DepolarizingNoise(0.01))
+    nm.add_global_noise(AmplitudeDampingNoise(0.02))
+    s12 = Simulator(nm)
+    s12.ensemble_density_matrix(qc, 8, seed=1)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    rho = s12.ensemble_density_matrix(qc, 500, seed=42)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    out["config3_ensemble_rho"] = {"qubits": n, "trials": 500, "seconds": dt, "trace": float(np.real(np.trace(rho))),
+                                   "purity": float(np.real(np.sum(rho * rho.T))),
+                                   "includes": "host draws, 500 trajectories, DMMA rho, 256 MiB d2h"}
+    # config 4: Steane [[7,1,3]] cycles (13 qubits), batched
+    qs = QECSimulator(SteaneCode())
+    seeds = list(range(1000, 1000 + 2048))
+    qs.run_cycles([t % 2 for t in range(64)], "depolarizing", 0.05, seeds[:64])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    qs.run_cycles([t % 2 for t in range(2048)], "depolarizing", 0.05, seeds)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    out["config4_steane_cycles"] = {"cycles": 2048, "seconds": dt, "cycles_per_s": 2048 / dt,
+                                    "includes": "host Pauli decisions, decode table, d2h of syndromes"}
+    # config 5 (single-GPU leg): 26-qubit layered circuit streamed through shared memory
+    try:
+        from qsb.bigstate import BigState
+        nb = 26
+        gl = [(g.gate_name, list(g.target_qubits), list(g.params)) for g in
+              to_gate_instances(layered_circuit(nb, 20, 2026), GateInstance)]
+        st = BigState(nb, layout="textbook")
+        st.apply_gates(gl[:8])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        st.apply_gates(gl)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        out["config5_streamed_26q"] = {"qubits": nb, "gates": len(gl), "seconds": dt, "gate_apps_per_s": len(gl) / dt,
+                                       "algorithmic_GBps": len(gl) * 2 * 16 * 2 ** nb / dt / 1e9, "norm2": st.norm2()}
+        del st
+    except Exception as e:           # never let a secondary measurement break the headline line
+        out["config5_streamed_26q"] = {"error": repr(e)}
+    return out
 
 
 def main():
@@ -314,6 +400,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the short secondary measurements (configs 2-5)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
