@@ -41,13 +41,22 @@
 #if defined(__CUDACC__)
 #define QSB_HD __host__ __device__ __forceinline__
 #define QSB_PASS __device__ __forceinline__   // whole-tile sweeps: inlined into the worker loop (an ABI call would leave them ~48 registers)
-#define QSB_CTL __device__ __noinline__       // control-warp helpers: called from many ops, keep one copy
+#define QSB_CTL __device__ __forceinline__    // control-warp helpers: inlined so that the control state stays in registers (an ABI call spills it to local memory)
 typedef double2 c128;
 #else
 #define QSB_HD inline
 #define QSB_PASS inline
 #define QSB_CTL inline
 struct alignas(16) c128 { double x, y; };
+#endif
+
+// count trailing zeros / index of the highest set bit of a non-zero 32-bit word
+#if defined(__CUDA_ARCH__)
+#define QSB_CTZ(x) (__ffs((int)(x)) - 1)
+#define QSB_MSB(x) (31 - __clz((int)(x)))
+#else
+#define QSB_CTZ(x) __builtin_ctz((unsigned)(x))
+#define QSB_MSB(x) (31 - __builtin_clz((unsigned)(x)))
 #endif
 
 #define QSB_MAX_QUBITS 16          // resident (cluster) mode
@@ -60,7 +69,7 @@ struct alignas(16) c128 { double x, y; };
 #define QSB_GROUP_POS 1        // 1: bank-conflict-free group order (qsb_group_order), 0: ascending free bits
 #endif
 #define QSB_PROF_WORDS 128
-#define QSB_RING 4             // descriptors in flight between control warp and workers
+#define QSB_RING 6             // descriptors in flight between control warp and workers
 
 struct qsb_exec_args {
   const qsb_op* ops;
@@ -104,9 +113,9 @@ struct alignas(16) qsb_desc {
   c128* gptr;              // INIT: source state (LOAD) ; STORE: destination (or NULL)
   double* probs;           // STORE: |psi|^2 accumulation target (or NULL)
   int64_t tile;            // INIT / STORE: value of the non-resident index bits (cluster rank or tile id)
-  int8_t pos[16];          // SWEEP: index bit that bit t of the group number lands on (bank-conflict-free order)
+  uint64_t pos;            // SWEEP: 16 nibbles, nibble t = index bit that bit t of the group number lands on
   int32_t hmask;           // SWEEP: index bits the group-number bits above log2(W) land on (ascending)
-  int32_t pad1[3];
+  int32_t pad1;
   c128 P[3][4];            // pending matrices (row-major), valid where cls != NONE
   c128 mat[64];            // dense 4x4 / 8x8 gate of this sweep
 };
@@ -131,6 +140,8 @@ struct qsb_ctl {
   qsb_dec dec[QSB_CHUNK];      // ... and their decoded form (control warp, lane-parallel decode)
   double wpart[32 * 4];        // per-warp partial sums (workers)
   double red[2][4];            // this CTA's contribution to a cluster reduction, double-buffered
+  double red_total[4];         // cluster-wide result handed to the control warp (RDM1)
+  unsigned long long xbar;     // mbarrier of the workers-only cluster barrier (device)
 };
 
 // ---- small helpers ---------------------------------------------------------------
@@ -198,24 +209,36 @@ QSB_HD int qsb_choice(const double* p, int k, double u) {
 // quarter-warp differ in group bits 0..2, so these go to one free position out of each pair
 // {0,3}, {1,4}, {2,5}: every LDS.128 / STS.128 of a sweep is then conflict-free whatever the targets
 // (unless the targets cover both members of a pair).  The remaining positions follow in ascending order.
-QSB_HD void qsb_group_order(int m, int nb, const int* bits, int8_t* pos) {
-  uint32_t used = 0;
-  for (int k = 0; k < nb; ++k) used |= 1u << bits[k];
-  int cnt = 0;
+QSB_HD uint64_t qsb_group_order(int m, uint32_t used, int wbits, int nfree, int* hmask) {
+  const uint32_t all = m >= 32 ? 0xffffffffu : ((1u << m) - 1u);
+  uint64_t pos = 0;
+  int cnt = 0, hm = 0;
   for (int j = 0; j < 3; ++j) {
     int q = -1;
     if (j < m && !((used >> j) & 1u)) q = j;
     else if (j + 3 < m && !((used >> (j + 3)) & 1u)) q = j + 3;
-    if (q >= 0) { pos[cnt++] = (int8_t)q; used |= 1u << q; }
+    if (q >= 0) {
+      pos |= (uint64_t)q << (4 * cnt);
+      if (cnt >= wbits && cnt < nfree) hm |= 1 << q;
+      ++cnt;
+      used |= 1u << q;
+    }
   }
-  for (int q = 0; q < m; ++q)
-    if (!((used >> q) & 1u)) pos[cnt++] = (int8_t)q;
-  for (; cnt < 16; ++cnt) pos[cnt] = 0;
+  uint32_t rest = ~used & all;
+  while (rest && cnt < 16) {
+    const int q = QSB_CTZ(rest);
+    pos |= (uint64_t)q << (4 * cnt);
+    if (cnt >= wbits && cnt < nfree) hm |= 1 << q;
+    ++cnt;
+    rest &= rest - 1;
+  }
+  *hmask = hm;
+  return pos;
 }
-// deposit the low `nbits` bits of g onto the positions pos[0..nbits)
-QSB_HD int qsb_deposit(int g, const int8_t* pos, int nbits) {
+// deposit the low `nbits` bits of g onto the positions packed in `pos`
+QSB_HD int qsb_deposit(int g, uint64_t pos, int nbits) {
   int r = 0;
-  for (int t = 0; t < nbits; ++t) r |= ((g >> t) & 1) << pos[t];
+  for (int t = 0; t < nbits; ++t) r |= ((g >> t) & 1) << (int)((pos >> (4 * t)) & 15u);
   return r;
 }
 
@@ -596,9 +619,20 @@ QSB_HD void qsb_worker_loop(Env& env, const qsb_exec_args& a) {
         double v[4];
         qsb_partial_rdm1(env, m, d->b[0], v);
         qsb_block_reduce(env, v, 4);
+        if (env.C > 1) {
+          if (env.wid == 0)
+            for (int k = 0; k < 4; ++k) env.ctl()->red[parity][k] = v[k];
+          env.cluster_sync_w();
+          if (env.wid == 0)
+            for (int k = 0; k < 4; ++k) {
+              double s = 0.0;
+              for (int r = 0; r < env.C; ++r) s += env.peer_ctl(r)->red[parity][k];
+              v[k] = s;
+            }
+        }
         if (env.wid == 0)
-          for (int k = 0; k < 4; ++k) env.ctl()->red[parity][k] = v[k];
-        env.handoff_w();                    // control warps gather after this barrier
+          for (int k = 0; k < 4; ++k) env.ctl()->red_total[k] = v[k];
+        env.handoff_w();                    // the local control warp reads red_total after this barrier
         parity ^= 1;
         break;
       }
@@ -630,7 +664,7 @@ QSB_HD void qsb_worker_loop(Env& env, const qsb_exec_args& a) {
     o[0] = pw;
     for (int k = 0; k < 8; ++k) { o[1 + k] = pb[k]; o[9 + k] = pn[k]; }
   }
-  if (env.C > 1) env.cluster_sync_w();      // no CTA may exit while a peer can still read its shared memory
+  if (env.C > 1) env.cluster_exit();        // no CTA may exit while a peer can still read its shared memory
 }
 
 // =========================================================================================
@@ -643,12 +677,13 @@ struct qsb_cstate {
   uint32_t seq;                    // descriptors published so far
   uint64_t clsword;                // 2-bit structure class per slot bit
   int parity;
-  bool cl_wait;                    // a cluster-barrier arrival of this warp has not been waited for yet
   // per-unit constants
   int64_t t, tile, dim;
   bool record;
   bool prof;
   unsigned long long ring_wait;    // cycles blocked on a full ring
+  unsigned long long t_decode, t_fold, t_slow, n_slow;   // control-warp cycles per phase (profiling only)
+  unsigned long long t_emit_body, t_emit_pub, n_emit;
 };
 
 QSB_HD int qsb_cls_of(uint64_t w, int b) { return (int)((w >> (2 * b)) & 3u); }
@@ -657,9 +692,13 @@ QSB_HD uint64_t qsb_cls_set(uint64_t w, int b, int cls) {
 }
 // slot bits (as a bit mask) whose class is not NONE
 QSB_HD uint32_t qsb_cls_mask(uint64_t w) {
-  uint32_t r = 0;
-  for (int b = 0; b < 32; ++b) if ((w >> (2 * b)) & 3u) r |= 1u << b;
-  return r;
+  uint64_t any = (w | (w >> 1)) & 0x5555555555555555ull;        // bit 2b set <=> class of b is not NONE
+  any = (any | (any >> 1)) & 0x3333333333333333ull;              // compress the even bits
+  any = (any | (any >> 2)) & 0x0f0f0f0f0f0f0f0full;
+  any = (any | (any >> 4)) & 0x00ff00ff00ff00ffull;
+  any = (any | (any >> 8)) & 0x0000ffff0000ffffull;
+  any = (any | (any >> 16)) & 0x00000000ffffffffull;
+  return (uint32_t)any;
 }
 QSB_HD void qsb_pend_identity(c128* P) { P[0] = qsb_c(1, 0); P[1] = qsb_c(0, 0); P[2] = qsb_c(0, 0); P[3] = qsb_c(1, 0); }
 // P <- U P
@@ -687,39 +726,43 @@ QSB_HD void qsb_desc_end(Env& env, qsb_cstate& st) {
   env.ring_publish((int)(st.seq % QSB_RING));
   ++st.seq;
 }
-// one cluster-barrier event the control warp takes part in without waiting for its completion
+// publish one sweep over `nb` local bits (bits[0] = MSB of the gate index) and reset their pending matrices.
+// The lanes of the control warp share the copies: entry e of bit k goes through lane 4k + e.
 template <class Env>
-QSB_HD void qsb_cluster_event(Env& env, qsb_cstate& st) {
-  if (env.C == 1) return;
-  if (st.cl_wait) env.cluster_wait_c();
-  env.cluster_arrive_c();
-  st.cl_wait = true;
-}
-
-// publish one sweep over `nb` local bits (bits[0] = MSB of the gate index) and reset their pending matrices
-template <class Env>
-QSB_CTL void qsb_emit_sweep(Env& env, qsb_cstate& st, int m, int gate, int nb, const int* bits, const c128* mat_src) {
+QSB_CTL void qsb_emit_sweep(Env& env, qsb_cstate& st, int m, int gate, int nb, int b0, int b1, int b2, const c128* mat_src) {
   qsb_desc* d = qsb_desc_begin(env, st);
   qsb_ctl* ctl = env.ctl();
+  const unsigned long long pe0 = st.prof ? env.clock() : 0;
+  const uint64_t w = st.clsword;
+  env.sync_control();                          // the fold's pending matrices are visible to every lane
+  for (int e = env.clane; e < 4 * nb; e += env.CL) {
+    const int k = e >> 2, j = e & 3;
+    const int b = k == 0 ? b0 : (k == 1 ? b1 : b2);
+    d->P[k][j] = ctl->pend[b][j];
+    ctl->pend[b][j] = qsb_c((j == 0 || j == 3) ? 1.0 : 0.0, 0.0);
+  }
   if (env.lead) {
     d->kind = QSB_D_SWEEP; d->gate = gate; d->k = nb; d->flags = 0;
-    for (int k = 0; k < nb; ++k) {
-      const int b = bits[k], cls = qsb_cls_of(st.clsword, b);
-      d->b[k] = b; d->cls[k] = cls;
-      for (int e = 0; e < 4; ++e) d->P[k][e] = ctl->pend[b][e];
-      if (cls != QSB_CLS_NONE) qsb_pend_identity(ctl->pend[b]);
-    }
-    qsb_group_order(m, nb, bits, d->pos);
-    int hm = 0;
-    for (int t = env.wbits; t < m - nb; ++t) hm |= 1 << d->pos[t];
+    d->b[0] = b0; d->b[1] = b1; d->b[2] = b2;
+    d->cls[0] = qsb_cls_of(w, b0); d->cls[1] = nb > 1 ? qsb_cls_of(w, b1) : 0; d->cls[2] = nb > 2 ? qsb_cls_of(w, b2) : 0;
+    uint32_t used = 1u << b0;
+    if (nb > 1) used |= 1u << b1;
+    if (nb > 2) used |= 1u << b2;
+    int hm;
+    d->pos = qsb_group_order(m, used, env.wbits, m - nb, &hm);
     d->hmask = hm;
   }
   if (mat_src) {
     const int cnt = 1 << (2 * nb);
     for (int e = env.clane; e < cnt; e += env.CL) d->mat[e] = mat_src[e];
   }
-  for (int k = 0; k < nb; ++k) st.clsword = qsb_cls_set(st.clsword, bits[k], QSB_CLS_NONE);
+  uint64_t nw = qsb_cls_set(w, b0, QSB_CLS_NONE);
+  if (nb > 1) nw = qsb_cls_set(nw, b1, QSB_CLS_NONE);
+  if (nb > 2) nw = qsb_cls_set(nw, b2, QSB_CLS_NONE);
+  st.clsword = nw;
+  const unsigned long long pe1 = st.prof ? env.clock() : 0;
   qsb_desc_end(env, st);
+  if (st.prof) { st.t_emit_body += pe1 - pe0; st.t_emit_pub += env.clock() - pe1; st.n_emit += 1; }
 }
 
 // apply and reset every pending matrix in `which` (slot-bit mask; local bits three per sweep, rank bits
@@ -731,12 +774,11 @@ QSB_CTL void qsb_flush(Env& env, qsb_cstate& st, int m, uint32_t which) {
   while (todo) {
     int bits[3], nb = 0;
     while (todo && nb < 3) {
-      int b = 31;
-      while (!((todo >> b) & 1u)) --b;
+      const int b = QSB_MSB(todo);
       bits[nb++] = b;
       todo &= ~(1u << b);
     }
-    qsb_emit_sweep(env, st, m, QSB_G_NONE, nb, bits, (const c128*)nullptr);
+    qsb_emit_sweep(env, st, m, QSB_G_NONE, nb, bits[0], nb > 1 ? bits[1] : 0, nb > 2 ? bits[2] : 0, (const c128*)nullptr);
   }
   uint32_t gtodo = m >= 32 ? 0u : (pending >> m);
   for (int gb = 0; gtodo; ++gb, gtodo >>= 1) {
@@ -749,8 +791,6 @@ QSB_CTL void qsb_flush(Env& env, qsb_cstate& st, int m, uint32_t which) {
     }
     st.clsword = qsb_cls_set(st.clsword, m + gb, QSB_CLS_NONE);
     qsb_desc_end(env, st);
-    const int ns = qsb_gflush_syncs(m, env.W);
-    for (int s = 0; s < ns; ++s) qsb_cluster_event(env, st);
   }
 }
 
@@ -760,14 +800,8 @@ QSB_CTL void qsb_ctl_rdm1(Env& env, qsb_cstate& st, int b, double v[4]) {
   qsb_desc* d = qsb_desc_begin(env, st);
   if (env.lead) { d->kind = QSB_D_RDM1; d->k = 1; d->b[0] = b; }
   qsb_desc_end(env, st);
-  if (env.C > 1 && st.cl_wait) { env.cluster_wait_c(); st.cl_wait = false; }
   env.handoff_c();
-  for (int k = 0; k < 4; ++k) {
-    double s = 0.0;
-    for (int r = 0; r < env.C; ++r) s += env.peer_ctl(r)->red[st.parity][k];
-    v[k] = s;
-  }
-  st.parity ^= 1;
+  for (int k = 0; k < 4; ++k) v[k] = env.ctl()->red_total[k];
 }
 
 template <class Env>
@@ -779,10 +813,6 @@ QSB_CTL void qsb_emit_store(Env& env, qsb_cstate& st, const qsb_exec_args& a, co
     d->perm = perm; d->gptr = out; d->probs = probs; d->tile = st.tile;
   }
   qsb_desc_end(env, st);
-  if (a.flags & QSB_RUN_NORMALIZE) {
-    qsb_cluster_event(env, st);
-    st.parity ^= 1;
-  }
 }
 
 // ---- lane-parallel decode of one op (any control lane) ------------------------------------------
@@ -913,16 +943,14 @@ QSB_CTL void qsb_control_slow(Env& env, const qsb_exec_args& a, qsb_cstate& st, 
     }
     // ---------------- multi-qubit gates: one sweep = pending matrices of the bits + the gate
     case QSB_OP_CX: case QSB_OP_CZ: case QSB_OP_SWAP: case QSB_OP_U2: {
-      int bits[2] = {op.b0, op.b1};
       const int g = op.kind == QSB_OP_CX ? QSB_G_CX : op.kind == QSB_OP_CZ ? QSB_G_CZ :
                     op.kind == QSB_OP_SWAP ? QSB_G_SWAP : QSB_G_DENSE;
-      qsb_emit_sweep(env, st, m, g, 2, bits, op.kind == QSB_OP_U2 ? (const c128*)(a.cdata + op.data) : (const c128*)nullptr);
+      qsb_emit_sweep(env, st, m, g, 2, op.b0, op.b1, 0, op.kind == QSB_OP_U2 ? (const c128*)(a.cdata + op.data) : (const c128*)nullptr);
       break;
     }
     case QSB_OP_CCX: case QSB_OP_CSWAP: case QSB_OP_U3Q: {
-      int bits[3] = {op.b0, op.b1, op.b2};
       const int g = op.kind == QSB_OP_CCX ? QSB_G_CCX : op.kind == QSB_OP_CSWAP ? QSB_G_CSWAP : QSB_G_DENSE;
-      qsb_emit_sweep(env, st, m, g, 3, bits, op.kind == QSB_OP_U3Q ? (const c128*)(a.cdata + op.data) : (const c128*)nullptr);
+      qsb_emit_sweep(env, st, m, g, 3, op.b0, op.b1, op.b2, op.kind == QSB_OP_U3Q ? (const c128*)(a.cdata + op.data) : (const c128*)nullptr);
       break;
     }
     case QSB_OP_REMAP: {
@@ -931,8 +959,6 @@ QSB_CTL void qsb_control_slow(Env& env, const qsb_exec_args& a, qsb_cstate& st, 
       qsb_desc* d = qsb_desc_begin(env, st);
       if (env.lead) { d->kind = QSB_D_REMAP; d->k = 2; d->b[0] = gb; d->b[1] = lb; }
       qsb_desc_end(env, st);
-      const int ns = qsb_remap_syncs(m, env.W);
-      for (int s = 0; s < ns; ++s) qsb_cluster_event(env, st);
       const int ca = qsb_cls_of(st.clsword, lb), cb = qsb_cls_of(st.clsword, m + gb);
       if (env.lead)
         for (int e = 0; e < 4; ++e) { c128 x = ctl->pend[lb][e]; ctl->pend[lb][e] = ctl->pend[m + gb][e]; ctl->pend[m + gb][e] = x; }
@@ -979,13 +1005,13 @@ QSB_HD void qsb_control_unit(Env& env, qsb_cstate& st, const qsb_exec_args& a, i
       d->gptr = a.states ? a.states + ((a.flags & QSB_RUN_LOAD_BROADCAST) ? 0 : t * st.dim) : nullptr;
     }
     qsb_desc_end(env, st);
-    if (a.flags & QSB_RUN_LOAD) qsb_cluster_event(env, st);     // matches the barrier at the end of a LOAD
   }
 
   for (int64_t pc0 = 0; pc0 < a.n_ops; pc0 += QSB_CHUNK) {
     const int len = (int)((a.n_ops - pc0) < QSB_CHUNK ? (a.n_ops - pc0) : QSB_CHUNK);
     // ---- phase A: the lanes decode a chunk in parallel (op records, uniforms, angles, matrices)
     env.sync_control();
+    unsigned long long pc_t0 = st.prof ? env.clock() : 0;
     for (int i = env.clane; i < len; i += env.CL) {
       const qsb_op op = ops[pc0 + i];
       double u = 0.0;
@@ -995,29 +1021,50 @@ QSB_HD void qsb_control_unit(Env& env, qsb_cstate& st, const qsb_exec_args& a, i
       qsb_decode_op(env, a, st, op, u, prm, &ctl->dec[i]);
     }
     env.sync_control();
+    if (st.prof) st.t_decode += env.clock() - pc_t0;
 
-    // ---- phase B: fold the MUL records in order (one lane, a tight loop), stop at every SLOW op
+    // ---- phase B: fold the MUL records in order up to the next SLOW op.  Control lane L owns slot L: it keeps
+    // that slot's pending matrix in registers over the segment and multiplies in the ops aimed at it (the
+    // select keeps the loop branch-free, so consecutive ops overlap); every lane tracks the class word.
     int i = 0;
     while (i < len) {
       uint64_t w = st.clsword;
-      if (lead) {
-        while (i < len) {
-          const qsb_dec* d = &ctl->dec[i];
+      pc_t0 = st.prof ? env.clock() : 0;
+      env.sync_control();
+      int stop = i;
+      for (int slot = env.clane; slot < 32; slot += env.CL) {      // one iteration per lane on the device
+        c128 p0 = ctl->pend[slot][0], p1 = ctl->pend[slot][1], p2 = ctl->pend[slot][2], p3 = ctl->pend[slot][3];
+        bool dirty = false;
+        int j = i;
+        for (; j < len; ++j) {
+          const qsb_dec* d = &ctl->dec[j];
           const int type = d->type;
           if (type == QSB_DEC_SLOW) break;
-          if (type == QSB_DEC_MUL) {
-            const int b = d->b & 31;
-            qsb_pend_apply(ctl->pend[b], d->U);
+          if (type != QSB_DEC_MUL) continue;
+          const int b = d->b & 31;
+          if (slot == env.clane) {
             const int c = qsb_cls_of(w, b), uc = d->ucls;
             w = qsb_cls_set(w, b, c > uc ? c : uc);
           }
-          ++i;
+          const bool mine = b == slot;
+          const c128 u0 = d->U[0], u1 = d->U[1], u2 = d->U[2], u3 = d->U[3];
+          const c128 n0 = qsb_fma(u1, p2, qsb_mul(u0, p0)), n1 = qsb_fma(u1, p3, qsb_mul(u0, p1));
+          const c128 n2 = qsb_fma(u3, p2, qsb_mul(u2, p0)), n3 = qsb_fma(u3, p3, qsb_mul(u2, p1));
+          p0 = mine ? n0 : p0; p1 = mine ? n1 : p1; p2 = mine ? n2 : p2; p3 = mine ? n3 : p3;
+          dirty |= mine;
         }
+        if (dirty) { ctl->pend[slot][0] = p0; ctl->pend[slot][1] = p1; ctl->pend[slot][2] = p2; ctl->pend[slot][3] = p3; }
+        stop = j;
       }
-      i = env.bcast_i(i);
-      st.clsword = env.bcast_u64(w);
+      i = stop;
+      st.clsword = w;
+      env.sync_control();
+      if (st.prof) st.t_fold += env.clock() - pc_t0;
       if (i < len) {
+        pc_t0 = st.prof ? env.clock() : 0;
+        const unsigned long long rw0 = st.ring_wait;
         qsb_control_slow(env, a, st, i);
+        if (st.prof) { st.t_slow += env.clock() - pc_t0 - (st.ring_wait - rw0); st.n_slow += 1; }
         ++i;
       }
     }
@@ -1036,8 +1083,10 @@ QSB_HD void qsb_control_unit(Env& env, qsb_cstate& st, const qsb_exec_args& a, i
 template <class Env>
 QSB_HD void qsb_control_loop(Env& env, const qsb_exec_args& a, int64_t first, int64_t stride) {
   qsb_cstate st;
-  st.seq = 0; st.clsword = 0; st.parity = 0; st.cl_wait = false;
+  st.seq = 0; st.clsword = 0; st.parity = 0;
   st.prof = a.prof != nullptr; st.ring_wait = 0;
+  st.t_decode = st.t_fold = st.t_slow = st.n_slow = 0;
+  st.t_emit_body = st.t_emit_pub = st.n_emit = 0;
   const unsigned long long c0 = st.prof ? env.clock() : 0;
   const int64_t total = a.count << a.tile_bits;
   for (int64_t u = first; u < total; u += stride) qsb_control_unit(env, st, a, u);
@@ -1046,12 +1095,11 @@ QSB_HD void qsb_control_loop(Env& env, const qsb_exec_args& a, int64_t first, in
     o[17] = st.ring_wait;
     o[18] = env.clock() - c0;
     o[19] = st.seq;
+    o[20] = st.t_decode; o[21] = st.t_fold; o[22] = st.t_slow; o[23] = st.n_slow;
+    o[24] = st.t_emit_body; o[25] = st.t_emit_pub; o[26] = st.n_emit;
   }
   qsb_desc* d = qsb_desc_begin(env, st);
   if (env.lead) d->kind = QSB_D_EXIT;
   qsb_desc_end(env, st);
-  if (env.C > 1) {
-    qsb_cluster_event(env, st);
-    env.cluster_wait_c();
-  }
+  if (env.C > 1) env.cluster_exit();
 }

@@ -88,26 +88,48 @@ struct DeviceEnv {
   // ---- descriptor ring
   __device__ __forceinline__ void ring_wait_empty(int s) { __syncwarp(); qsb_bar_sync(QSB_BAR_EMPTY + s, W + QSB_CTL_THREADS); }
   __device__ __forceinline__ void ring_publish(int s) {
-    __syncwarp();
-    __threadfence_block();
-    qsb_bar_arrive(QSB_BAR_FULL + s, W + QSB_CTL_THREADS);
+    __syncwarp();                              // bar.arrive orders this warp's prior shared-memory writes for the
+    qsb_bar_arrive(QSB_BAR_FULL + s, W + QSB_CTL_THREADS);   // threads that complete the barrier: no extra fence
   }
   __device__ __forceinline__ void ring_wait_full(int s) { qsb_bar_sync(QSB_BAR_FULL + s, W + QSB_CTL_THREADS); }
   __device__ __forceinline__ void ring_release(int s) { qsb_bar_arrive(QSB_BAR_EMPTY + s, W + QSB_CTL_THREADS); }
   // ---- barriers
   __device__ __forceinline__ void sync_workers() { qsb_bar_sync(QSB_BAR_WORKERS, W); }
   __device__ __forceinline__ void sync_control() { __syncwarp(); }
-  __device__ __forceinline__ void cluster_sync_w() { qsb_cluster_arrive(); qsb_cluster_wait(); }
-  __device__ __forceinline__ void cluster_arrive_c() { __syncwarp(); qsb_cluster_arrive(); }
-  __device__ __forceinline__ void cluster_wait_c() { qsb_cluster_wait(); }
-  // workers -> control hand-off of a reduction (every CTA of the cluster takes part)
-  __device__ __forceinline__ void handoff_w() {
-    if (CS > 1) cluster_sync_w(); else qsb_bar_sync(QSB_BAR_ALL, W + QSB_CTL_THREADS);
+  // Cluster barrier among the WORKERS of all CTAs (the control warps run ahead and never take part): the CTA's
+  // workers meet on a named barrier, one of them arrives on every peer's mbarrier (expected count = cluster
+  // size), then every worker waits for its own CTA's mbarrier phase.
+  int xphase;
+  __device__ __forceinline__ uint32_t xbar_addr() { return (uint32_t)__cvta_generic_to_shared(&ctl()->xbar); }
+  __device__ __forceinline__ void cluster_sync_w() {
+    if (CS == 1) { qsb_bar_sync(QSB_BAR_WORKERS, W); return; }
+    qsb_bar_sync(QSB_BAR_WORKERS, W);
+    const uint32_t local = xbar_addr();
+    if (wid < CS) {                            // worker r signals peer r (release arrives issued one after the other
+      uint32_t remote;                         // by a single thread cost ~500 cycles each)
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(wid));
+      asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+    }
+    if (wid == 0) {
+      // one thread waits for the phase (256 pollers would fight the arrivals for the barrier unit) ...
+      uint32_t done = 0;
+      while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(local), "r"((uint32_t)xphase) : "memory");
+      }
+    }
+    qsb_bar_sync(QSB_BAR_WORKERS, W);          // ... and releases the others
+    xphase ^= 1;
   }
-  __device__ __forceinline__ void handoff_c() {
-    __syncwarp();
-    if (CS > 1) { qsb_cluster_arrive(); qsb_cluster_wait(); } else qsb_bar_sync(QSB_BAR_ALL, W + QSB_CTL_THREADS);
-  }
+  // every thread of every CTA (kernel start: the mbarriers are initialised; kernel end: nobody reads a peer's
+  // shared memory any more)
+  __device__ __forceinline__ void cluster_exit() { __syncwarp(); qsb_cluster_arrive(); qsb_cluster_wait(); }
+  // workers -> local control warp hand-off of a reduction result
+  __device__ __forceinline__ void handoff_w() { qsb_bar_sync(QSB_BAR_ALL, W + QSB_CTL_THREADS); }
+  __device__ __forceinline__ void handoff_c() { __syncwarp(); qsb_bar_sync(QSB_BAR_ALL, W + QSB_CTL_THREADS); }
 };
 
 template <int CS>
@@ -115,6 +137,14 @@ __global__ void __launch_bounds__(QSB_MAX_WORKERS + QSB_CTL_THREADS, 1)
 qsb_traj_kernel(const __grid_constant__ qsb_exec_args a) {
   DeviceEnv<CS> env(a.m);
   env.prof_ = a.prof;
+  env.xphase = 0;
+  if (CS > 1) {
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(env.xbar_addr()), "r"(CS) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    env.cluster_exit();                       // every mbarrier of the cluster is initialised before its first use
+  }
   if (env.wid >= 0) {
     qsb_worker_loop(env, a);
   } else {

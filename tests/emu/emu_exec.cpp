@@ -26,7 +26,8 @@ struct Cta {
 struct Shared {
   int C, W, m;
   std::vector<std::unique_ptr<Cta>> cta;
-  std::unique_ptr<std::barrier<>> cluster;    // every thread of every CTA of the cluster, like barrier.cluster
+  std::unique_ptr<std::barrier<>> cluster;    // the workers of every CTA of the cluster (mbarrier-based on the device)
+  std::unique_ptr<std::barrier<>> cluster_all; // every thread of every CTA, like barrier.cluster (kernel exit)
   std::mutex mu;
 };
 
@@ -58,11 +59,10 @@ struct HostEnv {
   void ring_release(int s) { (void)me().empty[s]->arrive(); }
   void sync_workers() { me().workers->arrive_and_wait(); }
   void sync_control() {}
-  void cluster_sync_w() { sh->cluster->arrive_and_wait(); }
-  void cluster_arrive_c() { tok.emplace(sh->cluster->arrive()); }
-  void cluster_wait_c() { sh->cluster->wait(std::move(*tok)); tok.reset(); }
-  void handoff_w() { if (C > 1) sh->cluster->arrive_and_wait(); else me().all->arrive_and_wait(); }
-  void handoff_c() { if (C > 1) sh->cluster->arrive_and_wait(); else me().all->arrive_and_wait(); }
+  void cluster_sync_w() { if (C > 1) sh->cluster->arrive_and_wait(); else me().workers->arrive_and_wait(); }
+  void cluster_exit() { sh->cluster_all->arrive_and_wait(); }
+  void handoff_w() { me().all->arrive_and_wait(); }
+  void handoff_c() { me().all->arrive_and_wait(); }
 };
 
 extern "C" int emu_run(int n, int m, int T, const qsb_op* ops, int64_t n_ops, int64_t ops_stride, const double* cdata, int64_t n_cdata,
@@ -91,7 +91,8 @@ extern "C" int emu_run(int n, int m, int T, const qsb_op* ops, int64_t n_ops, in
     c.workers.reset(new std::barrier<>(T));
     c.all.reset(new std::barrier<>(T + 1));
   }
-  sh.cluster.reset(new std::barrier<>(sh.C * (T + 1)));
+  sh.cluster.reset(new std::barrier<>(sh.C * T));
+  sh.cluster_all.reset(new std::barrier<>(sh.C * (T + 1)));
 
   qsb_exec_args a;
   memset(&a, 0, sizeof a);

@@ -28,6 +28,8 @@ def prof(label, prog, T):
     p0 = p[0] / units
     print(f"--- {label}: CTAs={len(p)} units/cluster={units}  per unit, CTA 0 (cycles):")
     print(f"   control total {p0[18]:10.0f}   ring-full wait {p0[17]:10.0f}   descriptors {p0[19]:7.1f}")
+    print(f"   control: decode {p0[20]:10.0f}  fold {p0[21]:10.0f}  slow ops {p0[22]:10.0f} (n={p0[23]:6.1f}, {p0[22] / max(p0[23], 1):6.0f} each, excl. ring wait)")
+    print(f"   control emit_sweep: n={p0[26]:6.1f} body {p0[24] / max(p0[26], 1):7.0f}  publish {p0[25] / max(p0[26], 1):7.0f} cycles each")
     print(f"   worker wait   {p0[0]:10.0f}")
     for k, name in enumerate(KINDS):
         if p0[9 + k]:
