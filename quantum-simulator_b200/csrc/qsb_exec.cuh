@@ -141,6 +141,7 @@ struct qsb_ctl {
   double wpart[32 * 4];        // per-warp partial sums (workers)
   double red[2][4];            // this CTA's contribution to a cluster reduction, double-buffered
   double red_total[4];         // cluster-wide result handed to the control warp (RDM1)
+  double wtab[192];            // weighted marginal: products of diagonal-pending weights over index bits 0..6 | 7..12
   unsigned long long xbar;     // mbarrier of the workers-only cluster barrier (device)
 };
 
@@ -420,6 +421,40 @@ QSB_PASS void qsb_partial_rdm1(Env& env, int m, int b, double v[4]) {
   }
 }
 
+// Marginal of slot bit b when some slots still carry DIAGONAL pending matrices (they need no flush: a diagonal
+// only reweights |amplitude|^2).  wt[j][v] = |P_j[v][v]|^2; v[0], v[1] = sum over x with x_b = 0 / 1 of
+// W(x) |phi_x|^2, W(x) = prod_j wt[j][x_j] (rank bits contribute this CTA's constant factor).
+template <class Env>
+QSB_PASS void qsb_partial_marginal_w(Env& env, int m, int b, const double* wt, double v[4]) {
+  const c128* tile = env.tile();
+  double* tab = env.ctl()->wtab;
+  const int nlo = m < 7 ? m : 7, nhi = m - nlo;
+  env.sync_workers();                                    // previous users of wtab are done
+  for (int e = env.wid; e < 192; e += env.W) {
+    double w = 1.0;
+    if (e < 128) { for (int j = 0; j < nlo; ++j) w *= wt[2 * j + ((e >> j) & 1)]; }
+    else { for (int j = 0; j < nhi; ++j) w *= wt[2 * (nlo + j) + (((e - 128) >> j) & 1)]; }
+    tab[e] = w;
+  }
+  env.sync_workers();
+  double crank = 1.0;
+  for (int g = 0; (1 << g) < env.C; ++g) crank *= wt[2 * (m + g) + ((env.rank >> g) & 1)];
+  v[0] = v[1] = v[2] = v[3] = 0.0;
+  if (b >= m) {
+    double s = 0.0;
+    for (int i = env.wid; i < (1 << m); i += env.W) s += tab[i & 127] * tab[128 + (i >> 7)] * qsb_norm2(tile[qsb_slot(i)]);
+    v[(env.rank >> (b - m)) & 1] = s * crank;
+    return;
+  }
+  const int cnt = 1 << (m - 1);
+  for (int g = env.wid; g < cnt; g += env.W) {
+    const int i0 = qsb_ins0(g, b), i1 = i0 | (1 << b);
+    v[0] += tab[i0 & 127] * tab[128 + (i0 >> 7)] * qsb_norm2(tile[qsb_slot(i0)]);
+    v[1] += tab[i1 & 127] * tab[128 + (i1 >> 7)] * qsb_norm2(tile[qsb_slot(i1)]);
+  }
+  v[0] *= crank; v[1] *= crank;
+}
+
 template <class Env>
 QSB_HD void qsb_build_perm(Env& env, const int32_t* perm, int n) {
   uint32_t* tab = env.ctl()->perm;
@@ -617,7 +652,8 @@ QSB_HD void qsb_worker_loop(Env& env, const qsb_exec_args& a) {
       case QSB_D_GFLUSH: qsb_do_gflush(env, m, d); break;
       case QSB_D_RDM1: {
         double v[4];
-        qsb_partial_rdm1(env, m, d->b[0], v);
+        if (d->flags & 1) qsb_partial_marginal_w(env, m, d->b[0], reinterpret_cast<const double*>(d->mat), v);
+        else qsb_partial_rdm1(env, m, d->b[0], v);
         qsb_block_reduce(env, v, 4);
         if (env.C > 1) {
           if (env.wid == 0)
@@ -694,6 +730,16 @@ QSB_HD uint64_t qsb_cls_set(uint64_t w, int b, int cls) {
 QSB_HD uint32_t qsb_cls_mask(uint64_t w) {
   uint64_t any = (w | (w >> 1)) & 0x5555555555555555ull;        // bit 2b set <=> class of b is not NONE
   any = (any | (any >> 1)) & 0x3333333333333333ull;              // compress the even bits
+  any = (any | (any >> 2)) & 0x0f0f0f0f0f0f0f0full;
+  any = (any | (any >> 4)) & 0x00ff00ff00ff00ffull;
+  any = (any | (any >> 8)) & 0x0000ffff0000ffffull;
+  any = (any | (any >> 16)) & 0x00000000ffffffffull;
+  return (uint32_t)any;
+}
+// slot bits whose class is DENSE (both class bits set)
+QSB_HD uint32_t qsb_cls_dense_mask(uint64_t w) {
+  uint64_t any = (w & (w >> 1)) & 0x5555555555555555ull;
+  any = (any | (any >> 1)) & 0x3333333333333333ull;
   any = (any | (any >> 2)) & 0x0f0f0f0f0f0f0f0full;
   any = (any | (any >> 4)) & 0x00ff00ff00ff00ffull;
   any = (any | (any >> 8)) & 0x0000ffff0000ffffull;
@@ -796,9 +842,18 @@ QSB_CTL void qsb_flush(Env& env, qsb_cstate& st, int m, uint32_t which) {
 
 // (unnormalised) 1-qubit reduced density matrix sums of slot bit b of the CURRENT state, in every control warp
 template <class Env>
-QSB_CTL void qsb_ctl_rdm1(Env& env, qsb_cstate& st, int b, double v[4]) {
+QSB_CTL void qsb_ctl_rdm1(Env& env, qsb_cstate& st, int b, double v[4], bool weighted = false) {
   qsb_desc* d = qsb_desc_begin(env, st);
-  if (env.lead) { d->kind = QSB_D_RDM1; d->k = 1; d->b[0] = b; }
+  if (env.lead) { d->kind = QSB_D_RDM1; d->k = 1; d->b[0] = b; d->flags = weighted ? 1 : 0; }
+  if (weighted) {
+    // weights |P[v][v]|^2 of the (diagonal) pending matrices that stay pending; identity where nothing is pending
+    env.sync_control();
+    double* wt = reinterpret_cast<double*>(d->mat);
+    for (int e = env.clane; e < 64; e += env.CL) {
+      const c128 z = env.ctl()->pend[e >> 1][(e & 1) ? 3 : 0];
+      wt[e] = z.x * z.x + z.y * z.y;
+    }
+  }
   qsb_desc_end(env, st);
   env.handoff_c();
   for (int k = 0; k < 4; ++k) v[k] = env.ctl()->red_total[k];
@@ -907,17 +962,22 @@ QSB_CTL void qsb_control_slow(Env& env, const qsb_exec_args& a, qsb_cstate& st, 
       const double* cd = a.cdata + op.data;
       const double u = ctl->u[i], gam = cd[0];
       double v[4];
-      qsb_flush(env, st, m, all_bits);
-      qsb_ctl_rdm1(env, st, b, v);
+      // only DENSE pending matrices have to be applied before the marginal is taken: diagonal ones (the K0's of
+      // earlier draws, Rz / phase gates) just reweight |amplitude|^2 and ride along as weights
+      qsb_flush(env, st, m, qsb_cls_dense_mask(st.clsword));
+      qsb_ctl_rdm1(env, st, b, v, true);
       double p[2] = {v[0] + (1.0 - gam) * v[1], gam * v[1]};
       const int idx = qsb_choice(p, 2, u);
       if (st.record) a.branches[st.t * a.branches_stride + op.draw] = idx;
+      const int cls = qsb_cls_of(st.clsword, b);
       if (env.lead) {
-        c128* P = ctl->pend[b];
-        if (idx == 0) { P[0] = qsb_c(1, 0); P[1] = qsb_c(0, 0); P[2] = qsb_c(0, 0); P[3] = qsb_c(cd[1], 0); }
-        else { P[0] = qsb_c(0, 0); P[1] = qsb_c(1, 0); P[2] = qsb_c(0, 0); P[3] = qsb_c(0, 0); }   // a0 <- a1, a1 <- 0
+        c128 K[4];
+        if (idx == 0) { K[0] = qsb_c(1, 0); K[1] = qsb_c(0, 0); K[2] = qsb_c(0, 0); K[3] = qsb_c(cd[1], 0); }
+        else { K[0] = qsb_c(0, 0); K[1] = qsb_c(1, 0); K[2] = qsb_c(0, 0); K[3] = qsb_c(0, 0); }   // a0 <- a1, a1 <- 0
+        qsb_pend_apply(ctl->pend[b], K);
       }
-      st.clsword = qsb_cls_set(st.clsword, b, idx == 0 ? QSB_CLS_RDIAG : QSB_CLS_DENSE);
+      const int kcls = idx == 0 ? QSB_CLS_RDIAG : QSB_CLS_DENSE;
+      st.clsword = qsb_cls_set(st.clsword, b, cls > kcls ? cls : kcls);
       break;
     }
     case QSB_OP_KRAUS_GEN: {              // target is a local bit (host compiler remaps it in)
