@@ -68,6 +68,9 @@ struct alignas(16) c128 { double x, y; };
 #ifndef QSB_GROUP_POS
 #define QSB_GROUP_POS 1        // 1: bank-conflict-free group order (qsb_group_order), 0: ascending free bits
 #endif
+#ifndef QSB_REMAP_PUSH
+#define QSB_REMAP_PUSH 0      // measured: push (local read + DSMEM store, 3 barriers) 13.5k cycles vs pull 12.8k
+#endif
 #define QSB_PROF_WORDS 128
 #define QSB_RING 6             // descriptors in flight between control warp and workers
 
@@ -126,7 +129,7 @@ struct alignas(16) qsb_dec {
   int32_t type;            // SKIP | MUL: pend[b] <- U pend[b] | SLOW: needs the descriptor ring / the state
   int32_t b;               // slot bit
   int32_t ucls;            // structure class of U
-  int32_t pad;
+  int32_t next;            // MUL: index (in the chunk) of the next MUL op on the same slot, or QSB_CHUNK
   c128 U[4];
 };
 
@@ -141,6 +144,7 @@ struct qsb_ctl {
   double wpart[32 * 4];        // per-warp partial sums (workers)
   double red[2][4];            // this CTA's contribution to a cluster reduction, double-buffered
   double red_total[4];         // cluster-wide result handed to the control warp (RDM1)
+  int32_t head[32];            // first MUL op of each slot in the staged chunk (QSB_CHUNK = none)
   double wtab[192];            // weighted marginal: products of diagonal-pending weights over index bits 0..6 | 7..12
   unsigned long long xbar;     // mbarrier of the workers-only cluster barrier (device)
 };
@@ -576,6 +580,26 @@ QSB_PASS void qsb_do_remap(Env& env, int m, const qsb_desc* d) {
   const unsigned long long pt0 = env.prof_on() ? env.clock() : 0;
   env.cluster_sync_w();                       // every CTA finished the sweeps before the exchange
   if (env.prof_on()) env.prof_add(120, env.clock() - pt0);
+#if QSB_REMAP_PUSH
+  // Push: read OUR outgoing half into registers (local), barrier (the partner has its outgoing half -- the
+  // positions we are about to overwrite -- in registers too), store into the PARTNER's tile (posted DSMEM
+  // stores instead of latency-bound DSMEM loads), barrier before anyone reads its tile again.
+  c128* peer_w = const_cast<c128*>(peer);
+  for (int base = 0; base < cnt; base += QSB_REMAP_REGS * env.W) {
+#pragma unroll
+    for (int e = 0; e < QSB_REMAP_REGS; ++e) {
+      int g = base + e * env.W + env.wid;
+      if (g < cnt) val[e] = tile[qsb_slot(qsb_ins0(g, lb) | ((1 - mybit) << lb))];
+    }
+    env.cluster_sync_w();
+#pragma unroll
+    for (int e = 0; e < QSB_REMAP_REGS; ++e) {
+      int g = base + e * env.W + env.wid;
+      if (g < cnt) peer_w[qsb_slot(qsb_ins0(g, lb) | (mybit << lb))] = val[e];
+    }
+  }
+  env.cluster_sync_w();
+#else
   // Round r pulls the partner's groups g and then overwrites OUR groups g (the ones the partner pulls
   // in the same round), so one cluster barrier between the two halves of a round is enough.
   for (int base = 0; base < cnt; base += QSB_REMAP_REGS * env.W) {
@@ -591,6 +615,7 @@ QSB_PASS void qsb_do_remap(Env& env, int m, const qsb_desc* d) {
       if (g < cnt) tile[qsb_slot(qsb_ins0(g, lb) | ((1 - mybit) << lb))] = val[e];
     }
   }
+#endif
 }
 QSB_HD int qsb_remap_syncs(int m, int W) {
   const int cnt = 1 << (m - 1), per = QSB_REMAP_REGS * W;
@@ -722,30 +747,15 @@ struct qsb_cstate {
   unsigned long long t_emit_body, t_emit_pub, n_emit;
 };
 
-QSB_HD int qsb_cls_of(uint64_t w, int b) { return (int)((w >> (2 * b)) & 3u); }
+// class word: two bit planes, bit b of the low word = class bit 0 of slot b, bit b of the high word = class bit 1
+QSB_HD int qsb_cls_of(uint64_t w, int b) { return (int)(((w >> b) & 1u) | (((w >> (32 + b)) & 1u) << 1)); }
 QSB_HD uint64_t qsb_cls_set(uint64_t w, int b, int cls) {
-  return (w & ~((uint64_t)3 << (2 * b))) | ((uint64_t)cls << (2 * b));
+  const uint64_t keep = ~(((uint64_t)1 << b) | ((uint64_t)1 << (32 + b)));
+  return (w & keep) | ((uint64_t)(cls & 1) << b) | ((uint64_t)(cls >> 1) << (32 + b));
 }
-// slot bits (as a bit mask) whose class is not NONE
-QSB_HD uint32_t qsb_cls_mask(uint64_t w) {
-  uint64_t any = (w | (w >> 1)) & 0x5555555555555555ull;        // bit 2b set <=> class of b is not NONE
-  any = (any | (any >> 1)) & 0x3333333333333333ull;              // compress the even bits
-  any = (any | (any >> 2)) & 0x0f0f0f0f0f0f0f0full;
-  any = (any | (any >> 4)) & 0x00ff00ff00ff00ffull;
-  any = (any | (any >> 8)) & 0x0000ffff0000ffffull;
-  any = (any | (any >> 16)) & 0x00000000ffffffffull;
-  return (uint32_t)any;
-}
-// slot bits whose class is DENSE (both class bits set)
-QSB_HD uint32_t qsb_cls_dense_mask(uint64_t w) {
-  uint64_t any = (w & (w >> 1)) & 0x5555555555555555ull;
-  any = (any | (any >> 1)) & 0x3333333333333333ull;
-  any = (any | (any >> 2)) & 0x0f0f0f0f0f0f0f0full;
-  any = (any | (any >> 4)) & 0x00ff00ff00ff00ffull;
-  any = (any | (any >> 8)) & 0x0000ffff0000ffffull;
-  any = (any | (any >> 16)) & 0x00000000ffffffffull;
-  return (uint32_t)any;
-}
+// slot bits (as a bit mask) whose class is not NONE / is DENSE
+QSB_HD uint32_t qsb_cls_mask(uint64_t w) { return (uint32_t)w | (uint32_t)(w >> 32); }
+QSB_HD uint32_t qsb_cls_dense_mask(uint64_t w) { return (uint32_t)w & (uint32_t)(w >> 32); }
 QSB_HD void qsb_pend_identity(c128* P) { P[0] = qsb_c(1, 0); P[1] = qsb_c(0, 0); P[2] = qsb_c(0, 0); P[3] = qsb_c(1, 0); }
 // P <- U P
 QSB_HD void qsb_pend_apply(c128* P, const c128* U) {
@@ -1036,6 +1046,37 @@ QSB_CTL void qsb_control_slow(Env& env, const qsb_exec_args& a, qsb_cstate& st, 
   }
 }
 
+// Per-slot lists over the decoded chunk: head[slot] = first MUL op of the slot, dec[i].next = next one (QSB_CHUNK =
+// none).  Device: 32 ops per step, __match_any_sync groups the lanes by slot; the windows are walked from the
+// last to the first so that each op can point at the first op of its slot in the later windows.
+template <class Env>
+QSB_HD void qsb_link_chunk(Env& env, qsb_ctl* ctl, int len) {
+  env.sync_control();
+  for (int slot = env.clane; slot < 32; slot += env.CL) ctl->head[slot] = QSB_CHUNK;
+  env.sync_control();
+  if (Env::CL == 1) {                                   // one control thread (host emulation): plain backward scan
+    for (int j = len - 1; j >= 0; --j) {
+      qsb_dec* d = &ctl->dec[j];
+      if (d->type != QSB_DEC_MUL) continue;
+      d->next = ctl->head[d->b & 31];
+      ctl->head[d->b & 31] = j;
+    }
+    return;
+  }
+  for (int base = ((len - 1) / 32) * 32; base >= 0; base -= 32) {
+    const int j = base + env.clane;
+    const bool mul = j < len && ctl->dec[j].type == QSB_DEC_MUL;
+    const int slot = mul ? (ctl->dec[j].b & 31) : 0;
+    // lanes of the same slot; ops that are not MUL get a key of their own
+    const uint32_t grp = env.match_any(mul ? slot : 32 + env.clane);
+    const uint32_t above = grp & ~((2u << env.clane) - 1u);
+    if (mul) ctl->dec[j].next = above ? base + QSB_CTZ(above) : ctl->head[slot];
+    env.sync_control();                                 // every lane read head[] before the group leaders update it
+    if (mul && QSB_CTZ(grp) == env.clane) ctl->head[slot] = j;
+    env.sync_control();
+  }
+}
+
 // ---- one unit (trajectory, or tile of a streamed state) on the control warp ----------------
 template <class Env>
 QSB_HD void qsb_control_unit(Env& env, qsb_cstate& st, const qsb_exec_args& a, int64_t unit) {
@@ -1083,41 +1124,49 @@ QSB_HD void qsb_control_unit(Env& env, qsb_cstate& st, const qsb_exec_args& a, i
     env.sync_control();
     if (st.prof) st.t_decode += env.clock() - pc_t0;
 
-    // ---- phase B: fold the MUL records in order up to the next SLOW op.  Control lane L owns slot L: it keeps
-    // that slot's pending matrix in registers over the segment and multiplies in the ops aimed at it (the
-    // select keeps the loop branch-free, so consecutive ops overlap); every lane tracks the class word.
+    // ---- phase A2: link the MUL records of each slot into a list (head[slot], dec[].next), lane-parallel
+    qsb_link_chunk(env, ctl, len);
+    int cur[(32 + Env::CL - 1) / Env::CL];              // next unapplied op of the slot(s) this lane owns
+    {
+      int q = 0;
+      for (int slot = env.clane; slot < 32; slot += env.CL) cur[q++] = ctl->head[slot];
+    }
+
+    // ---- phase B: fold the MUL records up to the next SLOW op.  Control lane L owns slot L and walks that slot's
+    // list; the lanes run their (independent) chains side by side, so a segment costs its longest chain.
     int i = 0;
     while (i < len) {
-      uint64_t w = st.clsword;
       pc_t0 = st.prof ? env.clock() : 0;
       env.sync_control();
       int stop = i;
-      for (int slot = env.clane; slot < 32; slot += env.CL) {      // one iteration per lane on the device
-        c128 p0 = ctl->pend[slot][0], p1 = ctl->pend[slot][1], p2 = ctl->pend[slot][2], p3 = ctl->pend[slot][3];
-        bool dirty = false;
-        int j = i;
-        for (; j < len; ++j) {
-          const qsb_dec* d = &ctl->dec[j];
-          const int type = d->type;
-          if (type == QSB_DEC_SLOW) break;
-          if (type != QSB_DEC_MUL) continue;
-          const int b = d->b & 31;
-          if (slot == env.clane) {
-            const int c = qsb_cls_of(w, b), uc = d->ucls;
-            w = qsb_cls_set(w, b, c > uc ? c : uc);
+      while (stop < len && ctl->dec[stop].type != QSB_DEC_SLOW) ++stop;
+      uint64_t w = st.clsword;
+      uint32_t lo = 0, hi = 0;                            // class bit planes rebuilt from the lanes
+      {
+        int q = 0;
+        for (int slot = env.clane; slot < 32; slot += env.CL, ++q) {
+          int c = qsb_cls_of(w, slot);
+          if (cur[q] < stop) {
+            c128 p0 = ctl->pend[slot][0], p1 = ctl->pend[slot][1], p2 = ctl->pend[slot][2], p3 = ctl->pend[slot][3];
+            int j = cur[q];
+            while (j < stop) {
+              const qsb_dec* d = &ctl->dec[j];
+              const c128 u0 = d->U[0], u1 = d->U[1], u2 = d->U[2], u3 = d->U[3];
+              const c128 n0 = qsb_fma(u1, p2, qsb_mul(u0, p0)), n1 = qsb_fma(u1, p3, qsb_mul(u0, p1));
+              const c128 n2 = qsb_fma(u3, p2, qsb_mul(u2, p0)), n3 = qsb_fma(u3, p3, qsb_mul(u2, p1));
+              p0 = n0; p1 = n1; p2 = n2; p3 = n3;
+              c = c > d->ucls ? c : d->ucls;
+              j = d->next;
+            }
+            cur[q] = j;
+            ctl->pend[slot][0] = p0; ctl->pend[slot][1] = p1; ctl->pend[slot][2] = p2; ctl->pend[slot][3] = p3;
           }
-          const bool mine = b == slot;
-          const c128 u0 = d->U[0], u1 = d->U[1], u2 = d->U[2], u3 = d->U[3];
-          const c128 n0 = qsb_fma(u1, p2, qsb_mul(u0, p0)), n1 = qsb_fma(u1, p3, qsb_mul(u0, p1));
-          const c128 n2 = qsb_fma(u3, p2, qsb_mul(u2, p0)), n3 = qsb_fma(u3, p3, qsb_mul(u2, p1));
-          p0 = mine ? n0 : p0; p1 = mine ? n1 : p1; p2 = mine ? n2 : p2; p3 = mine ? n3 : p3;
-          dirty |= mine;
+          lo |= env.ballot_slot(c & 1, slot);
+          hi |= env.ballot_slot(c >> 1, slot);
         }
-        if (dirty) { ctl->pend[slot][0] = p0; ctl->pend[slot][1] = p1; ctl->pend[slot][2] = p2; ctl->pend[slot][3] = p3; }
-        stop = j;
       }
       i = stop;
-      st.clsword = w;
+      st.clsword = ((uint64_t)hi << 32) | lo;
       env.sync_control();
       if (st.prof) st.t_fold += env.clock() - pc_t0;
       if (i < len) {

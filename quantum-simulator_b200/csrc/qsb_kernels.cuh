@@ -79,6 +79,9 @@ struct DeviceEnv {
   __device__ __forceinline__ bool prof_on() { return prof_ != nullptr && threadIdx.x == 0; }
   __device__ __forceinline__ void prof_add(int slot, unsigned long long v) { prof_[(size_t)blockIdx.x * QSB_PROF_WORDS + slot] += v; }
   __device__ __forceinline__ int cta_id() { return (int)blockIdx.x; }
+  // control-warp collectives: lanes with the same key; bit `slot` of the result = this lane's predicate (lane == slot)
+  __device__ __forceinline__ uint32_t match_any(int key) { return __match_any_sync(0xffffffffu, key); }
+  __device__ __forceinline__ uint32_t ballot_slot(int pred, int slot) { (void)slot; return __ballot_sync(0xffffffffu, pred); }
   // lane 0 of the control warp -> every lane
   __device__ __forceinline__ int bcast_i(int x) { return __shfl_sync(0xffffffffu, x, 0); }
   __device__ __forceinline__ uint64_t bcast_u64(uint64_t x) {

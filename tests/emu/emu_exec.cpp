@@ -51,6 +51,8 @@ struct HostEnv {
   bool prof_on() { return false; }
   void prof_add(int, unsigned long long) {}
   int cta_id() { return cta; }
+  uint32_t match_any(int) { return 1u; }
+  uint32_t ballot_slot(int pred, int slot) { return pred ? (1u << slot) : 0u; }
   int bcast_i(int x) { return x; }
   uint64_t bcast_u64(uint64_t x) { return x; }
   void ring_wait_empty(int s) { me().empty[s]->arrive_and_wait(); }
