@@ -375,7 +375,7 @@ def measure_other_paths(ctx, sim, qc16):
         nb = 26
         gl = [(g.gate_name, list(g.target_qubits), list(g.params)) for g in
               to_gate_instances(layered_circuit(nb, 20, 2026), GateInstance)]
-        st = BigState(nb, layout="textbook")
+        st = BigState(nb, layout="textbook", distributed=False)   # rank 0 alone: no collectives here
         st.apply_gates(gl[:8])
         torch.cuda.synchronize()
         t0 = time.perf_counter()

@@ -145,14 +145,15 @@ def exchange_rank_bits(src, dst, group=None):
 class BigState:
     """One n-qubit complex128 state on this rank's GPU (a 2^(n-g) shard when the process group has 2^g ranks)."""
 
-    def __init__(self, n, *, group=None, device=None, layout="reference", local_bits=None):
+    def __init__(self, n, *, group=None, device=None, layout="reference", local_bits=None, distributed=True):
+        """distributed=False keeps the whole state on this device even when a process group is initialised."""
         import torch
         import torch.distributed as dist
         self.torch = torch
         self.n = int(n)
         self.layout = layout
         self.group = group
-        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.world = dist.get_world_size(group) if (distributed and dist.is_available() and dist.is_initialized()) else 1
         self.rank = dist.get_rank(group) if self.world > 1 else 0
         self.g = self.world.bit_length() - 1
         if 1 << self.g != self.world:
