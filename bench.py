@@ -358,6 +358,23 @@ def measure_other_paths(ctx, sim, qc16):
     out["config3_ensemble_rho"] = {"qubits": n, "trials": 500, "seconds": dt, "trace": float(np.real(np.trace(rho))),
                                    "purity": float(np.real(np.sum(rho * rho.T))),
                                    "includes": "host draws, 500 trajectories, DMMA rho, 256 MiB d2h"}
+    # config 3, second half: all 66 pair mutual informations of every per-column snapshot of every trajectory
+    from quantum_sim.engine.analysis import all_pairs_mutual_information_device
+    dp, _ = s12._program(qc, record_steps=True)
+    T3, ns, dim3 = 500, dp.prog.n_snapshots, 1 << n
+    u3 = ctx.to_device(np.random.default_rng(3).random((T3, dp.prog.n_draws)))
+    snaps = ctx.alloc(T3 * ns * dim3 * 16)
+    ctx.run(dp, 8, uniforms=u3, uniforms_stride=dp.prog.n_draws, snapshots=snaps, store=False)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ctx.run(dp, T3, uniforms=u3, uniforms_stride=dp.prog.n_draws, snapshots=snaps, store=False)
+    mi = all_pairs_mutual_information_device(n, snaps, 0, T3 * ns)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    out["config3_layer_mi"] = {"qubits": n, "trials": T3, "layers": ns, "pairs": int(mi.shape[1]), "seconds": dt,
+                               "state_layers_per_s": T3 * ns / dt, "mean_mi_bits": float(mi.mean()),
+                               "includes": "trajectories with per-column snapshots, RDMs, Jacobi entropies, d2h of MI"}
+    del snaps
     # config 4: Steane [[7,1,3]] cycles (13 qubits), batched
     qs = QECSimulator(SteaneCode())
     seeds = list(range(1000, 1000 + 2048))

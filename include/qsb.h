@@ -199,6 +199,11 @@ int qsb_masked_parity(qsb_ctx* ctx, int32_t n, qsb_buffer* states, int64_t first
  * rdm1 complex128[count][n][2][2], rdm2 complex128[count][n(n-1)/2][4][4], pair order (i<j) row-major */
 int qsb_rdm_all(qsb_ctx* ctx, int32_t n, qsb_buffer* states, int64_t first, int64_t count,
                 qsb_buffer* rdm1, qsb_buffer* rdm2);
+/* all-pairs mutual information I(i:j) = max(0, S_i + S_j - S_ij) in bits (analysis.py:99-104, :183-191, :315-333):
+ * reduced density matrices as in qsb_rdm_all, eigenvalues by Jacobi rotations on the device, eigenvalues <= 1e-15
+ * dropped.  mi double[count][n(n-1)/2] (pairs i<j row-major); entropy1 double[count][n] or NULL */
+int qsb_mi_all_pairs(qsb_ctx* ctx, int32_t n, qsb_buffer* states, int64_t first, int64_t count,
+                     qsb_buffer* mi, qsb_buffer* entropy1);
 /* ensemble rho (simulator.py:195-198): rho[i][j] += scale * sum_t psi_t[i] conj(psi_t[j]) */
 int qsb_rho_accumulate(qsb_ctx* ctx, int32_t n, qsb_buffer* states, int64_t first, int64_t count,
                        double scale, qsb_buffer* rho);

@@ -739,6 +739,32 @@ int qsb_rdm_all(qsb_ctx* ctx, int32_t n, qsb_buffer* states, int64_t first, int6
   return QSB_OK;
 }
 
+int qsb_mi_all_pairs(qsb_ctx* ctx, int32_t n, qsb_buffer* states, int64_t first, int64_t count, qsb_buffer* mi,
+                     qsb_buffer* entropy1) {
+  CHECK_N(ctx, n);
+  if (n < 2) return fail(ctx, QSB_E_INVAL, "mutual information needs at least 2 qubits");
+  const int npairs = n * (n - 1) / 2;
+  int rc;
+  if (count <= 0) return count == 0 ? QSB_OK : fail(ctx, QSB_E_INVAL, "negative count");
+  if ((rc = need(ctx, mi, count * npairs * 8, "mutual information"))) return rc;
+  if (entropy1 && (rc = need(ctx, entropy1, count * n * 8, "entropy1"))) return rc;
+  qsb_buffer *r1 = nullptr, *r2 = nullptr;
+  if ((rc = qsb_buffer_alloc(ctx, count * n * 4 * 16, &r1))) return rc;
+  if ((rc = qsb_buffer_alloc(ctx, count * npairs * 16 * 16, &r2))) { qsb_buffer_free(r1); return rc; }
+  rc = qsb_rdm_all(ctx, n, states, first, count, r1, r2);
+  if (rc == QSB_OK) {
+    const int64_t total = count * npairs;
+    qsb_mi_kernel<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>((const c128*)r1->ptr, (const c128*)r2->ptr, n,
+                                                                           npairs, total,
+                                                                           entropy1 ? (double*)entropy1->ptr : nullptr,
+                                                                           (double*)mi->ptr);
+    rc = after_launch(ctx, "mutual_information");
+  }
+  qsb_buffer_free(r1);
+  qsb_buffer_free(r2);
+  return rc;
+}
+
 int qsb_rho_accumulate(qsb_ctx* ctx, int32_t n, qsb_buffer* states, int64_t first, int64_t count, double scale,
                        qsb_buffer* rho) {
   CHECK_N(ctx, n);

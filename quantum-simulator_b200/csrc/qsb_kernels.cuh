@@ -379,6 +379,90 @@ __global__ void qsb_rdm2_kernel(const c128* __restrict__ psi, int n, int npairs,
   }
 }
 
+// ---- entropies and mutual information on the device -----------------------------------------------------
+// Eigenvalues of a D x D Hermitian matrix (D = 2 or 4, row-major complex) by cyclic complex Jacobi rotations;
+// the reference calls np.linalg.eigvalsh (analysis.py:102).  Off-diagonal mass below 1e-32 of the norm ends it.
+template <int D>
+__device__ void qsb_herm_eigvals(const c128* a_in, double* lam) {
+  c128 A[D][D];
+#pragma unroll
+  for (int r = 0; r < D; ++r)
+#pragma unroll
+    for (int c = 0; c < D; ++c) A[r][c] = a_in[r * D + c];
+  for (int sweep = 0; sweep < 24; ++sweep) {
+    double off = 0.0, dia = 0.0;
+#pragma unroll
+    for (int r = 0; r < D; ++r) {
+      dia += A[r][r].x * A[r][r].x;
+#pragma unroll
+      for (int c = r + 1; c < D; ++c) off += A[r][c].x * A[r][c].x + A[r][c].y * A[r][c].y;
+    }
+    if (off <= 1e-34 * dia || off == 0.0) break;
+#pragma unroll
+    for (int p = 0; p < D - 1; ++p)
+#pragma unroll
+      for (int q = p + 1; q < D; ++q) {
+        const double ax = A[p][q].x, ay = A[p][q].y;
+        const double mag = sqrt(ax * ax + ay * ay);
+        if (mag == 0.0) continue;
+        // phase e = a_pq / |a_pq|; real rotation angle from the 2x2 block [[app, mag], [mag, aqq]]
+        const double ex = ax / mag, ey = ay / mag;
+        const double tau = (A[q][q].x - A[p][p].x) / (2.0 * mag);
+        const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+        const double c = 1.0 / sqrt(1.0 + t * t), sn = t * c;
+        // columns: A <- A G with G[p][p] = c, G[q][p] = -sn conj(e)... implemented as the unitary
+        // U = [[c, sn e], [-sn conj(e), c]] acting on rows/cols (p, q):  A <- U^H A U
+#pragma unroll
+        for (int k = 0; k < D; ++k) {                      // A <- A U  (columns p, q)
+          const c128 akp = A[k][p], akq = A[k][q];
+          // new_p = c akp - sn conj(e) akq ; new_q = sn e akp + c akq
+          A[k][p] = make_double2(c * akp.x - sn * (ex * akq.x + ey * akq.y), c * akp.y - sn * (ex * akq.y - ey * akq.x));
+          A[k][q] = make_double2(sn * (ex * akp.x - ey * akp.y) + c * akq.x, sn * (ex * akp.y + ey * akp.x) + c * akq.y);
+        }
+#pragma unroll
+        for (int k = 0; k < D; ++k) {                      // A <- U^H A  (rows p, q)
+          const c128 apk = A[p][k], aqk = A[q][k];
+          // new_p = c apk - sn e aqk ; new_q = sn conj(e) apk + c aqk
+          A[p][k] = make_double2(c * apk.x - sn * (ex * aqk.x - ey * aqk.y), c * apk.y - sn * (ex * aqk.y + ey * aqk.x));
+          A[q][k] = make_double2(sn * (ex * apk.x + ey * apk.y) + c * aqk.x, sn * (ex * apk.y - ey * apk.x) + c * aqk.y);
+        }
+      }
+  }
+#pragma unroll
+  for (int r = 0; r < D; ++r) lam[r] = A[r][r].x;
+}
+
+// -sum lambda log2 lambda over eigenvalues > 1e-15 (analysis.py:102-104)
+template <int D>
+__device__ double qsb_entropy_bits(const c128* rho) {
+  double lam[D], s = 0.0;
+  qsb_herm_eigvals<D>(rho, lam);
+#pragma unroll
+  for (int r = 0; r < D; ++r) if (lam[r] > 1e-15) s -= lam[r] * log2(lam[r]);
+  return s;
+}
+
+// I(i:j) = max(0, S_i + S_j - S_ij) for all pairs i < j (analysis.py:183-191, :315-333); one thread per (state, pair)
+__global__ void qsb_mi_kernel(const c128* __restrict__ rdm1, const c128* __restrict__ rdm2, int n, int npairs,
+                              int64_t total, double* __restrict__ s1_out, double* __restrict__ mi) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int64_t t = e / npairs;
+  const int pair = (int)(e % npairs);
+  int qi = 0, rem = pair;
+  while (rem >= n - 1 - qi) { rem -= n - 1 - qi; ++qi; }
+  const int qj = qi + 1 + rem;
+  const double si = qsb_entropy_bits<2>(rdm1 + (t * n + qi) * 4);
+  const double sj = qsb_entropy_bits<2>(rdm1 + (t * n + qj) * 4);
+  const double sij = qsb_entropy_bits<4>(rdm2 + (t * npairs + pair) * 16);
+  const double v = si + sj - sij;
+  mi[e] = v > 0.0 ? v : 0.0;
+  if (s1_out) {                                   // single-qubit entropies, written once per qubit
+    if (rem == 0 && qi < n - 1) s1_out[t * n + qi] = si;
+    if (pair == npairs - 1) s1_out[t * n + qj] = sj;
+  }
+}
+
 // rho[i][j] += scale * sum_t psi_t[i] conj(psi_t[j])   (simulator.py:195-198)
 // The one dense contraction of the path: with A = Re Psi, B = Im Psi (dim x N),
 //   Re rho = A A^T + B B^T,   Im rho = B A^T - A B^T

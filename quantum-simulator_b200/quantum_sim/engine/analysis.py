@@ -46,8 +46,19 @@ def pair_index(n, a, b):
     return i * (n - 1) - i * (i - 1) // 2 + (j - i - 1)
 
 
+def all_pairs_mutual_information_device(n, states, first, count) -> np.ndarray:
+    """float64[count][n(n-1)/2]: I(i:j) in bits for every i < j of `count` device-resident states, entirely on the
+    device (RDM reductions + Jacobi eigenvalues + entropies; analysis.py:99-104, :183-191)."""
+    c = runtime.ctx()
+    npairs = n * (n - 1) // 2
+    out = c.alloc(max(count * npairs, 1) * 8)
+    c.mi_all_pairs(n, states, first, count, out)
+    return out.download(np.float64, (count, npairs))
+
+
 def all_pairs_mutual_information(state: StateVector) -> np.ndarray:
-    """I(i:j) for every i < j in one device pass (order of analysis.py:331-333)."""
+    """I(i:j) for every i < j in one device pass (order of analysis.py:331-333); eigenvalues on the host with the
+    reference's own np.linalg.eigvalsh (see all_pairs_mutual_information_device for the all-device batch path)."""
     n = state.num_qubits
     r1, r2 = device_rdms(state)
     s1 = _entropy_bits_batch(r1)

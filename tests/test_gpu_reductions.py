@@ -147,3 +147,41 @@ def test_argument_errors(ctx):
     dp = ctx.program(prog)
     with pytest.raises(ValueError):
         ctx.run(dp, 4, states=small)           # states buffer too small
+
+
+@pytest.mark.gpu
+def test_mutual_information_all_pairs_on_device(golden):
+    """qsb_mi_all_pairs (device RDMs + Jacobi eigenvalues + entropies) against the host eigvalsh path and the
+    reference's own mutual_information values frozen in the golden file."""
+    from qsb import capi
+    from quantum_sim.engine.analysis import all_pairs_mutual_information, all_pairs_mutual_information_device
+    from quantum_sim.engine.state_vector import StateVector
+    j, a = golden
+    ctx = capi.get_context()
+    rng = np.random.default_rng(12)
+    for n in (2, 3, 6, 10, 12):
+        count = 5
+        psi = rng.normal(size=(count, 2 ** n)) + 1j * rng.normal(size=(count, 2 ** n))
+        psi[0] = 0.0
+        psi[0, 0] = psi[0, -1] = 1.0                      # GHZ: every pair has I = 1 bit, rank-deficient RDMs
+        psi[1] = 0.0
+        psi[1, 5 % 2 ** n] = 1.0                          # product state: I = 0, zero eigenvalues
+        psi /= np.linalg.norm(psi, axis=1, keepdims=True)
+        buf = ctx.to_device(psi)
+        got = all_pairs_mutual_information_device(n, buf, 0, count)
+        for t in range(count):
+            sv = StateVector._from_host(n, psi[t].copy())
+            want = all_pairs_mutual_information(sv)
+            assert np.max(np.abs(got[t] - want)) < 1e-10, (n, t)
+        assert np.max(np.abs(got[0] - (2.0 if n == 2 else 1.0))) < 1e-12 and np.max(np.abs(got[1])) < 1e-12
+    # the reference's numbers: per-layer MI of a GHZ-4 run with record_steps (tests/golden/make_golden.py)
+    from quantum_sim.engine.circuit import QuantumCircuit, GateInstance
+    from quantum_sim.engine.simulator import Simulator
+    from qsb.workloads import ghz
+    qc = QuantumCircuit(4)
+    for g in ghz(4):
+        qc.add_gate(GateInstance(g[0], list(g[1]), list(g[2]), g[3]))
+    res = Simulator().run(qc, shots=0, record_steps=True)
+    states = np.stack([s.data for s in res.step_states])
+    got = all_pairs_mutual_information_device(4, ctx.to_device(states), 0, len(states))
+    assert np.max(np.abs(got - np.array(j["ghz4_layer_mi"]))) < 1e-10
