@@ -537,15 +537,18 @@ __global__ void __launch_bounds__(256) qsb_rho_kernel(const c128* __restrict__ p
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         const int64_t i = i0 + wr + a * 8 + grp, j = j0 + wc + b * 8 + 2 * tig + c;
-        if (i < dim && j < dim) {
+        // every pair (i, j), i <= j, is written once together with its mirror image, so rho is exactly
+        // Hermitian (as the reference's sum of outer products is); a diagonal tile skips its lower half
+        if (i < dim && j < dim && i <= j) {
+          const double vim = (i == j) ? 0.0 : im[a][b][c];
           c128 o = rho[i * dim + j];
           o.x += scale * re[a][b][c];
-          o.y += scale * im[a][b][c];
+          o.y += scale * vim;
           rho[i * dim + j] = o;
-          if (ti != tj) {
+          if (i != j) {
             c128 m = rho[j * dim + i];
             m.x += scale * re[a][b][c];
-            m.y -= scale * im[a][b][c];
+            m.y -= scale * vim;
             rho[j * dim + i] = m;
           }
         }
