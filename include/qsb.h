@@ -199,6 +199,10 @@ int qsb_masked_parity(qsb_ctx* ctx, int32_t n, qsb_buffer* states, int64_t first
  * rdm1 complex128[count][n][2][2], rdm2 complex128[count][n(n-1)/2][4][4], pair order (i<j) row-major */
 int qsb_rdm_all(qsb_ctx* ctx, int32_t n, qsb_buffer* states, int64_t first, int64_t count,
                 qsb_buffer* rdm1, qsb_buffer* rdm2);
+/* reduced density matrix of k <= 6 kept qubits, ascending (StateAnalysis.partial_trace, analysis.py:120-166):
+ * out complex128[count][2^k][2^k], first kept qubit = most significant bit of the row / column index */
+int qsb_rdm_general(qsb_ctx* ctx, int32_t n, qsb_buffer* states, int64_t first, int64_t count,
+                    const int32_t* keep_qubits, int32_t k, qsb_buffer* out);
 /* all-pairs mutual information I(i:j) = max(0, S_i + S_j - S_ij) in bits (analysis.py:99-104, :183-191, :315-333):
  * reduced density matrices as in qsb_rdm_all, eigenvalues by Jacobi rotations on the device, eigenvalues <= 1e-15
  * dropped.  mi double[count][n(n-1)/2] (pairs i<j row-major); entropy1 double[count][n] or NULL */

@@ -21,6 +21,7 @@ struct qsb_ctx {
   std::string err;
   uint64_t* d_masks;      // scratch for qsb_masked_parity
   c128* d_part;                 // partial sums of the large-state reductions
+  int* d_bits;                  // bit lists of qsb_rdm_general
   unsigned long long* d_prof;   // cycle counters of the last qsb_run (qsb_debug_profile), or NULL
   int prof_ctas;
 };
@@ -104,6 +105,7 @@ int qsb_ctx_create(int device, qsb_ctx** out) {
   c->d_masks = nullptr;
   c->d_prof = nullptr;
   c->d_part = nullptr;
+  c->d_bits = nullptr;
   c->prof_ctas = 0;
   cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
@@ -127,6 +129,7 @@ int qsb_ctx_destroy(qsb_ctx* ctx) {
   cudaFree(ctx->d_masks);
   cudaFree(ctx->d_prof);
   cudaFree(ctx->d_part);
+  cudaFree(ctx->d_bits);
   delete ctx;
   return QSB_OK;
 }
@@ -737,6 +740,35 @@ int qsb_rdm_all(qsb_ctx* ctx, int32_t n, qsb_buffer* states, int64_t first, int6
     if ((rc = after_launch(ctx, "rdm2"))) return rc;
   }
   return QSB_OK;
+}
+
+int qsb_rdm_general(qsb_ctx* ctx, int32_t n, qsb_buffer* states, int64_t first, int64_t count, const int32_t* keep_qubits,
+                    int32_t k, qsb_buffer* out) {
+  CHECK_N(ctx, n);
+  if (k < 1 || k > 6 || k > n || !keep_qubits) return fail(ctx, QSB_E_INVAL, "keep 1..6 qubits, got %d", (int)k);
+  const int64_t dim = (int64_t)1 << n;
+  int rc;
+  if (count <= 0) return count == 0 ? QSB_OK : fail(ctx, QSB_E_INVAL, "negative count");
+  if ((rc = need(ctx, states, (first + count) * dim * 16, "states"))) return rc;
+  if ((rc = need(ctx, out, count * ((int64_t)1 << (2 * k)) * 16, "rdm"))) return rc;
+  int host[40];                                     // kept index bits (qubit q = bit n-1-q), then the environment bits
+  unsigned used = 0;
+  for (int j = 0; j < k; ++j) {
+    const int q = keep_qubits[j];
+    if (q < 0 || q >= n || ((used >> q) & 1u)) return fail(ctx, QSB_E_INVAL, "bad keep_qubits entry %d", q);
+    if (j > 0 && q <= keep_qubits[j - 1]) return fail(ctx, QSB_E_INVAL, "keep_qubits must be ascending");
+    used |= 1u << q;
+    host[j] = n - 1 - q;
+  }
+  int ne = 0;
+  for (int b = 0; b < n; ++b)
+    if (!((used >> (n - 1 - b)) & 1u)) host[8 + ne++] = b;
+  CU(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->d_bits) CU(ctx, cudaMalloc(&ctx->d_bits, 40 * sizeof(int)));
+  CU(ctx, cudaMemcpyAsync(ctx->d_bits, host, 40 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  qsb_rdm_general_kernel<<<(unsigned)count, 256, 0, ctx->stream>>>((const c128*)states->ptr + first * dim, n, k, ctx->d_bits,
+                                                                  ctx->d_bits + 8, (c128*)out->ptr);
+  return after_launch(ctx, "rdm_general");
 }
 
 int qsb_mi_all_pairs(qsb_ctx* ctx, int32_t n, qsb_buffer* states, int64_t first, int64_t count, qsb_buffer* mi,

@@ -379,6 +379,41 @@ __global__ void qsb_rdm2_kernel(const c128* __restrict__ psi, int n, int npairs,
   }
 }
 
+// Reduced density matrix of an arbitrary set of k <= 6 kept qubits (analysis.py:120-166):
+// rho[r][c] = sum_env psi[r, env] conj(psi[c, env]); kept_bits[0] = index bit of the first kept qubit (the MSB of
+// r), env_bits = the other n - k index bits.  One CTA per state; a thread owns whole (r, c) entries, so every
+// entry is one ordered sum (deterministic).
+__global__ void qsb_rdm_general_kernel(const c128* __restrict__ psi, int n, int k, const int* __restrict__ kept_bits,
+                                       const int* __restrict__ env_bits, c128* __restrict__ out) {
+  const int64_t dim = (int64_t)1 << n;
+  const c128* s = psi + blockIdx.x * dim;
+  const int D = 1 << k, ne = n - k;
+  __shared__ int kb[8], eb[32];
+  if (threadIdx.x < k) kb[threadIdx.x] = kept_bits[threadIdx.x];
+  if (threadIdx.x < ne) eb[threadIdx.x] = env_bits[threadIdx.x];
+  __syncthreads();
+  for (int e = threadIdx.x; e < D * D; e += blockDim.x) {
+    const int r = e / D, c = e % D;
+    if (c < r) continue;                               // Hermitian: the lower triangle is mirrored below
+    int64_t ir = 0, ic = 0;
+    for (int j = 0; j < k; ++j) {
+      if ((r >> (k - 1 - j)) & 1) ir |= (int64_t)1 << kb[j];
+      if ((c >> (k - 1 - j)) & 1) ic |= (int64_t)1 << kb[j];
+    }
+    double re = 0.0, im = 0.0;
+    for (int64_t env = 0; env < ((int64_t)1 << ne); ++env) {
+      int64_t base = 0;
+      for (int j = 0; j < ne; ++j) base |= ((env >> j) & 1) << eb[j];
+      const c128 a = s[base | ir], b = s[base | ic];
+      re += a.x * b.x + a.y * b.y;                     // a conj(b)
+      im += a.y * b.x - a.x * b.y;
+    }
+    c128* o = out + (int64_t)blockIdx.x * D * D;
+    o[r * D + c] = make_double2(re, r == c ? 0.0 : im);
+    if (r != c) o[c * D + r] = make_double2(re, -im);
+  }
+}
+
 // ---- entropies and mutual information on the device -----------------------------------------------------
 // Eigenvalues of a D x D Hermitian matrix (D = 2 or 4, row-major complex) by cyclic complex Jacobi rotations;
 // the reference calls np.linalg.eigvalsh (analysis.py:102).  Off-diagonal mass below 1e-32 of the norm ends it.

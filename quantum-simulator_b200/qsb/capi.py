@@ -28,7 +28,7 @@ SYMBOLS = [
     "qsb_host_alloc", "qsb_host_free", "qsb_program_create", "qsb_program_free", "qsb_run",
     "qsb_debug_profile",
     "qsb_probabilities", "qsb_probabilities_sum", "qsb_sample_index", "qsb_overlap",
-    "qsb_masked_parity", "qsb_rdm_all", "qsb_mi_all_pairs", "qsb_rho_accumulate", "qsb_readout_transform",
+    "qsb_masked_parity", "qsb_rdm_all", "qsb_rdm_general", "qsb_mi_all_pairs", "qsb_rho_accumulate", "qsb_readout_transform",
 ]
 
 
@@ -96,6 +96,7 @@ def load_library():
             "qsb_overlap": (C.c_int, [vp, i32, vp, i64, vp, i64, i64, i64, vp]),
             "qsb_masked_parity": (C.c_int, [vp, i32, vp, i64, i64, vp, i32, vp]),
             "qsb_rdm_all": (C.c_int, [vp, i32, vp, i64, i64, vp, vp]),
+            "qsb_rdm_general": (C.c_int, [vp, i32, vp, i64, i64, vp, i32, vp]),
             "qsb_mi_all_pairs": (C.c_int, [vp, i32, vp, i64, i64, vp, vp]),
             "qsb_rho_accumulate": (C.c_int, [vp, i32, vp, i64, i64, dbl, vp]),
             "qsb_readout_transform": (C.c_int, [vp, i32, vp, i64, dbl, dbl]),
@@ -310,6 +311,11 @@ class Context:
         _check(self.lib.qsb_rdm_all(self.handle, n, states.handle, first, count,
                                     rdm1.handle if rdm1 is not None else None,
                                     rdm2.handle if rdm2 is not None else None), self.handle)
+
+    def rdm_general(self, n, states, first, count, keep_qubits, out):
+        kq = np.ascontiguousarray(keep_qubits, dtype=np.int32)
+        _check(self.lib.qsb_rdm_general(self.handle, n, states.handle, first, count, _hostptr(kq), len(kq), out.handle),
+               self.handle)
 
     def mi_all_pairs(self, n, states, first, count, mi, entropy1=None):
         _check(self.lib.qsb_mi_all_pairs(self.handle, n, states.handle, first, count, mi.handle,

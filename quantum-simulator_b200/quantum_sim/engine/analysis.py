@@ -122,12 +122,17 @@ class StateAnalysis:
         k = len(keep)
         if k == n:
             return state.get_density_matrix()
-        r1, r2 = device_rdms(state)
+        r1, r2 = device_rdms(state) if k <= 2 else (None, None)
         if k == 1:
             return r1[keep[0]].copy()
         if k == 2:
             return r2[pair_index(n, keep[0], keep[1])].copy()
-        raise NotImplementedError("device partial_trace keeps 1, 2 or all qubits")
+        if k <= 6:
+            c = runtime.ctx()
+            out = c.alloc(16 << (2 * k))
+            c.rdm_general(n, state._device(), 0, 1, keep, out)
+            return out.download(np.complex128, (2 ** k, 2 ** k))
+        raise NotImplementedError("device partial_trace keeps at most 6 qubits (or all of them)")
 
     # ---- purity ---------------------------------------------------------------------------------
     @staticmethod

@@ -185,3 +185,27 @@ def test_mutual_information_all_pairs_on_device(golden):
     states = np.stack([s.data for s in res.step_states])
     got = all_pairs_mutual_information_device(4, ctx.to_device(states), 0, len(states))
     assert np.max(np.abs(got - np.array(j["ghz4_layer_mi"]))) < 1e-10
+
+
+@pytest.mark.gpu
+def test_partial_trace_general_subsystems():
+    """StateAnalysis.partial_trace / entanglement_entropy for 3..6 kept qubits against the oracle's O(2^n) restatement."""
+    from oracle import qsim_oracle as O
+    from quantum_sim.engine.analysis import StateAnalysis
+    from quantum_sim.engine.state_vector import StateVector
+    rng = np.random.default_rng(21)
+    for n, keep in ((5, [0, 2, 4]), (7, [1, 2, 3, 6]), (9, [0, 3, 4, 7, 8]), (10, [9, 1, 5, 2, 7, 0])):
+        psi = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+        psi /= np.linalg.norm(psi)
+        sv = StateVector._from_host(n, psi.copy())
+        got = StateAnalysis.partial_trace(sv, keep)
+        t = psi.reshape([2] * n)
+        ks = sorted(keep)
+        m = np.moveaxis(t, ks, list(range(len(ks)))).reshape(2 ** len(ks), -1)
+        want = m @ m.conj().T
+        assert np.max(np.abs(got - want)) < 1e-13
+        assert np.max(np.abs(got - got.conj().T)) == 0.0
+        s = StateAnalysis.entanglement_entropy(sv, keep)
+        w = np.linalg.eigvalsh(want)
+        w = w[w > 1e-15]
+        assert abs(s - float(-np.sum(w * np.log2(w)))) < 1e-10
