@@ -92,6 +92,32 @@ class StateAnalysis:
         return float(np.abs(out.download(np.complex128, (1,))[0]) ** 2)
 
     @staticmethod
+    def _sanitize_density_matrix(rho: np.ndarray) -> np.ndarray:
+        """Hermitian symmetrisation + trace normalisation (analysis.py:66-77); works on stacks of matrices."""
+        rho = np.asarray(rho)
+        rho = (rho + np.conj(np.swapaxes(rho, -1, -2))) / 2
+        tr = np.real(np.trace(rho, axis1=-2, axis2=-1))
+        scale = np.where(tr > 1e-15, tr, 1.0)
+        return rho / np.asarray(scale)[..., None, None]
+
+    @staticmethod
+    def _matrix_sqrt(mat: np.ndarray) -> np.ndarray:
+        w, v = np.linalg.eigh(mat)
+        w = np.maximum(w, 0.0)
+        return (v * np.sqrt(w)[..., None, :]) @ np.conj(np.swapaxes(v, -1, -2))
+
+    @staticmethod
+    def density_fidelity(rho: np.ndarray, sigma: np.ndarray):
+        """Uhlmann fidelity (Tr sqrt(sqrt(rho) sigma sqrt(rho)))^2 (analysis.py:47-64).  Small-matrix host linear
+        algebra, like the reference; accepts stacks [..., d, d] and then returns an array."""
+        rho = StateAnalysis._sanitize_density_matrix(rho)
+        sigma = StateAnalysis._sanitize_density_matrix(sigma)
+        sq = StateAnalysis._matrix_sqrt(rho)
+        w = np.maximum(np.linalg.eigvalsh(sq @ sigma @ sq), 0.0)
+        fid = np.minimum(np.sum(np.sqrt(w), axis=-1) ** 2, 1.0)
+        return float(fid) if np.ndim(fid) == 0 else fid
+
+    @staticmethod
     def process_fidelity(ideal: StateVector, actual: StateVector) -> float:
         c = runtime.ctx()
         out = c.alloc(16)

@@ -25,8 +25,8 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-sys.path.insert(0, "/root/reference")
-sys.path.insert(0, os.path.join(ROOT, "quantum-simulator_b200"))
+sys.path.insert(0, "/root/reference")                               # the reference's quantum_sim wins ...
+sys.path.append(os.path.join(ROOT, "quantum-simulator_b200"))       # ... ours only provides qsb.workloads
 
 from quantum_sim.engine.circuit import QuantumCircuit, GateInstance          # noqa: E402
 from quantum_sim.engine.state_vector import StateVector                      # noqa: E402
@@ -410,11 +410,48 @@ def case_cfg3_rho():
     print("cfg3 rho", meta)
 
 
+# ---------------------------------------------------------------- debugger
+def case_debugger():
+    """CircuitDebugger: step snapshots, noise impact, noise attribution, state diff -> golden_debugger.{json,npz}."""
+    from quantum_sim.engine.debugger import CircuitDebugger
+    JD, AD = {}, {}
+    g = layered_circuit(5, 4, 31)
+    spec = {"global": [("depolarizing", 0.05), ("amplitude_damping", 0.1)], "gate": {"CNOT": [("bit_flip", 0.2)]}}
+    JD["gates"], JD["noise"], JD["n"] = g, spec, 5
+    dbg = CircuitDebugger()
+    nm = noise_model(spec, seed=11)
+    snaps = dbg.run_full_debug(circuit(5, g), nm, seed=3)
+    JD["full_debug"] = {"noise_seed": 11, "columns": [s.column_index for s in snaps], "labels": [s.gate_labels for s in snaps],
+                        "fidelity": [s.fidelity for s in snaps], "cumulative_fidelity": [s.cumulative_fidelity for s in snaps],
+                        "entropy": [s.entropy for s in snaps]}
+    AD["dbg_states"] = np.stack([s.state.data for s in snaps])
+    AD["dbg_ideal"] = np.stack([s.ideal_state.data for s in snaps])
+    d = CircuitDebugger.compute_state_diff(snaps[1], snaps[-1])
+    JD["state_diff"] = {"fidelity": d["fidelity"], "tvd": d["tvd"], "entropy_diff": d["entropy_diff"],
+                        "amplitude_diffs": [[a[0], a[1], a[2].real, a[2].imag, a[3].real, a[3].imag, a[4]] for a in d["amplitude_diffs"]]}
+    AD["dbg_prob_diffs"] = d["prob_diffs"]
+    snaps0 = CircuitDebugger().run_full_debug(circuit(5, g), None, seed=3)
+    JD["full_debug_noiseless"] = {"fidelity": [s.fidelity for s in snaps0], "entropy": [s.entropy for s in snaps0]}
+    AD["dbg_states_noiseless"] = np.stack([s.state.data for s in snaps0])
+    imp = CircuitDebugger().compute_noise_impact(circuit(5, g), noise_model(spec), n_trials=7, seed=5)
+    JD["noise_impact"] = [vars(r) for r in imp]
+    att = CircuitDebugger().compute_noise_attribution(circuit(5, g), noise_model(spec), n_trials=7, seed=6)
+    JD["noise_attribution"] = vars(att)
+    with open(os.path.join(HERE, "golden_debugger.json"), "w") as f:
+        json.dump(JD, f, indent=1)
+    np.savez_compressed(os.path.join(HERE, "golden_debugger.npz"), **AD)
+    print("debugger golden written")
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--debugger", action="store_true", help="only (re)write golden_debugger.*")
     ap.add_argument("--slow", action="store_true")
     ap.add_argument("--only-slow", action="store_true")
     args = ap.parse_args()
+    if args.debugger:
+        case_debugger()
+        return
     if not args.only_slow:
         for fn in (case_ghz3, case_sigma, case_random_circuits, case_layered16, case_noisy,
                    case_ensemble, case_measurement, case_analysis, case_qec, case_vqe):
