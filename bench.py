@@ -58,6 +58,11 @@ def measured_peak():
 def _oracle_prefix_worker(args):
     cols, seed = args
     os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    try:                                   # forked workers inherit an already initialised BLAS pool: pin it to 1 thread
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=1)
+    except Exception:
+        pass
     from oracle import qsim_oracle as O
     from qsb.workloads import layered_circuit, config3_noise
     gates = [g for g in layered_circuit(N_QUBITS, DEPTH, CIRCUIT_SEED) if g[3] < cols]
