@@ -390,7 +390,16 @@ def measure_other_paths(ctx, sim, qc16):
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     out["config4_steane_cycles"] = {"cycles": 2048, "seconds": dt, "cycles_per_s": 2048 / dt,
-                                    "includes": "host Pauli decisions, decode table, d2h of syndromes"}
+                                    "includes": "reference streams (one default_rng per trial), decode table, d2h of syndromes"}
+    # throughput mode of config 4: one vectorised generator per sweep point instead of one default_rng per trial
+    Tq = 16384
+    uq = np.random.default_rng(77).random((Tq, 7))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    qs.run_cycles([t % 2 for t in range(Tq)], "depolarizing", 0.05, None, uniforms=uq)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    out["config4_steane_cycles_bulk_draws"] = {"cycles": Tq, "seconds": dt, "cycles_per_s": Tq / dt}
     # config 5 (single-GPU leg): 26-qubit layered circuit streamed through shared memory
     try:
         from qsb.bigstate import BigState

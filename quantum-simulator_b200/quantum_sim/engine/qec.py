@@ -320,56 +320,61 @@ def _sigma1(n, q):
     return _SIGMA1[key]
 
 
-def _pauli_programs(n, per_trial, layout):
+def _pauli_programs(n, codes, qubits, layout):
     """One tiny program per trial: its Paulis (through apply_gate, i.e. with the axis scramble), then a store of
-    the result with the trial's own bit permutation.  Returns a Program with ops_stride = longest list + 1."""
-    stride = max((len(p) for p in per_trial), default=0) + 1
-    B = len(per_trial)
-    ops = np.zeros((B, stride), dtype=OP_DTYPE)
+    the result with the trial's own bit permutation.  Vectorised over the trials.
+
+    codes, qubits: int arrays [T][L]; event l of trial t applies Pauli code (1 X, 2 Y, 3 Z; 0 = no event) to qubit
+    qubits[t][l], in order l = 0..L-1.  Returns a Program with ops_stride = L + 1."""
+    codes = np.asarray(codes, dtype=np.int64).reshape(len(codes), -1)
+    qubits = np.asarray(qubits, dtype=np.int64).reshape(codes.shape)
+    T, L = codes.shape
+    stride = L + 1
+    ops = np.zeros((T, stride), dtype=OP_DTYPE)
     ops["data"], ops["param"], ops["draw"] = -1, -1, -1
+    boa = np.tile(np.arange(n - 1, -1, -1, dtype=np.int64), (T, 1))       # physical bit playing reference axis j
+    pos = np.zeros(T, dtype=np.int64)                                      # next free op slot of each trial
+    rows = np.arange(T)
+    kind_of = np.array([NOP, PX, PY, PZ], dtype=np.int32)
+    for l in range(L):
+        fired = codes[:, l] != 0
+        if not fired.any():
+            continue
+        r = rows[fired]
+        q = qubits[fired, l]
+        ops["kind"][r, pos[r]] = kind_of[codes[fired, l]]
+        ops["b0"][r, pos[r]] = boa[r, q]
+        pos[r] += 1
+        if layout == "reference":
+            for qv in np.unique(q):
+                rr = r[q == qv]
+                boa[rr] = boa[rr][:, np.array(_sigma1(n, int(qv)))]
+    perm = np.empty((T, n), dtype=np.int64)
+    np.put_along_axis(perm, boa, np.tile(np.arange(n - 1, -1, -1, dtype=np.int64), (T, 1)), axis=1)
+    uniq, inv = np.unique(perm, axis=0, return_inverse=True)
     ident = list(range(n))
-    idata = ident + ident                      # load permutation, (unused) store permutation
-    perm_off = {}
-    scrambled = layout == "reference"
-    for t, paulis in enumerate(per_trial):
-        boa = [n - 1 - j for j in range(n)]    # physical bit playing reference axis j
-        for i, (name, q) in enumerate(paulis):
-            ops[t, i]["kind"] = _PAULI_KIND[name]
-            ops[t, i]["b0"] = boa[q]
-            if scrambled:
-                s = _sigma1(n, q)
-                boa = [boa[s[k]] for k in range(n)]
-        perm = [0] * n
-        for axis in range(n):
-            perm[boa[axis]] = n - 1 - axis
-        key = tuple(perm)
-        if key not in perm_off:
-            perm_off[key] = len(idata)
-            idata += perm
-        last = ops[t, len(paulis)]
-        last["kind"], last["b0"], last["aux"] = SNAPSHOT, 0, perm_off[key]
-    return Program(n=n, m=n, ops=ops.reshape(-1), cdata=np.zeros(2), idata=np.array(idata, dtype=np.int32), load_perm=0,
-                   store_perm=n, n_snapshots=1, n_draws=0, n_params=0, normalize=False, ops_stride=stride, n_programs=B)
+    idata = np.concatenate([np.array(ident + ident, dtype=np.int64), uniq.reshape(-1)])
+    ops["kind"][rows, pos] = SNAPSHOT
+    ops["b0"][rows, pos] = 0
+    ops["aux"][rows, pos] = 2 * n + np.asarray(inv).reshape(-1) * n
+    return Program(n=n, m=n, ops=ops.reshape(-1), cdata=np.zeros(2), idata=idata.astype(np.int32), load_perm=0,
+                   store_perm=n, n_snapshots=1, n_draws=0, n_params=0, normalize=False, ops_stride=stride, n_programs=T)
 
 
-def _noise_paulis(noise_type, prob, n_data, rng):
-    """QECSimulator._apply_noise (qec.py:669-693): one rng.random() per data qubit for the three known noise
-    types; an unknown type draws nothing."""
-    fired = []
-    if noise_type in ("bit_flip", "phase_flip"):
-        name = "X" if noise_type == "bit_flip" else "Z"
-        r = rng.random(n_data)
-        fired = [(name, q) for q in range(n_data) if r[q] < prob]
+def _noise_codes(noise_type, prob, uniforms):
+    """QECSimulator._apply_noise (qec.py:669-693) on a [T][n_data] array of the per-qubit draws: Pauli code per data
+    qubit (0 none, 1 X, 2 Y, 3 Z).  An unknown noise type fires nothing."""
+    u = np.asarray(uniforms)
+    codes = np.zeros(u.shape, dtype=np.int64)
+    if noise_type == "bit_flip":
+        codes[u < prob] = 1
+    elif noise_type == "phase_flip":
+        codes[u < prob] = 3
     elif noise_type == "depolarizing":
-        r = rng.random(n_data)
-        for q in range(n_data):
-            if r[q] < prob / 3:
-                fired.append(("X", q))
-            elif r[q] < 2 * prob / 3:
-                fired.append(("Y", q))
-            elif r[q] < prob:
-                fired.append(("Z", q))
-    return fired
+        codes[u < prob] = 3
+        codes[u < 2 * prob / 3] = 2
+        codes[u < prob / 3] = 1
+    return codes
 
 
 class QECSimulator:
@@ -427,13 +432,15 @@ class QECSimulator:
 
         return runtime.cached_program(key, build)
 
-    def run_cycles(self, logical_states, noise_type, noise_prob, seeds):
+    def run_cycles(self, logical_states, noise_type, noise_prob, seeds, uniforms=None):
         """Batched `run_cycle`: arrays of the per-trial scalars
-        {syndrome[B][k], fidelity_before[B], fidelity_after[B], z_exp[B], logical_error[B], corrections[B]}."""
+        {syndrome[B][k], fidelity_before[B], fidelity_after[B], z_exp[B], logical_error[B], corrections[B]}.
+        `uniforms` (float64[B][data_qubits], optional) replaces the per-trial `default_rng(seed)` draws -- the
+        throughput mode of BASELINE config 4, where one vectorised generator feeds a whole sweep point."""
         code = self._code
         plan = code._batch_plan()
-        B = len(seeds)
         logical_states = [int(x) for x in logical_states]
+        B = len(logical_states)
         if plan is None:                           # custom code: the per-state path
             rs = [self.run_cycle(l, noise_type, noise_prob, s) for l, s in zip(logical_states, seeds)]
             return {"syndrome": np.array([r.syndrome for r in rs]), "fidelity_before": np.array([r.fidelity_before for r in rs]),
@@ -449,22 +456,33 @@ class QECSimulator:
             ideal.copy_from(code.encode(l)._device(), dim * 16, dst_off=l * dim * 16)
         out = {"syndrome": [None] * B, "fidelity_before": np.empty(B), "fidelity_after": np.empty(B), "z_exp": np.empty(B),
                "logical_error": np.empty(B, dtype=bool), "corrections": [None] * B}
-        fired = [_noise_paulis(noise_type, noise_prob, code.data_qubits, np.random.default_rng(s)) for s in seeds]
+        nd = code.data_qubits
+        if uniforms is None:
+            # the reference's streams: trial t draws from default_rng(seed_t), one double per data qubit -- and none at
+            # all for a noise type it does not know (qec.py:679-693)
+            known = noise_type in ("bit_flip", "phase_flip", "depolarizing")
+            uniforms = np.ones((B, nd))
+            if known:
+                for t, sd in enumerate(seeds):
+                    uniforms[t] = np.random.default_rng(sd).random(nd)
+        codes = _noise_codes(noise_type, noise_prob, np.asarray(uniforms, dtype=np.float64).reshape(B, nd))
+        lg = np.asarray(logical_states)
         for logical in (0, 1):
-            idx_all = [t for t in range(B) if logical_states[t] == logical]
+            idx_all = np.nonzero(lg == logical)[0]
             for lo in range(0, len(idx_all), _BATCH):
                 idx = idx_all[lo:lo + _BATCH]
-                self._cycle_batch(c, code, plan, n, ideal, logical, idx, [fired[t] for t in idx], out)
+                self._cycle_batch(c, code, plan, n, ideal, logical, idx, codes[idx], out)
         out["syndrome"] = np.array(out["syndrome"])
         return out
 
-    def _cycle_batch(self, c, code, plan, n, ideal, logical, idx, fired, out):
+    def _cycle_batch(self, c, code, plan, n, ideal, logical, idx, codes, out):
         dim = 1 << n
         cnt = len(idx)
         layout = StateVector.layout
-        # noisy = Paulis(ideal codeword)
+        # noisy = Paulis(ideal codeword); data qubit q is hit (if at all) in order q = 0, 1, ...
         noisy = c.alloc(cnt * dim * 16)
-        c.run(c.program(_pauli_programs(n, fired, layout)), cnt, states=ideal, first=logical, load=True, store=False,
+        qs = np.tile(np.arange(codes.shape[1]), (cnt, 1))
+        c.run(c.program(_pauli_programs(n, codes, qs, layout)), cnt, states=ideal, first=logical, load=True, store=False,
               load_broadcast=True, snapshots=noisy)
         # syndromes: parity reductions on noisy, or on an H-rotated copy
         temp = None
@@ -479,10 +497,21 @@ class QECSimulator:
             w = _parity_weights(n, src, 0, cnt, [_mask(n, ch) for ch in checks])
             bits.append(np.where(w[:, :, 0] >= w[:, :, 1], 0, 1))
         syndrome = np.concatenate(bits, axis=1)
-        corrections = [code.decode_syndrome(s.tolist()) for s in syndrome]
-        usable = [[(g, q) for g, q in cs if g in ("X", "Z") and q < n] for cs in corrections]     # qec.py:113-116
+        # decode once per distinct syndrome (at most 64), then spread over the trials
+        table = {}
+        for sv in np.unique(syndrome, axis=0):
+            table[tuple(sv.tolist())] = code.decode_syndrome(sv.tolist())
+        corrections = [table[tuple(sv)] for sv in syndrome.tolist()]
+        width = max((len(v) for v in table.values()), default=0)
+        ccode = np.zeros((cnt, max(width, 1)), dtype=np.int64)
+        cq = np.zeros((cnt, max(width, 1)), dtype=np.int64)
+        gate_code = {"X": 1, "Z": 3}
+        for k, cs in enumerate(corrections):
+            for l, (g, q) in enumerate(cs):
+                if g in gate_code and q < n:                                   # qec.py:113-116
+                    ccode[k, l], cq[k, l] = gate_code[g], q
         corrected = c.alloc(cnt * dim * 16)
-        c.run(c.program(_pauli_programs(n, usable, layout)), cnt, states=noisy, load=True, store=False, snapshots=corrected)
+        c.run(c.program(_pauli_programs(n, ccode, cq, layout)), cnt, states=noisy, load=True, store=False, snapshots=corrected)
         # fidelities |<ideal|.>|^2 and <Z_L>
         ov = c.alloc(cnt * 16)
         c.overlap(n, noisy, 0, ideal, logical, 0, cnt, ov)
@@ -498,7 +527,7 @@ class QECSimulator:
         w = _parity_weights(n, zsrc, 0, cnt, [_mask(n, code.logical_z_operators())])[:, 0]
         z = w[:, 0] - w[:, 1]
         sign = 1.0 if logical == 0 else -1.0
-        for k, t in enumerate(idx):
+        for k, t in enumerate(np.asarray(idx).tolist()):
             out["syndrome"][t] = syndrome[k].tolist()
             out["corrections"][t] = corrections[k]
         out["fidelity_before"][idx] = fb
