@@ -40,6 +40,15 @@ enum {
   QSB_E_UNSUPPORTED = -5  /* valid request this build cannot run (e.g. n > 16)  */
 };
 
+/* amplitude type of the state buffers a context works on (qsb_ctx_set_precision) */
+enum {
+  QSB_C128 = 0,           /* complex128 states: the reference's precision, tolerance 1e-12 (default)       */
+  QSB_C64 = 1             /* complex64 states (BASELINE's separately reported 1e-5 mode): tiles hold twice the
+                             amplitudes (local_bits <= 14), arithmetic in fp32, reductions accumulate in fp64;
+                             every *state* buffer (states, snapshots, states_out) is complex64, every result
+                             buffer (probabilities, overlaps, RDMs, rho) keeps its double / complex128 type     */
+};
+
 typedef struct qsb_ctx qsb_ctx;
 typedef struct qsb_buffer qsb_buffer;     /* raw device bytes                      */
 typedef struct qsb_program qsb_program;   /* lowered circuit (+noise) on device    */
@@ -132,6 +141,7 @@ int qsb_ctx_create(int device, qsb_ctx** out);
 int qsb_ctx_destroy(qsb_ctx* ctx);
 int qsb_ctx_set_stream(qsb_ctx* ctx, void* cuda_stream);  /* run on a caller's stream (torch) */
 int qsb_ctx_sync(qsb_ctx* ctx);
+int qsb_ctx_set_precision(qsb_ctx* ctx, int precision);   /* QSB_C128 | QSB_C64; programs keep the mode they were created in */
 const char* qsb_last_error(qsb_ctx* ctx);         /* ctx may be NULL: last error of the thread */
 int qsb_ctx_info(qsb_ctx* ctx, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor,
                  int64_t* total_mem);

@@ -22,6 +22,7 @@ struct qsb_ctx {
   uint64_t* d_masks;      // scratch for qsb_masked_parity
   c128* d_part;                 // partial sums of the large-state reductions
   int* d_bits;                  // bit lists of qsb_rdm_general
+  int amp_bytes;                // 16: complex128 states (default); 8: complex64 mode (qsb_ctx_set_precision)
   unsigned long long* d_prof;   // cycle counters of the last qsb_run (qsb_debug_profile), or NULL
   int prof_ctas;
 };
@@ -44,6 +45,7 @@ struct qsb_program {
   int64_t n_idata, n_cdata;
   int32_t max_param, max_draw;   // highest parameter / draw index any op touches (argument checks)
   bool has_param;
+  int32_t amp_bytes;             // element size of the states this program runs on (the ctx precision at creation)
   int32_t tile_bits;             // > 0: streaming mode (one CTA per 2^m-amplitude tile of a state in HBM)
 };
 
@@ -106,6 +108,7 @@ int qsb_ctx_create(int device, qsb_ctx** out) {
   c->d_prof = nullptr;
   c->d_part = nullptr;
   c->d_bits = nullptr;
+  c->amp_bytes = 16;
   c->prof_ctas = 0;
   cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
@@ -148,6 +151,13 @@ int qsb_ctx_sync(qsb_ctx* ctx) {
   if (!ctx) return fail(nullptr, QSB_E_INVAL, "ctx is NULL");
   CU(ctx, cudaSetDevice(ctx->device));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return QSB_OK;
+}
+
+int qsb_ctx_set_precision(qsb_ctx* ctx, int precision) {
+  if (!ctx) return fail(nullptr, QSB_E_INVAL, "ctx is NULL");
+  if (precision != QSB_C128 && precision != QSB_C64) return fail(ctx, QSB_E_INVAL, "precision must be QSB_C128 or QSB_C64");
+  ctx->amp_bytes = precision == QSB_C64 ? 8 : 16;
   return QSB_OK;
 }
 
@@ -292,9 +302,9 @@ int qsb_program_create(qsb_ctx* ctx, int32_t n, int32_t m, const qsb_op* ops, in
   if (n < 1) return fail(ctx, QSB_E_INVAL, "num_qubits must be >= 1, got %d", n);
   if (n > 30)
     return fail(ctx, QSB_E_UNSUPPORTED, "executor holds n <= 30 qubits per device, got %d", n);
-  if (m < 1 || m > n || m > QSB_MAX_LOCAL_BITS)
-    return fail(ctx, QSB_E_INVAL, "local_bits %d invalid for n = %d (need 1 <= m <= min(n, %d))", m, n,
-                QSB_MAX_LOCAL_BITS);
+  const int max_m = ctx->amp_bytes == 8 ? QSB_MAX_LOCAL_BITS_C64 : QSB_MAX_LOCAL_BITS;
+  if (m < 1 || m > n || m > max_m)
+    return fail(ctx, QSB_E_INVAL, "local_bits %d invalid for n = %d (need 1 <= m <= min(n, %d))", m, n, max_m);
   // n - m <= 3 and n <= 16: the state is resident in a cluster of 2^(n-m) CTAs; otherwise it is streamed
   // through shared memory tile by tile (one pass over HBM per program)
   const bool streaming = (n - m > 3) || n > QSB_MAX_QUBITS;
@@ -391,6 +401,7 @@ int qsb_program_create(qsb_ctx* ctx, int32_t n, int32_t m, const qsb_op* ops, in
   p->max_draw = max_draw;
   p->has_param = has_param;
   p->tile_bits = streaming ? n - m : 0;
+  p->amp_bytes = ctx->amp_bytes;
   p->d_ops = nullptr;
   p->d_cdata = nullptr;
   p->d_idata = nullptr;
@@ -429,9 +440,9 @@ int qsb_program_free(qsb_program* p) {
 
 }  // extern "C"
 
-template <int C>
+template <int C, class A>
 static cudaError_t launch_traj(qsb_ctx* ctx, const qsb_exec_args& a, int threads, size_t smem, int* grid_out) {
-  auto kern = qsb_traj_kernel<C>;
+  auto kern = qsb_traj_kernel<C, A>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg;
@@ -483,11 +494,14 @@ int qsb_run(qsb_program* p, const qsb_run_args* r) {
   if (r->count < 0 || r->first < 0) return fail(ctx, QSB_E_INVAL, "qsb_run: negative range");
   if (r->count == 0) return QSB_OK;
   const int64_t dim = (int64_t)1 << p->n;
+  const int64_t AB = p->amp_bytes;
   int rc;
+  if (ctx->amp_bytes != p->amp_bytes)
+    return fail(ctx, QSB_E_INVAL, "qsb_run: the program was created in another precision mode than the context is in now");
   if ((r->flags & QSB_RUN_LOAD_BROADCAST) && (r->flags & QSB_RUN_STORE) && !r->states_out)
     return fail(ctx, QSB_E_INVAL, "qsb_run: LOAD_BROADCAST cannot store in place");
   if ((r->flags & QSB_RUN_LOAD) || ((r->flags & QSB_RUN_STORE) && !r->states_out))
-    if ((rc = need(ctx, r->states, (r->first + ((r->flags & QSB_RUN_LOAD_BROADCAST) ? 1 : r->count)) * dim * 16, "states")))
+    if ((rc = need(ctx, r->states, (r->first + ((r->flags & QSB_RUN_LOAD_BROADCAST) ? 1 : r->count)) * dim * AB, "states")))
       return rc;
   if (p->ops_stride && r->count > p->n_programs)
     return fail(ctx, QSB_E_INVAL, "qsb_run: %lld trajectories but only %lld per-trajectory programs",
@@ -508,7 +522,7 @@ int qsb_run(qsb_program* p, const qsb_run_args* r) {
   if (!r->init_basis && (r->default_basis < 0 || r->default_basis >= dim) && !(r->flags & QSB_RUN_LOAD))
     return fail(ctx, QSB_E_INVAL, "qsb_run: default_basis out of range");
   if (p->n_snapshots > 0 && r->snapshots &&
-      (rc = need(ctx, r->snapshots, r->count * p->n_snapshots * dim * 16, "snapshots")))
+      (rc = need(ctx, r->snapshots, r->count * p->n_snapshots * dim * AB, "snapshots")))
     return rc;
   if ((r->flags & QSB_RUN_ACCUM_PROBS) && (rc = need(ctx, r->probs_accum, dim * 8, "probs_accum"))) return rc;
 
@@ -526,12 +540,13 @@ int qsb_run(qsb_program* p, const qsb_run_args* r) {
   a.store_perm = p->store_perm;
   a.n_snapshots = p->n_snapshots;
   a.flags = r->flags;
-  a.states = r->states ? (c128*)r->states->ptr + r->first * dim : nullptr;
+  a.amp_bytes = AB;
+  a.states = r->states ? (char*)r->states->ptr + r->first * dim * AB : nullptr;
   a.states_out = a.states;
   if (r->states_out) {
     if (r->out_first < 0) return fail(ctx, QSB_E_INVAL, "qsb_run: negative out_first");
-    if ((rc = need(ctx, r->states_out, (r->out_first + r->count) * dim * 16, "states_out"))) return rc;
-    a.states_out = (c128*)r->states_out->ptr + r->out_first * dim;
+    if ((rc = need(ctx, r->states_out, (r->out_first + r->count) * dim * AB, "states_out"))) return rc;
+    a.states_out = (char*)r->states_out->ptr + r->out_first * dim * AB;
   }
   a.count = r->count;
   a.params = r->params ? (const double*)r->params->ptr : nullptr;
@@ -544,7 +559,7 @@ int qsb_run(qsb_program* p, const qsb_run_args* r) {
   a.default_basis = r->default_basis;
   a.branches = r->branches ? (int32_t*)r->branches->ptr : nullptr;
   a.branches_stride = r->branches_stride;
-  a.snapshots = (p->n_snapshots > 0 && r->snapshots) ? (c128*)r->snapshots->ptr : nullptr;
+  a.snapshots = (p->n_snapshots > 0 && r->snapshots) ? r->snapshots->ptr : nullptr;
   a.probs_accum = (r->flags & QSB_RUN_ACCUM_PROBS) ? (double*)r->probs_accum->ptr : nullptr;
 
   a.prof = ctx->d_prof;
@@ -563,14 +578,15 @@ int qsb_run(qsb_program* p, const qsb_run_args* r) {
   if (workers < 32) workers = 32;
   if (workers > QSB_MAX_WORKERS) workers = QSB_MAX_WORKERS;
   const int threads = workers + QSB_CTL_THREADS;
-  const size_t smem = ((size_t)16 << p->m) + QSB_SMEM_EXTRA;
+  const bool c64m = p->amp_bytes == 8;
+  const size_t smem = ((size_t)p->amp_bytes << p->m) + QSB_SMEM_EXTRA;
   int grid = 0;
   cudaError_t e;
   switch (C) {
-    case 1: e = launch_traj<1>(ctx, a, threads, smem, &grid); break;
-    case 2: e = launch_traj<2>(ctx, a, threads, smem, &grid); break;
-    case 4: e = launch_traj<4>(ctx, a, threads, smem, &grid); break;
-    case 8: e = launch_traj<8>(ctx, a, threads, smem, &grid); break;
+    case 1: e = c64m ? launch_traj<1, c64>(ctx, a, threads, smem, &grid) : launch_traj<1, c128>(ctx, a, threads, smem, &grid); break;
+    case 2: e = c64m ? launch_traj<2, c64>(ctx, a, threads, smem, &grid) : launch_traj<2, c128>(ctx, a, threads, smem, &grid); break;
+    case 4: e = c64m ? launch_traj<4, c64>(ctx, a, threads, smem, &grid) : launch_traj<4, c128>(ctx, a, threads, smem, &grid); break;
+    case 8: e = c64m ? launch_traj<8, c64>(ctx, a, threads, smem, &grid) : launch_traj<8, c128>(ctx, a, threads, smem, &grid); break;
     default: return fail(ctx, QSB_E_UNSUPPORTED, "cluster size %d", C);
   }
   if (e != cudaSuccess) {
@@ -622,6 +638,18 @@ static int after_launch(qsb_ctx* ctx, const char* what) {
   return QSB_OK;
 }
 
+// run STMT with `A` = the context's amplitude type (complex128, or complex64 in c64 mode)
+#define QSB_BY_AMP(ctx, STMT)            \
+  do {                                   \
+    if ((ctx)->amp_bytes == 8) {         \
+      typedef c64 A;                     \
+      STMT;                              \
+    } else {                             \
+      typedef c128 A;                    \
+      STMT;                              \
+    }                                    \
+  } while (0)
+
 static int grid_for(qsb_ctx* ctx, int64_t items, int threads) {
   int64_t g = (items + threads - 1) / threads;
   int64_t cap = (int64_t)ctx->sm_count * 16;
@@ -635,11 +663,11 @@ int qsb_probabilities(qsb_ctx* ctx, int32_t n, qsb_buffer* states, int64_t first
   const int64_t dim = (int64_t)1 << n;
   int rc;
   if (count <= 0) return count == 0 ? QSB_OK : fail(ctx, QSB_E_INVAL, "negative count");
-  if ((rc = need(ctx, states, (first + count) * dim * 16, "states"))) return rc;
+  if ((rc = need(ctx, states, (first + count) * dim * ctx->amp_bytes, "states"))) return rc;
   if ((rc = need(ctx, out, (out_first + count) * dim * 8, "probabilities"))) return rc;
   CU(ctx, cudaSetDevice(ctx->device));
-  qsb_probs_kernel<<<grid_for(ctx, count * dim, 256), 256, 0, ctx->stream>>>(
-      (const c128*)states->ptr + first * dim, (double*)out->ptr + out_first * dim, count * dim);
+  QSB_BY_AMP(ctx, (qsb_probs_kernel<A><<<grid_for(ctx, count * dim, 256), 256, 0, ctx->stream>>>(
+                      (const A*)states->ptr + first * dim, (double*)out->ptr + out_first * dim, count * dim)));
   return after_launch(ctx, "probabilities");
 }
 
@@ -648,11 +676,11 @@ int qsb_probabilities_sum(qsb_ctx* ctx, int32_t n, qsb_buffer* states, int64_t f
   const int64_t dim = (int64_t)1 << n;
   int rc;
   if (count <= 0) return count == 0 ? QSB_OK : fail(ctx, QSB_E_INVAL, "negative count");
-  if ((rc = need(ctx, states, (first + count) * dim * 16, "states"))) return rc;
+  if ((rc = need(ctx, states, (first + count) * dim * ctx->amp_bytes, "states"))) return rc;
   if ((rc = need(ctx, out, dim * 8, "probability sum"))) return rc;
   CU(ctx, cudaSetDevice(ctx->device));
-  qsb_probs_sum_kernel<<<grid_for(ctx, dim, 128), 128, 0, ctx->stream>>>((const c128*)states->ptr + first * dim,
-                                                                         (double*)out->ptr, dim, count);
+  QSB_BY_AMP(ctx, (qsb_probs_sum_kernel<A><<<grid_for(ctx, dim, 128), 128, 0, ctx->stream>>>(
+                      (const A*)states->ptr + first * dim, (double*)out->ptr, dim, count)));
   return after_launch(ctx, "probabilities_sum");
 }
 
@@ -662,13 +690,13 @@ int qsb_sample_index(qsb_ctx* ctx, int32_t n, qsb_buffer* states, int64_t first,
   const int64_t dim = (int64_t)1 << n;
   int rc;
   if (count <= 0) return count == 0 ? QSB_OK : fail(ctx, QSB_E_INVAL, "negative count");
-  if ((rc = need(ctx, states, (first + count) * dim * 16, "states"))) return rc;
+  if ((rc = need(ctx, states, (first + count) * dim * ctx->amp_bytes, "states"))) return rc;
   if ((rc = need(ctx, uniforms, count * 8, "uniforms"))) return rc;
   if ((rc = need(ctx, out, count * 8, "sample output"))) return rc;
   CU(ctx, cudaSetDevice(ctx->device));
   int threads = dim >= 256 ? 256 : 32;
-  qsb_sample_kernel<<<(unsigned)count, threads, 0, ctx->stream>>>((const c128*)states->ptr + first * dim,
-                                                                  (const double*)uniforms->ptr, (int64_t*)out->ptr, dim);
+  QSB_BY_AMP(ctx, (qsb_sample_kernel<A><<<(unsigned)count, threads, 0, ctx->stream>>>(
+                      (const A*)states->ptr + first * dim, (const double*)uniforms->ptr, (int64_t*)out->ptr, dim)));
   return after_launch(ctx, "sample_index");
 }
 
@@ -679,8 +707,8 @@ int qsb_overlap(qsb_ctx* ctx, int32_t n, qsb_buffer* a, int64_t a_first, qsb_buf
   int rc;
   if (count <= 0) return count == 0 ? QSB_OK : fail(ctx, QSB_E_INVAL, "negative count");
   if (b_stride_states != 0 && b_stride_states != 1) return fail(ctx, QSB_E_INVAL, "b_stride_states must be 0 or 1");
-  if ((rc = need(ctx, a, (a_first + count) * dim * 16, "states a"))) return rc;
-  if ((rc = need(ctx, b, (b_first + (b_stride_states ? count : 1)) * dim * 16, "states b"))) return rc;
+  if ((rc = need(ctx, a, (a_first + count) * dim * ctx->amp_bytes, "states a"))) return rc;
+  if ((rc = need(ctx, b, (b_first + (b_stride_states ? count : 1)) * dim * ctx->amp_bytes, "states b"))) return rc;
   if ((rc = need(ctx, out, count * 16, "overlap output"))) return rc;
   CU(ctx, cudaSetDevice(ctx->device));
   if (dim >= ((int64_t)1 << 18)) {
@@ -689,17 +717,17 @@ int qsb_overlap(qsb_ctx* ctx, int32_t n, qsb_buffer* a, int64_t a_first, qsb_buf
     const int64_t per = (dim + n_part - 1) / n_part;
     if (!ctx->d_part) CU(ctx, cudaMalloc(&ctx->d_part, sizeof(c128) * 148 * 16));
     for (int64_t t = 0; t < count; ++t) {
-      const c128* x = (const c128*)a->ptr + (a_first + t) * dim;
-      const c128* y = (const c128*)b->ptr + (b_first + t * b_stride_states) * dim;
-      qsb_overlap_partial_kernel<<<n_part, 256, 0, ctx->stream>>>(x, y, dim, per, ctx->d_part);
+      QSB_BY_AMP(ctx, (qsb_overlap_partial_kernel<A><<<n_part, 256, 0, ctx->stream>>>(
+                          (const A*)a->ptr + (a_first + t) * dim, (const A*)b->ptr + (b_first + t * b_stride_states) * dim,
+                          dim, per, ctx->d_part)));
       qsb_overlap_final_kernel<<<1, 256, 0, ctx->stream>>>(ctx->d_part, n_part, (c128*)out->ptr + t);
       ctx->launches += 1;
     }
     return after_launch(ctx, "overlap");
   }
-  qsb_overlap_kernel<<<(unsigned)count, 256, 0, ctx->stream>>>((const c128*)a->ptr + a_first * dim,
-                                                               (const c128*)b->ptr + b_first * dim,
-                                                               b_stride_states * dim, (c128*)out->ptr, dim);
+  QSB_BY_AMP(ctx, (qsb_overlap_kernel<A><<<(unsigned)count, 256, 0, ctx->stream>>>(
+                      (const A*)a->ptr + a_first * dim, (const A*)b->ptr + b_first * dim, b_stride_states * dim,
+                      (c128*)out->ptr, dim)));
   return after_launch(ctx, "overlap");
 }
 
@@ -710,12 +738,12 @@ int qsb_masked_parity(qsb_ctx* ctx, int32_t n, qsb_buffer* states, int64_t first
   int rc;
   if (count <= 0) return count == 0 ? QSB_OK : fail(ctx, QSB_E_INVAL, "negative count");
   if (n_masks < 1 || n_masks > 8 || !masks) return fail(ctx, QSB_E_INVAL, "n_masks must be 1..8");
-  if ((rc = need(ctx, states, (first + count) * dim * 16, "states"))) return rc;
+  if ((rc = need(ctx, states, (first + count) * dim * ctx->amp_bytes, "states"))) return rc;
   if ((rc = need(ctx, out, count * n_masks * 16, "parity output"))) return rc;
   CU(ctx, cudaSetDevice(ctx->device));
   CU(ctx, cudaMemcpyAsync(ctx->d_masks, masks, sizeof(uint64_t) * n_masks, cudaMemcpyHostToDevice, ctx->stream));
-  qsb_parity_kernel<<<(unsigned)count, 256, 0, ctx->stream>>>((const c128*)states->ptr + first * dim, dim, ctx->d_masks,
-                                                              n_masks, (double*)out->ptr);
+  QSB_BY_AMP(ctx, (qsb_parity_kernel<A><<<(unsigned)count, 256, 0, ctx->stream>>>(
+                      (const A*)states->ptr + first * dim, dim, ctx->d_masks, n_masks, (double*)out->ptr)));
   return after_launch(ctx, "masked_parity");
 }
 
@@ -726,17 +754,18 @@ int qsb_rdm_all(qsb_ctx* ctx, int32_t n, qsb_buffer* states, int64_t first, int6
   const int npairs = n * (n - 1) / 2;
   int rc;
   if (count <= 0) return count == 0 ? QSB_OK : fail(ctx, QSB_E_INVAL, "negative count");
-  if ((rc = need(ctx, states, (first + count) * dim * 16, "states"))) return rc;
+  if ((rc = need(ctx, states, (first + count) * dim * ctx->amp_bytes, "states"))) return rc;
   CU(ctx, cudaSetDevice(ctx->device));
-  const c128* s = (const c128*)states->ptr + first * dim;
+  const char* s = (const char*)states->ptr + first * dim * ctx->amp_bytes;
   if (rdm1) {
     if ((rc = need(ctx, rdm1, count * n * 4 * 16, "rdm1"))) return rc;
-    qsb_rdm1_kernel<<<(unsigned)(count * n), 256, 0, ctx->stream>>>(s, n, (c128*)rdm1->ptr);
+    QSB_BY_AMP(ctx, (qsb_rdm1_kernel<A><<<(unsigned)(count * n), 256, 0, ctx->stream>>>((const A*)s, n, (c128*)rdm1->ptr)));
     if ((rc = after_launch(ctx, "rdm1"))) return rc;
   }
   if (rdm2 && npairs > 0) {
     if ((rc = need(ctx, rdm2, count * npairs * 16 * 16, "rdm2"))) return rc;
-    qsb_rdm2_kernel<<<(unsigned)(count * npairs), 256, 0, ctx->stream>>>(s, n, npairs, (c128*)rdm2->ptr);
+    QSB_BY_AMP(ctx, (qsb_rdm2_kernel<A><<<(unsigned)(count * npairs), 256, 0, ctx->stream>>>((const A*)s, n, npairs,
+                                                                                          (c128*)rdm2->ptr)));
     if ((rc = after_launch(ctx, "rdm2"))) return rc;
   }
   return QSB_OK;
@@ -749,7 +778,7 @@ int qsb_rdm_general(qsb_ctx* ctx, int32_t n, qsb_buffer* states, int64_t first, 
   const int64_t dim = (int64_t)1 << n;
   int rc;
   if (count <= 0) return count == 0 ? QSB_OK : fail(ctx, QSB_E_INVAL, "negative count");
-  if ((rc = need(ctx, states, (first + count) * dim * 16, "states"))) return rc;
+  if ((rc = need(ctx, states, (first + count) * dim * ctx->amp_bytes, "states"))) return rc;
   if ((rc = need(ctx, out, count * ((int64_t)1 << (2 * k)) * 16, "rdm"))) return rc;
   int host[40];                                     // kept index bits (qubit q = bit n-1-q), then the environment bits
   unsigned used = 0;
@@ -766,8 +795,8 @@ int qsb_rdm_general(qsb_ctx* ctx, int32_t n, qsb_buffer* states, int64_t first, 
   CU(ctx, cudaSetDevice(ctx->device));
   if (!ctx->d_bits) CU(ctx, cudaMalloc(&ctx->d_bits, 40 * sizeof(int)));
   CU(ctx, cudaMemcpyAsync(ctx->d_bits, host, 40 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-  qsb_rdm_general_kernel<<<(unsigned)count, 256, 0, ctx->stream>>>((const c128*)states->ptr + first * dim, n, k, ctx->d_bits,
-                                                                  ctx->d_bits + 8, (c128*)out->ptr);
+  QSB_BY_AMP(ctx, (qsb_rdm_general_kernel<A><<<(unsigned)count, 256, 0, ctx->stream>>>(
+                      (const A*)states->ptr + first * dim, n, k, ctx->d_bits, ctx->d_bits + 8, (c128*)out->ptr)));
   return after_launch(ctx, "rdm_general");
 }
 
@@ -804,12 +833,12 @@ int qsb_rho_accumulate(qsb_ctx* ctx, int32_t n, qsb_buffer* states, int64_t firs
   const int64_t dim = (int64_t)1 << n;
   int rc;
   if (count <= 0) return count == 0 ? QSB_OK : fail(ctx, QSB_E_INVAL, "negative count");
-  if ((rc = need(ctx, states, (first + count) * dim * 16, "states"))) return rc;
+  if ((rc = need(ctx, states, (first + count) * dim * ctx->amp_bytes, "states"))) return rc;
   if ((rc = need(ctx, rho, dim * dim * 16, "rho"))) return rc;
   CU(ctx, cudaSetDevice(ctx->device));
   const unsigned g = (unsigned)((dim + QSB_RHO_TILE - 1) / QSB_RHO_TILE);
-  qsb_rho_kernel<<<g * (g + 1) / 2, 256, 0, ctx->stream>>>((const c128*)states->ptr + first * dim, dim, count, scale,
-                                                           (c128*)rho->ptr, (int)g);
+  QSB_BY_AMP(ctx, (qsb_rho_kernel<A><<<g * (g + 1) / 2, 256, 0, ctx->stream>>>((const A*)states->ptr + first * dim, dim, count,
+                                                                              scale, (c128*)rho->ptr, (int)g)));
   return after_launch(ctx, "rho_accumulate");
 }
 

@@ -43,11 +43,13 @@
 #define QSB_PASS __device__ __forceinline__   // whole-tile sweeps: inlined into the worker loop (an ABI call would leave them ~48 registers)
 #define QSB_CTL __device__ __forceinline__    // control-warp helpers: inlined so that the control state stays in registers (an ABI call spills it to local memory)
 typedef double2 c128;
+typedef float2 c64;
 #else
 #define QSB_HD inline
 #define QSB_PASS inline
 #define QSB_CTL inline
 struct alignas(16) c128 { double x, y; };
+struct alignas(8) c64 { float x, y; };
 #endif
 
 // count trailing zeros / index of the highest set bit of a non-zero 32-bit word
@@ -61,7 +63,8 @@ struct alignas(16) c128 { double x, y; };
 
 #define QSB_MAX_QUBITS 16          // resident (cluster) mode
 #define QSB_MAX_STREAM_QUBITS 32   // streaming mode (index arithmetic is 32-bit)
-#define QSB_MAX_LOCAL_BITS 13
+#define QSB_MAX_LOCAL_BITS 13      // complex128 tile of 128 KiB; complex64 tiles hold one bit more (QSB_MAX_LOCAL_BITS_C64)
+#define QSB_MAX_LOCAL_BITS_C64 14
 #define QSB_AD_MARGIN 1e-10
 #define QSB_CHUNK 128          // ops staged in shared memory per refill
 #define QSB_REMAP_REGS 16      // amplitudes a thread stages per remap / rank-bit flush round
@@ -86,15 +89,16 @@ struct qsb_exec_args {
   int32_t flags;
   int32_t tile_bits;      // streaming mode: n - m index bits select the tile (0 in resident mode)
   int32_t pad0;
-  c128* states;           // already offset to `first`
-  c128* states_out;       // STORE destination, already offset (== states when in place)
+  void* states;           // already offset to `first`; complex128 or complex64 elements (amp_bytes)
+  void* states_out;       // STORE destination, already offset (== states when in place)
   int64_t count;          // resident: trajectories; streaming: states (each 2^tile_bits tiles)
   const double* params;   int64_t params_stride;
   const double* uniforms; int64_t uniforms_stride;
   uint64_t seed;          int64_t traj_offset;
   const int64_t* init_basis; int64_t default_basis;
   int32_t* branches;      int64_t branches_stride;
-  c128* snapshots;
+  void* snapshots;
+  int64_t amp_bytes;      // 16 (complex128) or 8 (complex64): element size of states / snapshots
   double* probs_accum;
   unsigned long long* prof;   // optional cycle counters, QSB_PROF_WORDS per CTA (qsb_debug_profile), or NULL
 };
@@ -113,7 +117,7 @@ struct alignas(16) qsb_desc {
   int64_t unit;            // INIT: unit index (trajectory; streaming: state * tiles + tile)
   int64_t basis;           // INIT: reference-order basis index
   const int32_t* perm;     // INIT / STORE: n-entry bit permutation (slot bit -> reference-order bit)
-  c128* gptr;              // INIT: source state (LOAD) ; STORE: destination (or NULL)
+  void* gptr;              // INIT: source state (LOAD) ; STORE: destination (or NULL); elements of the tile's type
   double* probs;           // STORE: |psi|^2 accumulation target (or NULL)
   int64_t tile;            // INIT / STORE: value of the non-resident index bits (cluster rank or tile id)
   uint64_t pos;            // SWEEP: 16 nibbles, nibble t = index bit that bit t of the group number lands on
@@ -145,7 +149,7 @@ struct qsb_ctl {
   double red[2][4];            // this CTA's contribution to a cluster reduction, double-buffered
   double red_total[4];         // cluster-wide result handed to the control warp (RDM1)
   int32_t head[32];            // first MUL op of each slot in the staged chunk (QSB_CHUNK = none)
-  double wtab[192];            // weighted marginal: products of diagonal-pending weights over index bits 0..6 | 7..12
+  double wtab[256];            // weighted marginal: products of diagonal-pending weights over index bits 0..6 | 7..13
   unsigned long long xbar;     // mbarrier of the workers-only cluster barrier (device)
 };
 
@@ -163,6 +167,29 @@ QSB_HD c128 qsb_fma(c128 a, c128 b, c128 c) {   // a*b + c
 }
 QSB_HD c128 qsb_neg(c128 a) { return qsb_c(-a.x, -a.y); }
 QSB_HD double qsb_norm2(c128 a) { return a.x * a.x + a.y * a.y; }
+
+// ---- amplitude types: complex128 (default) and complex64 (BASELINE's separately reported 1e-5 mode) ----------
+// SW = log2(elements per 128-byte shared-memory row): the XOR swizzle folds index bits SW..2SW-1 onto bits 0..SW-1.
+template <class A> struct qsb_amp;
+template <> struct qsb_amp<c128> { typedef double real; enum { SW = 3 }; };
+template <> struct qsb_amp<c64> { typedef float real; enum { SW = 4 }; };
+QSB_HD c64 qsb_cf(float x, float y) { c64 r; r.x = x; r.y = y; return r; }
+QSB_HD c64 qsb_mul(c64 a, c64 b) { return qsb_cf(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+QSB_HD c64 qsb_fma(c64 a, c64 b, c64 c) {
+  return qsb_cf(fmaf(a.x, b.x, fmaf(-a.y, b.y, c.x)), fmaf(a.x, b.y, fmaf(a.y, b.x, c.y)));
+}
+QSB_HD c64 qsb_neg(c64 a) { return qsb_cf(-a.x, -a.y); }
+QSB_HD double qsb_norm2(c64 a) { return (double)a.x * a.x + (double)a.y * a.y; }
+template <class A> QSB_HD A qsb_cvt(c128 z);
+template <> QSB_HD c128 qsb_cvt<c128>(c128 z) { return z; }
+template <> QSB_HD c64 qsb_cvt<c64>(c128 z) { return qsb_cf((float)z.x, (float)z.y); }
+QSB_HD c128 qsb_wide(c128 z) { return z; }
+QSB_HD c128 qsb_wide(c64 z) { return qsb_c(z.x, z.y); }
+template <class A> QSB_HD A qsb_scale(A a, double s) {
+  typedef typename qsb_amp<A>::real R;
+  A r; r.x = a.x * (R)s; r.y = a.y * (R)s; return r;
+}
+template <int SW> QSB_HD int qsb_slot_sw(int i) { return i ^ ((i >> SW) & ((1 << SW) - 1)); }
 
 QSB_HD void qsb_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
                        uint32_t out[4]) {
@@ -214,14 +241,14 @@ QSB_HD int qsb_choice(const double* p, int k, double u) {
 // quarter-warp differ in group bits 0..2, so these go to one free position out of each pair
 // {0,3}, {1,4}, {2,5}: every LDS.128 / STS.128 of a sweep is then conflict-free whatever the targets
 // (unless the targets cover both members of a pair).  The remaining positions follow in ascending order.
-QSB_HD uint64_t qsb_group_order(int m, uint32_t used, int wbits, int nfree, int* hmask) {
+QSB_HD uint64_t qsb_group_order(int m, uint32_t used, int wbits, int nfree, int sw, int* hmask) {
   const uint32_t all = m >= 32 ? 0xffffffffu : ((1u << m) - 1u);
   uint64_t pos = 0;
   int cnt = 0, hm = 0;
-  for (int j = 0; j < 3; ++j) {
+  for (int j = 0; j < sw; ++j) {
     int q = -1;
     if (j < m && !((used >> j) & 1u)) q = j;
-    else if (j + 3 < m && !((used >> (j + 3)) & 1u)) q = j + 3;
+    else if (j + sw < m && !((used >> (j + sw)) & 1u)) q = j + sw;
     if (q >= 0) {
       pos |= (uint64_t)q << (4 * cnt);
       if (cnt >= wbits && cnt < nfree) hm |= 1 << q;
@@ -256,6 +283,9 @@ QSB_HD uint32_t qsb_permute(const uint32_t* tab, uint32_t x) {
 //                                      WORKER SIDE
 // =========================================================================================
 
+// swizzled slot for the tile's element type (Env in scope)
+#define QSB_SLOT(i) qsb_slot_sw<qsb_amp<typename Env::amp>::SW>(i)
+
 // One sweep over the tile for K slot bits (d->b[0] = MSB of the local index r): apply the pending 2x2 of
 // every bit whose class is not NONE, then gate G.  Each worker owns whole 2^K groups and keeps 16
 // amplitudes (NG groups) in registers per step: all loads are issued before the arithmetic, and the
@@ -264,7 +294,8 @@ QSB_HD uint32_t qsb_permute(const uint32_t* tab, uint32_t x) {
 // where 16 amplitudes plus three dense pending matrices would spill (measured: profiles/README.md)
 template <int K, bool DG, class Env>
 QSB_PASS void qsb_sweep(Env& env, int m, const qsb_desc* d) {
-  c128* tile = env.tile();          // re-derived here so device code keeps the shared address space (LDS/STS)
+  typedef typename Env::amp A;
+  A* tile = env.tile();             // re-derived here so device code keeps the shared address space (LDS/STS)
   constexpr int D = 1 << K;
   constexpr int NG = DG ? (K == 2 ? 2 : 1) : (K == 3 ? 1 : 16 / D);
   const int G = d->gate;
@@ -292,15 +323,15 @@ QSB_PASS void qsb_sweep(Env& env, int m, const qsb_desc* d) {
     for (int k = 0; k < K; ++k) if ((r >> (K - 1 - k)) & 1) o |= 1 << bits[k];
     off[r] = o;
   }
-  c128 P[K][4];                     // always a valid matrix (identity where nothing is pending)
+  A P[K][4];                        // always a valid matrix (identity where nothing is pending)
 #pragma unroll
   for (int k = 0; k < K; ++k) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) P[k][e] = d->P[k][e];
+    for (int e = 0; e < 4; ++e) P[k][e] = qsb_cvt<A>(d->P[k][e]);
   }
   const int cnt = 1 << (m - K);
   for (int g0 = env.wid; g0 < cnt; g0 += NG * env.W) {
-    c128 a[NG][D];
+    A a[NG][D];
     int base[NG];
 #pragma unroll
     for (int j = 0; j < NG; ++j) {
@@ -315,7 +346,7 @@ QSB_PASS void qsb_sweep(Env& env, int m, const qsb_desc* d) {
 #endif
       base[j] = bs;
 #pragma unroll
-      for (int r = 0; r < D; ++r) a[j][r] = tile[qsb_slot(bs | off[r])];
+      for (int r = 0; r < D; ++r) a[j][r] = tile[QSB_SLOT(bs | off[r])];
     }
 #pragma unroll
     for (int k = 0; k < K; ++k) {
@@ -326,12 +357,12 @@ QSB_PASS void qsb_sweep(Env& env, int m, const qsb_desc* d) {
 #pragma unroll
           for (int r = 0; r < D; ++r) {
             if (r & bit) continue;
-            c128 lo = a[j][r], hi = a[j][r | bit];
+            A lo = a[j][r], hi = a[j][r | bit];
             a[j][r] = qsb_fma(P[k][1], hi, qsb_mul(P[k][0], lo));
             a[j][r | bit] = qsb_fma(P[k][3], hi, qsb_mul(P[k][2], lo));
           }
       } else if (cls[k] == QSB_CLS_RDIAG) {
-        const double sc = P[k][3].x;
+        const typename qsb_amp<A>::real sc = P[k][3].x;
 #pragma unroll
         for (int j = 0; j < NG; ++j)
 #pragma unroll
@@ -343,34 +374,34 @@ QSB_PASS void qsb_sweep(Env& env, int m, const qsb_desc* d) {
       // its inputs are already in registers
 #pragma unroll
       for (int r = 0; r < D; ++r) {
-        c128 acc[NG];
+        A acc[NG];
 #pragma unroll
         for (int c = 0; c < D; ++c) {
-          const c128 mv = d->mat[r * D + c];
+          const A mv = qsb_cvt<A>(d->mat[r * D + c]);
 #pragma unroll
           for (int j = 0; j < NG; ++j) acc[j] = c == 0 ? qsb_mul(mv, a[j][0]) : qsb_fma(mv, a[j][c], acc[j]);
         }
 #pragma unroll
         for (int j = 0; j < NG; ++j)
-          if (g0 + j * env.W < cnt) tile[qsb_slot(base[j] | off[r])] = acc[j];
+          if (g0 + j * env.W < cnt) tile[QSB_SLOT(base[j] | off[r])] = acc[j];
       }
       continue;
     }
 #pragma unroll
     for (int j = 0; j < NG; ++j) {
-      c128* x = a[j];
+      A* x = a[j];
       // the gate is a CTA-uniform run-time choice: one sweep body per K keeps the instruction footprint small
       if (K == 2) {
-        if (G == QSB_G_CX) { c128 t = x[2]; x[2] = x[3]; x[3] = t; }                // b[0] control, b[1] target
+        if (G == QSB_G_CX) { A t = x[2]; x[2] = x[3]; x[3] = t; }                // b[0] control, b[1] target
         else if (G == QSB_G_CZ) { x[3] = qsb_neg(x[3]); }
-        else if (G == QSB_G_SWAP) { c128 t = x[1]; x[1] = x[2]; x[2] = t; }
+        else if (G == QSB_G_SWAP) { A t = x[1]; x[1] = x[2]; x[2] = t; }
       } else if (K == 3) {
-        if (G == QSB_G_CCX) { c128 t = x[D - 2]; x[D - 2] = x[D - 1]; x[D - 1] = t; }   // 110 <-> 111
-        else if (G == QSB_G_CSWAP) { c128 t = x[(D >> 1) | 1]; x[(D >> 1) | 1] = x[(D >> 1) | 2]; x[(D >> 1) | 2] = t; }  // 101 <-> 110
+        if (G == QSB_G_CCX) { A t = x[D - 2]; x[D - 2] = x[D - 1]; x[D - 1] = t; }   // 110 <-> 111
+        else if (G == QSB_G_CSWAP) { A t = x[(D >> 1) | 1]; x[(D >> 1) | 1] = x[(D >> 1) | 2]; x[(D >> 1) | 2] = t; }  // 101 <-> 110
       }
       if (g0 + j * env.W < cnt) {
 #pragma unroll
-        for (int r = 0; r < D; ++r) tile[qsb_slot(base[j] | off[r])] = x[r];
+        for (int r = 0; r < D; ++r) tile[QSB_SLOT(base[j] | off[r])] = x[r];
       }
     }
   }
@@ -406,7 +437,8 @@ QSB_HD void qsb_block_reduce(Env& env, double* v, int nv) {
 // the whole tile belongs to one side (off-diagonal terms are not available there and are not requested).
 template <class Env>
 QSB_PASS void qsb_partial_rdm1(Env& env, int m, int b, double v[4]) {
-  const c128* tile = env.tile();
+  typedef typename Env::amp A;
+  const A* tile = env.tile();
   v[0] = v[1] = v[2] = v[3] = 0.0;
   if (b >= m) {
     double s = 0.0;
@@ -417,7 +449,7 @@ QSB_PASS void qsb_partial_rdm1(Env& env, int m, int b, double v[4]) {
   const int cnt = 1 << (m - 1);
   for (int g = env.wid; g < cnt; g += env.W) {
     int i0 = qsb_ins0(g, b);
-    c128 a0 = tile[qsb_slot(i0)], a1 = tile[qsb_slot(i0 | (1 << b))];
+    const c128 a0 = qsb_wide(tile[QSB_SLOT(i0)]), a1 = qsb_wide(tile[QSB_SLOT(i0 | (1 << b))]);
     v[0] += qsb_norm2(a0);
     v[1] += qsb_norm2(a1);
     v[2] += a0.x * a1.x + a0.y * a1.y;
@@ -430,11 +462,12 @@ QSB_PASS void qsb_partial_rdm1(Env& env, int m, int b, double v[4]) {
 // W(x) |phi_x|^2, W(x) = prod_j wt[j][x_j] (rank bits contribute this CTA's constant factor).
 template <class Env>
 QSB_PASS void qsb_partial_marginal_w(Env& env, int m, int b, const double* wt, double v[4]) {
-  const c128* tile = env.tile();
+  typedef typename Env::amp A;
+  const A* tile = env.tile();
   double* tab = env.ctl()->wtab;
   const int nlo = m < 7 ? m : 7, nhi = m - nlo;
   env.sync_workers();                                    // previous users of wtab are done
-  for (int e = env.wid; e < 192; e += env.W) {
+  for (int e = env.wid; e < 256; e += env.W) {
     double w = 1.0;
     if (e < 128) { for (int j = 0; j < nlo; ++j) w *= wt[2 * j + ((e >> j) & 1)]; }
     else { for (int j = 0; j < nhi; ++j) w *= wt[2 * (nlo + j) + (((e - 128) >> j) & 1)]; }
@@ -446,15 +479,15 @@ QSB_PASS void qsb_partial_marginal_w(Env& env, int m, int b, const double* wt, d
   v[0] = v[1] = v[2] = v[3] = 0.0;
   if (b >= m) {
     double s = 0.0;
-    for (int i = env.wid; i < (1 << m); i += env.W) s += tab[i & 127] * tab[128 + (i >> 7)] * qsb_norm2(tile[qsb_slot(i)]);
+    for (int i = env.wid; i < (1 << m); i += env.W) s += tab[i & 127] * tab[128 + (i >> 7)] * qsb_norm2(tile[QSB_SLOT(i)]);
     v[(env.rank >> (b - m)) & 1] = s * crank;
     return;
   }
   const int cnt = 1 << (m - 1);
   for (int g = env.wid; g < cnt; g += env.W) {
     const int i0 = qsb_ins0(g, b), i1 = i0 | (1 << b);
-    v[0] += tab[i0 & 127] * tab[128 + (i0 >> 7)] * qsb_norm2(tile[qsb_slot(i0)]);
-    v[1] += tab[i1 & 127] * tab[128 + (i1 >> 7)] * qsb_norm2(tile[qsb_slot(i1)]);
+    v[0] += tab[i0 & 127] * tab[128 + (i0 >> 7)] * qsb_norm2(tile[QSB_SLOT(i0)]);
+    v[1] += tab[i1 & 127] * tab[128 + (i1 >> 7)] * qsb_norm2(tile[QSB_SLOT(i1)]);
   }
   v[0] *= crank; v[1] *= crank;
 }
@@ -476,7 +509,8 @@ QSB_HD void qsb_build_perm(Env& env, const int32_t* perm, int n) {
 
 template <class Env>
 QSB_PASS void qsb_do_init(Env& env, const qsb_exec_args& a, const qsb_desc* d) {
-  c128* tile = env.tile();
+  typedef typename Env::amp A;
+  A* tile = env.tile();
   const uint32_t* tab = env.ctl()->perm;
   const int m = a.m;
   qsb_build_perm(env, d->perm, a.n);
@@ -484,12 +518,12 @@ QSB_PASS void qsb_do_init(Env& env, const qsb_exec_args& a, const qsb_desc* d) {
   const bool hoist = (env.W & 31) == 0 && m >= 5;      // the low 5 index bits are then local and equal to the lane
   const uint32_t lo = hoist ? qsb_permute(tab, (uint32_t)env.wid & 31u) : 0u;
   if (d->flags & QSB_RUN_LOAD) {
-    const c128* src = d->gptr;
+    const A* src = static_cast<const A*>(d->gptr);
     // 8 loads in flight per worker: addresses first (the table look-ups and the tile stores are both shared
     // memory, so the compiler will not reorder them itself), then the global loads, then the stores
     for (int i0 = env.wid; i0 < (1 << m); i0 += 8 * env.W) {
       uint32_t s[8];
-      c128 v[8];
+      A v[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int i = i0 + e * env.W;
@@ -501,7 +535,7 @@ QSB_PASS void qsb_do_init(Env& env, const qsb_exec_args& a, const qsb_desc* d) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int i = i0 + e * env.W;
-        if (i < (1 << m)) tile[qsb_slot(i)] = v[e];
+        if (i < (1 << m)) tile[QSB_SLOT(i)] = v[e];
       }
     }
     // LOAD + STORE run in place and the two bit permutations differ, so a CTA's stores land on addresses
@@ -512,7 +546,7 @@ QSB_PASS void qsb_do_init(Env& env, const qsb_exec_args& a, const qsb_desc* d) {
     for (int i = env.wid; i < (1 << m); i += env.W) {
       const uint32_t x = hi | (uint32_t)i;
       const uint32_t s = hoist ? (qsb_permute(tab, x & ~31u) | lo) : qsb_permute(tab, x);
-      tile[qsb_slot(i)] = qsb_c(s == basis ? 1.0 : 0.0, 0.0);
+      tile[QSB_SLOT(i)] = qsb_cvt<A>(qsb_c(s == basis ? 1.0 : 0.0, 0.0));
     }
   }
 }
@@ -520,7 +554,8 @@ QSB_PASS void qsb_do_init(Env& env, const qsb_exec_args& a, const qsb_desc* d) {
 // write the tile (normalised when asked) to gptr[perm(x)], x = tile << m | i
 template <class Env>
 QSB_PASS void qsb_do_store(Env& env, const qsb_exec_args& a, const qsb_desc* d, int& parity) {
-  const c128* tile = env.tile();
+  typedef typename Env::amp A;
+  const A* tile = env.tile();
   const uint32_t* tab = env.ctl()->perm;
   const int m = a.m;
   double scale = 1.0;
@@ -542,19 +577,18 @@ QSB_PASS void qsb_do_store(Env& env, const qsb_exec_args& a, const qsb_desc* d, 
   const uint32_t hi = (uint32_t)d->tile << m;
   const bool hoist = (env.W & 31) == 0 && m >= 5;      // the low 5 index bits are then local and equal to the lane
   const uint32_t lo = hoist ? qsb_permute(tab, (uint32_t)env.wid & 31u) : 0u;
-  c128* out = d->gptr;
+  A* out = static_cast<A*>(d->gptr);
   double* probs = d->probs;
   for (int i0 = env.wid; i0 < (1 << m); i0 += 8 * env.W) {
     uint32_t dst[8];
-    c128 v[8];
+    A v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int i = i0 + e * env.W;
       const int ii = i < (1 << m) ? i : i0;
       const uint32_t x = hi | (uint32_t)ii;
       dst[e] = hoist ? (qsb_permute(tab, x & ~31u) | lo) : qsb_permute(tab, x);
-      v[e] = tile[qsb_slot(ii)];
-      v[e].x *= scale; v[e].y *= scale;
+      v[e] = qsb_scale(tile[QSB_SLOT(ii)], scale);
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -571,11 +605,12 @@ QSB_PASS void qsb_do_store(Env& env, const qsb_exec_args& a, const qsb_desc* d, 
 // Pending matrices travel with their qubits (control-warp bookkeeping), so nothing is flushed here.
 template <class Env>
 QSB_PASS void qsb_do_remap(Env& env, int m, const qsb_desc* d) {
-  c128* tile = env.tile();
+  typedef typename Env::amp A;
+  A* tile = env.tile();
   const int gb = d->b[0], lb = d->b[1];
   const int mybit = (env.rank >> gb) & 1;
-  const c128* peer = env.peer_tile(env.rank ^ (1 << gb));
-  c128 val[QSB_REMAP_REGS];
+  const A* peer = env.peer_tile(env.rank ^ (1 << gb));
+  A val[QSB_REMAP_REGS];
   const int cnt = 1 << (m - 1);
   const unsigned long long pt0 = env.prof_on() ? env.clock() : 0;
   env.cluster_sync_w();                       // every CTA finished the sweeps before the exchange
@@ -584,18 +619,18 @@ QSB_PASS void qsb_do_remap(Env& env, int m, const qsb_desc* d) {
   // Push: read OUR outgoing half into registers (local), barrier (the partner has its outgoing half -- the
   // positions we are about to overwrite -- in registers too), store into the PARTNER's tile (posted DSMEM
   // stores instead of latency-bound DSMEM loads), barrier before anyone reads its tile again.
-  c128* peer_w = const_cast<c128*>(peer);
+  A* peer_w = const_cast<A*>(peer);
   for (int base = 0; base < cnt; base += QSB_REMAP_REGS * env.W) {
 #pragma unroll
     for (int e = 0; e < QSB_REMAP_REGS; ++e) {
       int g = base + e * env.W + env.wid;
-      if (g < cnt) val[e] = tile[qsb_slot(qsb_ins0(g, lb) | ((1 - mybit) << lb))];
+      if (g < cnt) val[e] = tile[QSB_SLOT(qsb_ins0(g, lb) | ((1 - mybit) << lb))];
     }
     env.cluster_sync_w();
 #pragma unroll
     for (int e = 0; e < QSB_REMAP_REGS; ++e) {
       int g = base + e * env.W + env.wid;
-      if (g < cnt) peer_w[qsb_slot(qsb_ins0(g, lb) | (mybit << lb))] = val[e];
+      if (g < cnt) peer_w[QSB_SLOT(qsb_ins0(g, lb) | (mybit << lb))] = val[e];
     }
   }
   env.cluster_sync_w();
@@ -606,13 +641,13 @@ QSB_PASS void qsb_do_remap(Env& env, int m, const qsb_desc* d) {
 #pragma unroll
     for (int e = 0; e < QSB_REMAP_REGS; ++e) {
       int g = base + e * env.W + env.wid;
-      if (g < cnt) val[e] = peer[qsb_slot(qsb_ins0(g, lb) | (mybit << lb))];
+      if (g < cnt) val[e] = peer[QSB_SLOT(qsb_ins0(g, lb) | (mybit << lb))];
     }
     env.cluster_sync_w();
 #pragma unroll
     for (int e = 0; e < QSB_REMAP_REGS; ++e) {
       int g = base + e * env.W + env.wid;
-      if (g < cnt) tile[qsb_slot(qsb_ins0(g, lb) | ((1 - mybit) << lb))] = val[e];
+      if (g < cnt) tile[QSB_SLOT(qsb_ins0(g, lb) | ((1 - mybit) << lb))] = val[e];
     }
   }
 #endif
@@ -625,12 +660,13 @@ QSB_HD int qsb_remap_syncs(int m, int W) {
 // apply the pending 2x2 of cluster-rank bit gb: mine' = P[my][my] mine + P[my][other] partner
 template <class Env>
 QSB_PASS void qsb_do_gflush(Env& env, int m, const qsb_desc* d) {
-  c128* tile = env.tile();
+  typedef typename Env::amp A;
+  A* tile = env.tile();
   const int gb = d->b[0];
   const int mybit = (env.rank >> gb) & 1;
-  const c128* peer = env.peer_tile(env.rank ^ (1 << gb));
-  const c128 pm = d->P[0][mybit * 2 + mybit], po = d->P[0][mybit * 2 + (1 - mybit)];
-  c128 val[QSB_REMAP_REGS];
+  const A* peer = env.peer_tile(env.rank ^ (1 << gb));
+  const A pm = qsb_cvt<A>(d->P[0][mybit * 2 + mybit]), po = qsb_cvt<A>(d->P[0][mybit * 2 + (1 - mybit)]);
+  A val[QSB_REMAP_REGS];
   const int cnt = 1 << m;
   env.cluster_sync_w();
   for (int base = 0; base < cnt; base += QSB_REMAP_REGS * env.W) {
@@ -805,7 +841,7 @@ QSB_CTL void qsb_emit_sweep(Env& env, qsb_cstate& st, int m, int gate, int nb, i
     if (nb > 1) used |= 1u << b1;
     if (nb > 2) used |= 1u << b2;
     int hm;
-    d->pos = qsb_group_order(m, used, env.wbits, m - nb, &hm);
+    d->pos = qsb_group_order(m, used, env.wbits, m - nb, (int)qsb_amp<typename Env::amp>::SW, &hm);
     d->hmask = hm;
   }
   if (mat_src) {
@@ -871,7 +907,7 @@ QSB_CTL void qsb_ctl_rdm1(Env& env, qsb_cstate& st, int b, double v[4], bool wei
 
 template <class Env>
 QSB_CTL void qsb_emit_store(Env& env, qsb_cstate& st, const qsb_exec_args& a, const int32_t* perm,
-                            c128* out, double* probs) {
+                            void* out, double* probs) {
   qsb_desc* d = qsb_desc_begin(env, st);
   if (env.lead) {
     d->kind = QSB_D_STORE; d->flags = a.flags & QSB_RUN_NORMALIZE;
@@ -1038,7 +1074,7 @@ QSB_CTL void qsb_control_slow(Env& env, const qsb_exec_args& a, qsb_cstate& st, 
     case QSB_OP_SNAPSHOT: {
       qsb_flush(env, st, m, all_bits);
       qsb_emit_store(env, st, a, a.idata + op.aux,
-                     a.snapshots ? a.snapshots + (st.t * a.n_snapshots + op.b0) * st.dim : nullptr, nullptr);
+                     a.snapshots ? static_cast<char*>(a.snapshots) + (st.t * a.n_snapshots + op.b0) * st.dim * a.amp_bytes : nullptr, nullptr);
       break;
     }
     default:
@@ -1103,7 +1139,7 @@ QSB_HD void qsb_control_unit(Env& env, qsb_cstate& st, const qsb_exec_args& a, i
       d->unit = unit; d->tile = st.tile;
       d->basis = a.init_basis ? a.init_basis[t] : a.default_basis;
       d->perm = a.idata + a.load_perm;
-      d->gptr = a.states ? a.states + ((a.flags & QSB_RUN_LOAD_BROADCAST) ? 0 : t * st.dim) : nullptr;
+      d->gptr = a.states ? static_cast<char*>(a.states) + ((a.flags & QSB_RUN_LOAD_BROADCAST) ? 0 : t * st.dim) * a.amp_bytes : nullptr;
     }
     qsb_desc_end(env, st);
   }
@@ -1184,7 +1220,7 @@ QSB_HD void qsb_control_unit(Env& env, qsb_cstate& st, const qsb_exec_args& a, i
   qsb_flush(env, st, a.m, all_bits);
   if (a.flags & (QSB_RUN_STORE | QSB_RUN_ACCUM_PROBS))
     qsb_emit_store(env, st, a, a.idata + a.store_perm,
-                   (a.flags & QSB_RUN_STORE) ? a.states_out + t * st.dim : nullptr,
+                   (a.flags & QSB_RUN_STORE) ? static_cast<char*>(a.states_out) + t * st.dim * a.amp_bytes : nullptr,
                    (a.flags & QSB_RUN_ACCUM_PROBS) ? a.probs_accum : nullptr);
 }
 

@@ -36,8 +36,9 @@ __device__ __forceinline__ void qsb_cluster_wait() {
 }
 
 // threads [0, W) are workers, [W, W + 32) is the control warp
-template <int CS>
+template <int CS, class A = c128>
 struct DeviceEnv {
+  typedef A amp;
   static constexpr int C = CS;
   static constexpr int CL = QSB_CTL_THREADS;
   int wid, W, wbits, rank, m_;
@@ -59,9 +60,9 @@ struct DeviceEnv {
     m_ = m;
   }
   // pointers are re-derived from the shared symbol at every use so that loads/stores stay LDS/STS
-  __device__ __forceinline__ c128* tile() { return reinterpret_cast<c128*>(qsb_smem); }
-  __device__ __forceinline__ qsb_ctl* ctl() { return reinterpret_cast<qsb_ctl*>(qsb_smem + ((size_t)16 << m_)); }
-  __device__ __forceinline__ const c128* peer_tile(int r) {
+  __device__ __forceinline__ A* tile() { return reinterpret_cast<A*>(qsb_smem); }
+  __device__ __forceinline__ qsb_ctl* ctl() { return reinterpret_cast<qsb_ctl*>(qsb_smem + (sizeof(A) << m_)); }
+  __device__ __forceinline__ const A* peer_tile(int r) {
     if (CS > 1) return cg::this_cluster().map_shared_rank(tile(), r);
     return tile();
   }
@@ -135,10 +136,10 @@ struct DeviceEnv {
   __device__ __forceinline__ void handoff_c() { __syncwarp(); qsb_bar_sync(QSB_BAR_ALL, W + QSB_CTL_THREADS); }
 };
 
-template <int CS>
+template <int CS, class A>
 __global__ void __launch_bounds__(QSB_MAX_WORKERS + QSB_CTL_THREADS, 1)
 qsb_traj_kernel(const __grid_constant__ qsb_exec_args a) {
-  DeviceEnv<CS> env(a.m);
+  DeviceEnv<CS, A> env(a.m);
   env.prof_ = a.prof;
   env.xphase = 0;
   if (CS > 1) {
@@ -178,20 +179,24 @@ __device__ __forceinline__ void qsb_block_sum(double* v, double* scratch) {
   }
 }
 
+// The reductions read states in the context's amplitude type (complex128, or complex64 in c64 mode) and
+// accumulate in double.
 // |a|^2 elementwise (state_vector.py:36-39)
-__global__ void qsb_probs_kernel(const c128* __restrict__ psi, double* __restrict__ out, int64_t total) {
+template <class A>
+__global__ void qsb_probs_kernel(const A* __restrict__ psi, double* __restrict__ out, int64_t total) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    c128 a = psi[i];
+    c128 a = qsb_wide(psi[i]);
     out[i] = a.x * a.x + a.y * a.y;
   }
 }
 
 // out[i] += sum_t |psi_t[i]|^2
-__global__ void qsb_probs_sum_kernel(const c128* __restrict__ psi, double* __restrict__ out, int64_t dim, int64_t count) {
+template <class A>
+__global__ void qsb_probs_sum_kernel(const A* __restrict__ psi, double* __restrict__ out, int64_t dim, int64_t count) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < dim; i += (int64_t)gridDim.x * blockDim.x) {
     double s = 0.0;
     for (int64_t t = 0; t < count; ++t) {
-      c128 a = psi[t * dim + i];
+      c128 a = qsb_wide(psi[t * dim + i]);
       s += a.x * a.x + a.y * a.y;
     }
     out[i] += s;
@@ -200,15 +205,16 @@ __global__ void qsb_probs_sum_kernel(const c128* __restrict__ psi, double* __res
 
 // StateVector.measure_all (state_vector.py:107-113): first index whose running probability mass exceeds
 // u * total  (== searchsorted(cumsum(p / p.sum()) / cdf[-1], u, side='right'))
-__global__ void qsb_sample_kernel(const c128* __restrict__ psi, const double* __restrict__ u, int64_t* __restrict__ out,
+template <class A>
+__global__ void qsb_sample_kernel(const A* __restrict__ psi, const double* __restrict__ u, int64_t* __restrict__ out,
                                   int64_t dim) {
   __shared__ double chunk_sum[256];
   __shared__ double prefix[257];
-  const c128* s = psi + blockIdx.x * dim;
+  const A* s = psi + blockIdx.x * dim;
   const int T = blockDim.x, tid = threadIdx.x;
   const int64_t per = (dim + T - 1) / T, lo = tid * per, hi = (lo + per < dim) ? lo + per : dim;
   double acc = 0.0;
-  for (int64_t i = lo; i < hi; ++i) { c128 a = s[i]; acc += a.x * a.x + a.y * a.y; }
+  for (int64_t i = lo; i < hi; ++i) { c128 a = qsb_wide(s[i]); acc += a.x * a.x + a.y * a.y; }
   chunk_sum[tid] = acc;
   __syncthreads();
   if (tid == 0) {
@@ -225,7 +231,7 @@ __global__ void qsb_sample_kernel(const c128* __restrict__ psi, const double* __
     double run = prefix[tid];
     int64_t pick = -1, last_nz = hi - 1;
     for (int64_t i = lo; i < hi; ++i) {
-      c128 a = s[i];
+      c128 a = qsb_wide(s[i]);
       double p = a.x * a.x + a.y * a.y;
       run += p;
       if (p > 0.0) last_nz = i;
@@ -236,14 +242,15 @@ __global__ void qsb_sample_kernel(const c128* __restrict__ psi, const double* __
 }
 
 // out[t] = sum_i conj(a_t[i]) * b_t[i]   (np.vdot, analysis.py:40)
-__global__ void qsb_overlap_kernel(const c128* __restrict__ a, const c128* __restrict__ b, int64_t b_stride,
+template <class A>
+__global__ void qsb_overlap_kernel(const A* __restrict__ a, const A* __restrict__ b, int64_t b_stride,
                                    c128* __restrict__ out, int64_t dim) {
   __shared__ double scratch[64];
-  const c128* x = a + blockIdx.x * dim;
-  const c128* y = b + blockIdx.x * b_stride;
+  const A* x = a + blockIdx.x * dim;
+  const A* y = b + blockIdx.x * b_stride;
   double v[2] = {0.0, 0.0};
   for (int64_t i = threadIdx.x; i < dim; i += blockDim.x) {
-    c128 p = x[i], q = y[i];
+    c128 p = qsb_wide(x[i]), q = qsb_wide(y[i]);
     v[0] += p.x * q.x + p.y * q.y;
     v[1] += p.x * q.y - p.y * q.x;
   }
@@ -253,13 +260,14 @@ __global__ void qsb_overlap_kernel(const c128* __restrict__ a, const c128* __res
 
 // large states: stage 1, CTA c sums the slice [c * per, (c + 1) * per) of one state pair into part[c];
 // stage 2 (one CTA) adds the partials in index order, so the result does not depend on scheduling
-__global__ void qsb_overlap_partial_kernel(const c128* __restrict__ x, const c128* __restrict__ y, int64_t dim,
+template <class A>
+__global__ void qsb_overlap_partial_kernel(const A* __restrict__ x, const A* __restrict__ y, int64_t dim,
                                            int64_t per, c128* __restrict__ part) {
   __shared__ double scratch[64];
   const int64_t lo = blockIdx.x * per, hi = (lo + per < dim) ? lo + per : dim;
   double v[2] = {0.0, 0.0};
   for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-    c128 p = x[i], q = y[i];
+    c128 p = qsb_wide(x[i]), q = qsb_wide(y[i]);
     v[0] += p.x * q.x + p.y * q.y;
     v[1] += p.x * q.y - p.y * q.x;
   }
@@ -275,10 +283,11 @@ __global__ void qsb_overlap_final_kernel(const c128* __restrict__ part, int n_pa
 }
 
 // (p_even, p_odd) per mask (qec.py:466-484); up to 8 masks per launch
-__global__ void qsb_parity_kernel(const c128* __restrict__ psi, int64_t dim, const uint64_t* __restrict__ masks,
+template <class A>
+__global__ void qsb_parity_kernel(const A* __restrict__ psi, int64_t dim, const uint64_t* __restrict__ masks,
                                   int n_masks, double* __restrict__ out) {
   __shared__ double scratch[32 * 16];
-  const c128* s = psi + blockIdx.x * dim;
+  const A* s = psi + blockIdx.x * dim;
   double v[16];
 #pragma unroll
   for (int k = 0; k < 16; ++k) v[k] = 0.0;
@@ -286,7 +295,7 @@ __global__ void qsb_parity_kernel(const c128* __restrict__ psi, int64_t dim, con
 #pragma unroll
   for (int k = 0; k < 8; ++k) mk[k] = k < n_masks ? masks[k] : 0;
   for (int64_t i = threadIdx.x; i < dim; i += blockDim.x) {
-    c128 a = s[i];
+    c128 a = qsb_wide(s[i]);
     double p = a.x * a.x + a.y * a.y;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -304,17 +313,18 @@ __global__ void qsb_parity_kernel(const c128* __restrict__ psi, int64_t dim, con
 }
 
 // 1-qubit RDMs: block (t, q) -> rdm1[t][q][2][2]  (state_vector.py:121-140)
-__global__ void qsb_rdm1_kernel(const c128* __restrict__ psi, int n, c128* __restrict__ out) {
+template <class A>
+__global__ void qsb_rdm1_kernel(const A* __restrict__ psi, int n, c128* __restrict__ out) {
   __shared__ double scratch[32 * 4];
   const int64_t dim = (int64_t)1 << n;
   const int q = blockIdx.x % n;
   const int64_t t = blockIdx.x / n;
   const int b = n - 1 - q;
-  const c128* s = psi + t * dim;
+  const A* s = psi + t * dim;
   double v[4] = {0, 0, 0, 0};
   for (int64_t g = threadIdx.x; g < dim / 2; g += blockDim.x) {
     int64_t i0 = ((g >> b) << (b + 1)) | (g & (((int64_t)1 << b) - 1));
-    c128 a0 = s[i0], a1 = s[i0 | ((int64_t)1 << b)];
+    c128 a0 = qsb_wide(s[i0]), a1 = qsb_wide(s[i0 | ((int64_t)1 << b)]);
     v[0] += a0.x * a0.x + a0.y * a0.y;
     v[1] += a1.x * a1.x + a1.y * a1.y;
     v[2] += a0.x * a1.x + a0.y * a1.y;      // a0 conj(a1)
@@ -332,7 +342,8 @@ __global__ void qsb_rdm1_kernel(const c128* __restrict__ psi, int n, c128* __res
 
 // 2-qubit RDMs: block (t, pair) -> rdm2[t][pair][4][4], row index = (bit_i << 1 | bit_j), i < j
 // rho[r][c] = sum_env psi[r,env] conj(psi[c,env])   (analysis.py:159-166)
-__global__ void qsb_rdm2_kernel(const c128* __restrict__ psi, int n, int npairs, c128* __restrict__ out) {
+template <class A>
+__global__ void qsb_rdm2_kernel(const A* __restrict__ psi, int n, int npairs, c128* __restrict__ out) {
   __shared__ double scratch[32 * 16];
   const int64_t dim = (int64_t)1 << n;
   int pair = blockIdx.x % npairs;
@@ -341,7 +352,7 @@ __global__ void qsb_rdm2_kernel(const c128* __restrict__ psi, int n, int npairs,
   while (rem >= n - 1 - qi) { rem -= n - 1 - qi; ++qi; }
   const int qj = qi + 1 + rem;
   const int bh = n - 1 - qi, bl = n - 1 - qj;    // bh > bl
-  const c128* s = psi + t * dim;
+  const A* s = psi + t * dim;
   double v[16];
 #pragma unroll
   for (int k = 0; k < 16; ++k) v[k] = 0.0;
@@ -349,10 +360,10 @@ __global__ void qsb_rdm2_kernel(const c128* __restrict__ psi, int n, int npairs,
     int64_t i = ((g >> bl) << (bl + 1)) | (g & (((int64_t)1 << bl) - 1));
     i = ((i >> bh) << (bh + 1)) | (i & (((int64_t)1 << bh) - 1));
     c128 a[4];
-    a[0] = s[i];
-    a[1] = s[i | ((int64_t)1 << bl)];
-    a[2] = s[i | ((int64_t)1 << bh)];
-    a[3] = s[i | ((int64_t)1 << bh) | ((int64_t)1 << bl)];
+    a[0] = qsb_wide(s[i]);
+    a[1] = qsb_wide(s[i | ((int64_t)1 << bl)]);
+    a[2] = qsb_wide(s[i | ((int64_t)1 << bh)]);
+    a[3] = qsb_wide(s[i | ((int64_t)1 << bh) | ((int64_t)1 << bl)]);
     // diag (4 reals) + upper triangle (6 complex)
     int k = 0;
 #pragma unroll
@@ -383,10 +394,11 @@ __global__ void qsb_rdm2_kernel(const c128* __restrict__ psi, int n, int npairs,
 // rho[r][c] = sum_env psi[r, env] conj(psi[c, env]); kept_bits[0] = index bit of the first kept qubit (the MSB of
 // r), env_bits = the other n - k index bits.  One CTA per state; a thread owns whole (r, c) entries, so every
 // entry is one ordered sum (deterministic).
-__global__ void qsb_rdm_general_kernel(const c128* __restrict__ psi, int n, int k, const int* __restrict__ kept_bits,
+template <class A>
+__global__ void qsb_rdm_general_kernel(const A* __restrict__ psi, int n, int k, const int* __restrict__ kept_bits,
                                        const int* __restrict__ env_bits, c128* __restrict__ out) {
   const int64_t dim = (int64_t)1 << n;
-  const c128* s = psi + blockIdx.x * dim;
+  const A* s = psi + blockIdx.x * dim;
   const int D = 1 << k, ne = n - k;
   __shared__ int kb[8], eb[32];
   if (threadIdx.x < k) kb[threadIdx.x] = kept_bits[threadIdx.x];
@@ -404,7 +416,7 @@ __global__ void qsb_rdm_general_kernel(const c128* __restrict__ psi, int n, int 
     for (int64_t env = 0; env < ((int64_t)1 << ne); ++env) {
       int64_t base = 0;
       for (int j = 0; j < ne; ++j) base |= ((env >> j) & 1) << eb[j];
-      const c128 a = s[base | ir], b = s[base | ic];
+      const c128 a = qsb_wide(s[base | ir]), b = qsb_wide(s[base | ic]);
       re += a.x * b.x + a.y * b.y;                     // a conj(b)
       im += a.y * b.x - a.x * b.y;
     }
@@ -514,7 +526,8 @@ __device__ __forceinline__ void qsb_dmma(double& d0, double& d1, double a, doubl
                : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(256) qsb_rho_kernel(const c128* __restrict__ psi, int64_t dim, int64_t count,
+template <class A>
+__global__ void __launch_bounds__(256) qsb_rho_kernel(const A* __restrict__ psi, int64_t dim, int64_t count,
                                                        double scale, c128* __restrict__ rho, int tiles_per_side) {
   // re / im planes of the two 64-wide panels, [k][x]
   __shared__ double sa_re[QSB_RHO_KC][QSB_RHO_TILE + QSB_RHO_PAD], sa_im[QSB_RHO_KC][QSB_RHO_TILE + QSB_RHO_PAD];
@@ -537,8 +550,8 @@ __global__ void __launch_bounds__(256) qsb_rho_kernel(const c128* __restrict__ p
       const int k = e / QSB_RHO_TILE, x = e % QSB_RHO_TILE;
       c128 za = make_double2(0.0, 0.0), zb = za;
       if (t0 + k < count) {
-        if (i0 + x < dim) za = psi[(t0 + k) * dim + i0 + x];
-        if (j0 + x < dim) zb = psi[(t0 + k) * dim + j0 + x];
+        if (i0 + x < dim) za = qsb_wide(psi[(t0 + k) * dim + i0 + x]);
+        if (j0 + x < dim) zb = qsb_wide(psi[(t0 + k) * dim + j0 + x]);
       }
       sa_re[k][x] = za.x; sa_im[k][x] = za.y;
       sb_re[k][x] = zb.x; sb_im[k][x] = zb.y;

@@ -22,7 +22,7 @@ RUN_LOAD, RUN_STORE, RUN_NORMALIZE, RUN_ASYNC, RUN_ACCUM_PROBS, RUN_LOAD_BROADCA
 
 SYMBOLS = [
     "qsb_version", "qsb_device_count", "qsb_ctx_create", "qsb_ctx_destroy", "qsb_ctx_set_stream",
-    "qsb_ctx_sync", "qsb_last_error", "qsb_ctx_info", "qsb_timer_start", "qsb_timer_stop",
+    "qsb_ctx_sync", "qsb_ctx_set_precision", "qsb_last_error", "qsb_ctx_info", "qsb_timer_start", "qsb_timer_stop",
     "qsb_launch_count", "qsb_buffer_alloc", "qsb_buffer_wrap", "qsb_buffer_free", "qsb_buffer_upload",
     "qsb_buffer_download", "qsb_buffer_zero", "qsb_buffer_copy", "qsb_buffer_ptr", "qsb_buffer_bytes",
     "qsb_host_alloc", "qsb_host_free", "qsb_program_create", "qsb_program_free", "qsb_run",
@@ -70,6 +70,7 @@ def load_library():
             "qsb_ctx_destroy": (C.c_int, [vp]),
             "qsb_ctx_set_stream": (C.c_int, [vp, vp]),
             "qsb_ctx_sync": (C.c_int, [vp]),
+            "qsb_ctx_set_precision": (C.c_int, [vp, C.c_int]),
             "qsb_last_error": (C.c_char_p, [vp]),
             "qsb_ctx_info": (C.c_int, [vp, P(i32), P(i32), P(i32), P(i64)]),
             "qsb_timer_start": (C.c_int, [vp]),
@@ -203,6 +204,24 @@ class Context:
         sm, ma, mi, mem = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int64()
         _check(self.lib.qsb_ctx_info(h, C.byref(sm), C.byref(ma), C.byref(mi), C.byref(mem)), h)
         self.sm_count, self.cc, self.total_mem = sm.value, (ma.value, mi.value), mem.value
+        self.precision = "c128"
+
+    # -- precision -------------------------------------------------------------------------
+    def set_precision(self, precision):
+        """"c128" (default, the reference's complex128) or "c64" (complex64 state buffers, tolerance 1e-5).
+        Programs keep the mode they were created in; state buffers must be allocated / uploaded in that type."""
+        if precision not in ("c128", "c64"):
+            raise ValueError("precision must be 'c128' or 'c64'")
+        _check(self.lib.qsb_ctx_set_precision(self.handle, 1 if precision == "c64" else 0), self.handle)
+        self.precision = precision
+
+    @property
+    def amp_bytes(self):
+        return 8 if self.precision == "c64" else 16
+
+    @property
+    def amp_dtype(self):
+        return np.complex64 if self.precision == "c64" else np.complex128
 
     # -- memory -------------------------------------------------------------------------
     def alloc(self, nbytes):

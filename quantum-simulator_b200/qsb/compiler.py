@@ -328,12 +328,13 @@ class Lowering:
                           n_draws=self.n_draws, n_params=self.n_params)
 
     # -- slot placement + emission ------------------------------------------------------
-    def finish(self, local_bits=None):
+    def finish(self, local_bits=None, max_local_bits=MAX_LOCAL_BITS):
+        """max_local_bits: 13 for complex128 tiles, 14 in the context's complex64 mode (twice the amplitudes per CTA)."""
         n = self.n
         if n > MAX_QUBITS:
             raise NotImplementedError(f"the resident executor holds at most {MAX_QUBITS} qubits, got {n}")
-        m = default_local_bits(n) if local_bits is None else int(local_bits)
-        if not (1 <= m <= min(n, MAX_LOCAL_BITS)) or n - m > 3:
+        m = min(n, max_local_bits) if local_bits is None else int(local_bits)
+        if not (1 <= m <= min(n, max_local_bits)) or n - m > 3:
             raise ValueError(f"local_bits {m} invalid for n = {n}")
         g = n - m
         items = self.items

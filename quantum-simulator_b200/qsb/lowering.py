@@ -13,7 +13,7 @@ SKIP_TYPES = ("measurement", "barrier")
 
 
 def lower_circuit(n, columns, registry, channels_of=None, *, record_steps=False, param_offsets=None,
-                  layout="reference", local_bits=None, extra=None, stream=False):
+                  layout="reference", local_bits=None, extra=None, stream=False, max_local_bits=13):
     """Lower ordered gate columns.
 
     columns      : circuit.get_ordered_gates() -- lists of objects with gate_name / target_qubits / params
@@ -49,4 +49,4 @@ def lower_circuit(n, columns, registry, channels_of=None, *, record_steps=False,
         extra(lw)
     if stream:
         return lw.finish_stream(local_bits), has_meas
-    return lw.finish(local_bits), has_meas
+    return lw.finish(local_bits, max_local_bits), has_meas

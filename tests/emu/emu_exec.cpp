@@ -32,6 +32,7 @@ struct Shared {
 };
 
 struct HostEnv {
+  typedef c128 amp;
   static constexpr int CL = 1;
   int wid, W, wbits, rank, C;
   int cta;                      // index of this CTA's storage (== rank in cluster mode)
@@ -102,6 +103,7 @@ extern "C" int emu_run(int n, int m, int T, const qsb_op* ops, int64_t n_ops, in
   a.n = n; a.m = m; a.load_perm = load_perm; a.store_perm = store_perm; a.n_snapshots = n_snapshots;
   a.flags = flags; a.states = (c128*)states; a.states_out = states_out ? (c128*)states_out : (c128*)states; a.count = count;
   a.tile_bits = streaming ? n - m : 0;
+  a.amp_bytes = 16;
   a.params = params; a.params_stride = params_stride;
   a.uniforms = uniforms; a.uniforms_stride = uniforms_stride;
   a.seed = seed; a.traj_offset = traj_offset;

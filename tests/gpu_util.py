@@ -6,16 +6,28 @@ from qsb import capi
 
 
 def gpu_run(prog, count=1, T=None, states=None, params=None, uniforms=None, seed=0, traj_offset=0,
-            init_basis=None, default_basis=0, want_branches=False, store=True, accum_probs=False, out_of_place=False):
+            init_basis=None, default_basis=0, want_branches=False, store=True, accum_probs=False, out_of_place=False,
+            precision="c128"):
     ctx = capi.get_context()
+    ctx.set_precision(precision)
+    try:
+        return _gpu_run(ctx, prog, count, states, params, uniforms, seed, traj_offset, init_basis, default_basis,
+                        want_branches, store, accum_probs, out_of_place)
+    finally:
+        ctx.set_precision("c128")
+
+
+def _gpu_run(ctx, prog, count, states, params, uniforms, seed, traj_offset, init_basis, default_basis, want_branches,
+             store, accum_probs, out_of_place):
     dim = 1 << prog.n
+    AB, AD = ctx.amp_bytes, ctx.amp_dtype
     dp = ctx.program(prog)
     load = states is not None
     if load:
-        host = np.ascontiguousarray(states, dtype=np.complex128).reshape(count, dim)
+        host = np.ascontiguousarray(states, dtype=np.complex128).reshape(count, dim).astype(AD)
         sbuf = ctx.to_device(host)
     else:
-        sbuf = ctx.alloc(count * dim * 16).zero()
+        sbuf = ctx.alloc(count * dim * AB).zero()
     kw = {}
     if params is not None:
         p = np.ascontiguousarray(params, dtype=np.float64).reshape(count, -1)
@@ -31,17 +43,17 @@ def gpu_run(prog, count=1, T=None, states=None, params=None, uniforms=None, seed
         bbuf = ctx.to_device(np.full((count, bs), -1, dtype=np.int32))
         kw.update(branches=bbuf, branches_stride=bs)
     if prog.n_snapshots:
-        sn = ctx.alloc(count * prog.n_snapshots * dim * 16).zero()
+        sn = ctx.alloc(count * prog.n_snapshots * dim * AB).zero()
         kw.update(snapshots=sn)
     if accum_probs:
         pb = ctx.alloc(dim * 8).zero()
         kw.update(probs_accum=pb)
-    obuf = ctx.alloc(count * dim * 16).zero() if out_of_place else None
+    obuf = ctx.alloc(count * dim * AB).zero() if out_of_place else None
     ctx.run(dp, count, states=sbuf, load=load, store=store, seed=seed, traj_offset=traj_offset,
             default_basis=default_basis, states_out=obuf, **kw)
     if obuf is not None:
         sbuf = obuf
-    return dict(states=sbuf.download(np.complex128, (count, dim)),
-                snapshots=sn.download(np.complex128, (count, prog.n_snapshots, dim)) if sn is not None else None,
+    return dict(states=sbuf.download(AD, (count, dim)).astype(np.complex128),
+                snapshots=sn.download(AD, (count, prog.n_snapshots, dim)).astype(np.complex128) if sn is not None else None,
                 branches=bbuf.download(np.int32, (count, max(prog.n_draws, 1))) if bbuf is not None else None,
                 probs=pb.download(np.float64, (dim,)) if pb is not None else None)

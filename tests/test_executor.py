@@ -234,3 +234,58 @@ def test_streaming_passes_vs_oracle(run, n, m):
     for g in ordered:
         ref_t = O.apply_textbook(ref_t, n, O.gate_matrix(g.gate_name, g.params), list(g.target_qubits))
     assert np.max(np.abs(got_t - ref_t)) < TOL
+
+
+# ---- complex64 mode (BASELINE: reported separately, tolerance 1e-5) ---------------------------------------------
+TOL64 = 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gbits", [0, 1, 3])
+def test_c64_random_circuits_and_snapshots(golden, gbits):
+    from gpu_util import gpu_run
+    j, a = golden
+    for rec in j["random_circuits"]:
+        n = rec["n"]
+        m = n - gbits
+        if m < 3:
+            continue
+        qc = make_circuit(n, as_gates(rec["gates"]), rec["initial"])
+        prog, _ = lower_circuit(n, qc.get_ordered_gates(), REG, record_steps=True, local_bits=m)
+        out = gpu_run(prog, default_basis=basis_index(rec["initial"]), precision="c64")
+        assert np.max(np.abs(out["states"][0] - a[rec["tag"]])) < TOL64, rec["tag"]
+        assert np.max(np.abs(out["snapshots"][0] - a[rec["tag"] + "_steps"])) < TOL64, rec["tag"]
+
+
+@pytest.mark.gpu
+def test_c64_noisy_16q_cluster4_and_reductions():
+    """16 qubits in complex64: 2^14 amplitudes per CTA, clusters of 4; Philox-free reference draws.  Branch
+    decisions can differ from complex128 only when a uniform lands within fp32 rounding of a threshold."""
+    from gpu_util import gpu_run
+    from qsb import capi
+    n = 16
+    gates = layered_circuit(n, 8, 2026)
+    noise = config3_noise()
+    qc = make_circuit(n, gates)
+    prog, _ = lower_circuit(n, qc.get_ordered_gates(), REG, channels_of_factory(noise), local_bits=14, max_local_bits=14)
+    assert (prog.n, prog.m) == (16, 14)
+    draws = np.random.default_rng(5).random((3, prog.n_draws))
+    out = gpu_run(prog, count=3, uniforms=draws, want_branches=True, precision="c64")
+    for t in range(3):
+        psi, _, br, _ = O.run_state(n, gates, None, noise, draws[t])
+        assert out["branches"][t].tolist() == br
+        assert np.max(np.abs(out["states"][t] - psi)) < TOL64
+    # reductions on complex64 buffers accumulate in double
+    ctx = capi.get_context()
+    ctx.set_precision("c64")
+    try:
+        psi = out["states"].astype(np.complex64)
+        buf = ctx.to_device(psi)
+        pr = ctx.alloc(3 * 2 ** n * 8)
+        ctx.probabilities(n, buf, 0, 3, pr)
+        assert np.max(np.abs(pr.download(np.float64, (3, 2 ** n)) - np.abs(psi.astype(np.complex128)) ** 2)) < 1e-12
+        ov = ctx.alloc(3 * 16)
+        ctx.overlap(n, buf, 0, buf, 0, 1, 3, ov)
+        assert np.max(np.abs(ov.download(np.complex128, (3,)) - np.sum(np.abs(psi.astype(np.complex128)) ** 2, axis=1))) < 1e-12
+    finally:
+        ctx.set_precision("c128")
