@@ -270,7 +270,7 @@ def run_ours(args):
 
     # ---- end to end through the engine API with host buffers: Simulator.run_with_noise(circuit, shots)
     e2e_T = args.e2e_traj
-    sim.run_with_noise(qc, shots=min(e2e_T, 64), seed=1)        # warm-up (program cached, context hot)
+    sim.run_with_noise(qc, shots=e2e_T, seed=1)      # warm-up: program cached, staging pinned, pool blocks mapped
     fence()
     t0 = time.perf_counter()
     for s in range(args.e2e_steps):
@@ -400,6 +400,42 @@ def measure_other_paths(ctx, sim, qc16):
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     out["config4_steane_cycles_bulk_draws"] = {"cycles": Tq, "seconds": dt, "cycles_per_s": Tq / dt}
+    # complex64 mode of the headline workload (BASELINE: reported separately, tolerance 1e-5): same circuit, noise
+    # and draws; 2^14 complex64 amplitudes per CTA -> clusters of 4 and all 148 SMs busy
+    try:
+        from qsb.lowering import lower_circuit
+        nm16 = sim._noise_model
+        T64, n16 = 2048, qc16.num_qubits
+        u64 = ctx.to_device(np.random.default_rng(777).random((T64, 1)))     # placeholder, resized below
+        res64 = {}
+        for m64 in (14, 13):
+            prog64, _ = lower_circuit(n16, qc16.get_ordered_gates(), sim._gate_registry,
+                                      lambda name: nm16._channel_specs(name), local_bits=m64, max_local_bits=14)
+            D64 = prog64.n_draws
+            draws = np.random.default_rng(777).random((T64, D64))
+            ctx.set_precision("c64")
+            try:
+                dp64 = ctx.program(prog64)
+                u64 = ctx.to_device(draws)
+                st64 = ctx.alloc(T64 * (8 << n16))
+                ctx.run(dp64, 256, states=st64, uniforms=u64, uniforms_stride=D64)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                ctx.run(dp64, T64, states=st64, uniforms=u64, uniforms_stride=D64, async_=True)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1)
+                nrm = ctx.alloc(T64 * 16)
+                ctx.overlap(n16, st64, 0, st64, 0, 1, T64, nrm)
+                worst = float(np.max(np.abs(nrm.download(np.complex128, (T64,)) - 1.0)))
+            finally:
+                ctx.set_precision("c128")
+            res64[f"local_bits_{m64}"] = {"cluster": 1 << (n16 - m64), "trajectories": T64, "ms": ms,
+                                          "trajectories_per_s": T64 / (ms * 1e-3), "max_norm_error": worst}
+        out["headline_complex64"] = res64
+    except Exception as e:
+        out["headline_complex64"] = {"error": repr(e)}
     # config 5 (single-GPU leg): 26-qubit layered circuit streamed through shared memory
     try:
         from qsb.bigstate import BigState
@@ -428,7 +464,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--traj", type=int, default=4096, help="trajectories per GPU per step")
     ap.add_argument("--e2e-traj", type=int, default=2048)
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the short secondary measurements (configs 2-5)")

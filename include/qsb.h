@@ -152,10 +152,17 @@ int qsb_timer_stop(qsb_ctx* ctx, float* ms_out);  /* synchronises */
 int64_t qsb_launch_count(qsb_ctx* ctx);
 
 /* ---- device buffers / host staging ------------------------------------------- */
+/* Buffers come from a per-context stream-ordered pool that keeps freed blocks cached, so the per-call batch
+ * allocations of Simulator.run_with_noise (simulator.py:140-193 builds a fresh StateVector per shot) cost
+ * microseconds; qsb_ctx_trim hands the cached blocks back to the driver. */
 int qsb_buffer_alloc(qsb_ctx* ctx, int64_t bytes, qsb_buffer** out);
+int qsb_ctx_trim(qsb_ctx* ctx);
 int qsb_buffer_wrap(qsb_ctx* ctx, void* device_ptr, int64_t bytes, qsb_buffer** out);
 int qsb_buffer_free(qsb_buffer* buf);
 int qsb_buffer_upload(qsb_buffer* buf, int64_t offset, const void* host, int64_t bytes);
+/* no host wait: `host` must stay untouched until an event recorded after the call has been waited for
+ * (truly asynchronous only from qsb_host_alloc memory) */
+int qsb_buffer_upload_async(qsb_buffer* buf, int64_t offset, const void* host, int64_t bytes);
 int qsb_buffer_download(qsb_buffer* buf, int64_t offset, void* host, int64_t bytes);
 int qsb_buffer_zero(qsb_buffer* buf, int64_t offset, int64_t bytes);
 int qsb_buffer_copy(qsb_buffer* dst, int64_t dst_off, qsb_buffer* src, int64_t src_off, int64_t bytes);
@@ -163,6 +170,12 @@ void* qsb_buffer_ptr(qsb_buffer* buf);
 int64_t qsb_buffer_bytes(qsb_buffer* buf);
 int qsb_host_alloc(int64_t bytes, void** out);    /* pinned host memory for NumPy views */
 int qsb_host_free(void* p);
+/* markers on the ctx stream, for pipelining host-side draw generation against running trajectories */
+typedef struct qsb_event qsb_event;
+int qsb_event_create(qsb_ctx* ctx, qsb_event** out);
+int qsb_event_record(qsb_event* ev);
+int qsb_event_wait(qsb_event* ev);                 /* blocks the host until the recorded point has executed */
+int qsb_event_free(qsb_event* ev);
 
 /* ---- programs ------------------------------------------------------------------
  * Replaces the per-gate loop of Simulator.run (simulator.py:57-71), NoiseModel.apply

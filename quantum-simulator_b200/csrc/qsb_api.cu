@@ -25,6 +25,7 @@ struct qsb_ctx {
   int amp_bytes;                // 16: complex128 states (default); 8: complex64 mode (qsb_ctx_set_precision)
   unsigned long long* d_prof;   // cycle counters of the last qsb_run (qsb_debug_profile), or NULL
   int prof_ctas;
+  cudaMemPool_t pool = nullptr; // device buffers come from here (stream-ordered, freed blocks stay cached)
 };
 
 struct qsb_buffer {
@@ -114,6 +115,18 @@ int qsb_ctx_create(int device, qsb_ctx** out) {
   if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
   if (e == cudaSuccess) e = cudaMalloc(&c->d_masks, 8 * sizeof(uint64_t));
+  if (e == cudaSuccess) {                      // private stream-ordered pool that keeps freed blocks mapped
+    cudaMemPoolProps pp = {};
+    pp.allocType = cudaMemAllocationTypePinned;
+    pp.handleTypes = cudaMemHandleTypeNone;
+    pp.location.type = cudaMemLocationTypeDevice;
+    pp.location.id = device;
+    e = cudaMemPoolCreate(&c->pool, &pp);
+    if (e == cudaSuccess) {
+      uint64_t keep = UINT64_MAX;
+      e = cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   if (e != cudaSuccess) {
     delete c;
     return fail(nullptr, QSB_E_CUDA, "context setup: %s", cudaGetErrorString(e));
@@ -133,6 +146,7 @@ int qsb_ctx_destroy(qsb_ctx* ctx) {
   cudaFree(ctx->d_prof);
   cudaFree(ctx->d_part);
   cudaFree(ctx->d_bits);
+  if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
   delete ctx;
   return QSB_OK;
 }
@@ -192,13 +206,30 @@ int64_t qsb_launch_count(qsb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int qsb_buffer_alloc(qsb_ctx* ctx, int64_t bytes, qsb_buffer** out) {
   if (!ctx || !out || bytes < 0) return fail(ctx, QSB_E_INVAL, "qsb_buffer_alloc: bad argument");
   CU(ctx, cudaSetDevice(ctx->device));
+  // stream-ordered allocation from the context's pool, which keeps freed blocks (release threshold
+  // raised in qsb_ctx_create): per-call state batches of a few GB neither page-fault nor stall in cudaFree
   void* p = nullptr;
-  cudaError_t e = cudaMalloc(&p, bytes > 0 ? (size_t)bytes : 16);
+  size_t want = bytes > 0 ? (size_t)bytes : 16;
+  cudaError_t e = cudaMallocFromPoolAsync(&p, want, ctx->pool, ctx->stream);
+  if (e != cudaSuccess) {                    // give cached blocks back to the driver and try once more
+    cudaGetLastError();
+    cudaStreamSynchronize(ctx->stream);
+    cudaMemPoolTrimTo(ctx->pool, 0);
+    e = cudaMallocFromPoolAsync(&p, want, ctx->pool, ctx->stream);
+  }
   if (e != cudaSuccess) {
     cudaGetLastError();
-    return fail(ctx, QSB_E_OOM, "cudaMalloc(%lld bytes): %s", (long long)bytes, cudaGetErrorString(e));
+    return fail(ctx, QSB_E_OOM, "cudaMallocAsync(%lld bytes): %s", (long long)bytes, cudaGetErrorString(e));
   }
   *out = new qsb_buffer{ctx, p, bytes, true};
+  return QSB_OK;
+}
+
+int qsb_ctx_trim(qsb_ctx* ctx) {
+  if (!ctx) return fail(nullptr, QSB_E_INVAL, "ctx is NULL");
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  CU(ctx, cudaMemPoolTrimTo(ctx->pool, 0));
   return QSB_OK;
 }
 
@@ -212,8 +243,7 @@ int qsb_buffer_free(qsb_buffer* buf) {
   if (!buf) return QSB_OK;
   if (buf->owned) {
     cudaSetDevice(buf->ctx->device);
-    cudaStreamSynchronize(buf->ctx->stream);
-    cudaFree(buf->ptr);
+    cudaFreeAsync(buf->ptr, buf->ctx->stream);      // ordered after every kernel that used it on the ctx stream
   }
   delete buf;
   return QSB_OK;
@@ -235,6 +265,50 @@ int qsb_buffer_upload(qsb_buffer* buf, int64_t offset, const void* host, int64_t
   CU(ctx, cudaSetDevice(ctx->device));
   CU(ctx, cudaMemcpyAsync((char*)buf->ptr + offset, host, (size_t)bytes, cudaMemcpyHostToDevice, ctx->stream));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return QSB_OK;
+}
+
+int qsb_buffer_upload_async(qsb_buffer* buf, int64_t offset, const void* host, int64_t bytes) {
+  int rc = check_range(buf, offset, bytes, "qsb_buffer_upload_async");
+  if (rc) return rc;
+  if (!host && bytes) return fail(buf->ctx, QSB_E_INVAL, "qsb_buffer_upload_async: host is NULL");
+  qsb_ctx* ctx = buf->ctx;
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaMemcpyAsync((char*)buf->ptr + offset, host, (size_t)bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return QSB_OK;
+}
+
+struct qsb_event {
+  qsb_ctx* ctx;
+  cudaEvent_t ev;
+};
+
+int qsb_event_create(qsb_ctx* ctx, qsb_event** out) {
+  if (!ctx || !out) return fail(ctx, QSB_E_INVAL, "qsb_event_create: bad argument");
+  CU(ctx, cudaSetDevice(ctx->device));
+  cudaEvent_t e;
+  CU(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  *out = new qsb_event{ctx, e};
+  return QSB_OK;
+}
+
+int qsb_event_record(qsb_event* ev) {
+  if (!ev) return fail(nullptr, QSB_E_INVAL, "event is NULL");
+  CU(ev->ctx, cudaSetDevice(ev->ctx->device));
+  CU(ev->ctx, cudaEventRecord(ev->ev, ev->ctx->stream));
+  return QSB_OK;
+}
+
+int qsb_event_wait(qsb_event* ev) {
+  if (!ev) return fail(nullptr, QSB_E_INVAL, "event is NULL");
+  CU(ev->ctx, cudaEventSynchronize(ev->ev));
+  return QSB_OK;
+}
+
+int qsb_event_free(qsb_event* ev) {
+  if (!ev) return QSB_OK;
+  cudaEventDestroy(ev->ev);
+  delete ev;
   return QSB_OK;
 }
 

@@ -22,7 +22,8 @@ RUN_LOAD, RUN_STORE, RUN_NORMALIZE, RUN_ASYNC, RUN_ACCUM_PROBS, RUN_LOAD_BROADCA
 
 SYMBOLS = [
     "qsb_version", "qsb_device_count", "qsb_ctx_create", "qsb_ctx_destroy", "qsb_ctx_set_stream",
-    "qsb_ctx_sync", "qsb_ctx_set_precision", "qsb_last_error", "qsb_ctx_info", "qsb_timer_start", "qsb_timer_stop",
+    "qsb_ctx_sync", "qsb_ctx_set_precision", "qsb_ctx_trim", "qsb_buffer_upload_async",
+    "qsb_event_create", "qsb_event_record", "qsb_event_wait", "qsb_event_free", "qsb_last_error", "qsb_ctx_info", "qsb_timer_start", "qsb_timer_stop",
     "qsb_launch_count", "qsb_buffer_alloc", "qsb_buffer_wrap", "qsb_buffer_free", "qsb_buffer_upload",
     "qsb_buffer_download", "qsb_buffer_zero", "qsb_buffer_copy", "qsb_buffer_ptr", "qsb_buffer_bytes",
     "qsb_host_alloc", "qsb_host_free", "qsb_program_create", "qsb_program_free", "qsb_run",
@@ -71,6 +72,12 @@ def load_library():
             "qsb_ctx_set_stream": (C.c_int, [vp, vp]),
             "qsb_ctx_sync": (C.c_int, [vp]),
             "qsb_ctx_set_precision": (C.c_int, [vp, C.c_int]),
+            "qsb_ctx_trim": (C.c_int, [vp]),
+            "qsb_buffer_upload_async": (C.c_int, [vp, i64, vp, i64]),
+            "qsb_event_create": (C.c_int, [vp, P(vp)]),
+            "qsb_event_record": (C.c_int, [vp]),
+            "qsb_event_wait": (C.c_int, [vp]),
+            "qsb_event_free": (C.c_int, [vp]),
             "qsb_last_error": (C.c_char_p, [vp]),
             "qsb_ctx_info": (C.c_int, [vp, P(i32), P(i32), P(i32), P(i64)]),
             "qsb_timer_start": (C.c_int, [vp]),
@@ -136,6 +143,12 @@ class Buffer:
         _check(self.ctx.lib.qsb_buffer_upload(self.handle, offset, _hostptr(arr), arr.nbytes), self.ctx.handle)
         return self
 
+    def upload_async(self, arr, offset=0):
+        """No host wait; `arr` (pinned, contiguous) must stay untouched until an Event recorded afterwards is waited."""
+        assert arr.flags.c_contiguous
+        _check(self.ctx.lib.qsb_buffer_upload_async(self.handle, offset, _hostptr(arr), arr.nbytes), self.ctx.handle)
+        return self
+
     def download(self, dtype, shape, offset=0, out=None):
         if out is None:
             out = np.empty(shape, dtype=dtype)
@@ -163,6 +176,31 @@ class Buffer:
     def __del__(self):
         try:
             self.free()
+        except Exception:
+            pass
+
+
+class Event:
+    """Marker on the context's stream (qsb_event_*)."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        h = C.c_void_p()
+        _check(ctx.lib.qsb_event_create(ctx.handle, C.byref(h)), ctx.handle)
+        self.handle = h
+
+    def record(self):
+        _check(self.ctx.lib.qsb_event_record(self.handle), self.ctx.handle)
+        return self
+
+    def wait(self):
+        _check(self.ctx.lib.qsb_event_wait(self.handle), self.ctx.handle)
+
+    def __del__(self):
+        try:
+            if self.handle is not None:
+                self.ctx.lib.qsb_event_free(self.handle)
+                self.handle = None
         except Exception:
             pass
 
@@ -205,6 +243,7 @@ class Context:
         _check(self.lib.qsb_ctx_info(h, C.byref(sm), C.byref(ma), C.byref(mi), C.byref(mem)), h)
         self.sm_count, self.cc, self.total_mem = sm.value, (ma.value, mi.value), mem.value
         self.precision = "c128"
+        self._staging = {}
 
     # -- precision -------------------------------------------------------------------------
     def set_precision(self, precision):
@@ -237,6 +276,23 @@ class Context:
     def to_device(self, arr):
         arr = np.ascontiguousarray(arr)
         return self.alloc(max(arr.nbytes, 16)).upload(arr)
+
+    def trim(self):
+        """Give the cached device blocks of this context's pool back to the driver."""
+        _check(self.lib.qsb_ctx_trim(self.handle), self.handle)
+
+    def event(self):
+        return Event(self)
+
+    def staging(self, tag, shape, dtype=np.float64):
+        """Cached pinned host array for `tag`, grown on demand (callers fill it, upload_async it, and wait for an
+        event before refilling)."""
+        need = int(np.prod(shape))
+        cur = self._staging.get(tag)
+        if cur is None or cur.size < need or cur.dtype != np.dtype(dtype):
+            cur = self.pinned((max(need, 1),), dtype)
+            self._staging[tag] = cur
+        return cur[:need].reshape(shape)
 
     def pinned(self, shape, dtype):
         """NumPy array backed by pinned host memory (kept alive by the array's base object)."""

@@ -22,6 +22,7 @@ from .gates import GateType
 from .measurement import MeasurementEngine, MeasurementBasis
 from .state_vector import StateVector
 
+_PIPE_SHOTS = (64, 2048)        # first / largest pipelined slice of run_with_noise, in trajectories
 _CHUNK_BYTES = 8 << 30          # state bytes resident per launch when batching shots / trials
 
 
@@ -160,11 +161,31 @@ class Simulator:
         counts: dict = {}
         chunk = max(1, min(shots, _CHUNK_BYTES // (16 * dim)))
         c = runtime.ctx()
+        # Draws are generated straight into pinned staging memory in slices of _PIPE_SHOTS trajectories and
+        # uploaded without a host wait, so the generator works on slice k+1 while the GPU runs slice k.  The
+        # noise generator still hands out d doubles per shot in shot order, never reseeded (noise.py:253-259).
+        # Slice sizes grow 8x (draws are ~20x cheaper than trajectories), so few launches pay a ragged last wave.
+        sub = max(1, min(chunk, _PIPE_SHOTS[1]))
+        stage = [c.staging(("run_with_noise", k), (sub, max(d, 1))) for k in range(2)]
+        dev_u = [c.alloc(sub * max(d, 1) * 8) for _ in range(2)]
+        done = [None, None]
+        states = c.alloc(chunk * dim * 16)
+        basis = self._basis(circuit)
         for lo in range(0, shots, chunk):
             cnt = min(chunk, shots - lo)
-            # noise generator: d doubles per shot, never reseeded; measurement generator: one per shot
-            uniforms = self._noise_model._rng.random(cnt * d).reshape(cnt, d) if d else None
-            _, states = self._trajectory_batch(circuit, uniforms, cnt)
+            s0, m, j = 0, min(_PIPE_SHOTS[0], sub), 0
+            while s0 < cnt:
+                k, m = j & 1, min(m, cnt - s0)
+                kw = {}
+                if d:
+                    if done[k] is not None:
+                        done[k].wait()                       # slice j-2 has left this staging buffer
+                    self._noise_model._rng.random(out=stage[k][:m].reshape(-1))
+                    dev_u[k].upload_async(stage[k][:m])
+                    done[k] = (done[k] or c.event()).record()
+                    kw.update(uniforms=dev_u[k], uniforms_stride=d)
+                c.run(dp, m, states=states, first=s0, default_basis=basis, async_=True, **kw)
+                s0, m, j = s0 + m, min(8 * m, sub), j + 1
             u = c.to_device(rng.random(cnt))
             out = c.alloc(cnt * 8)
             c.sample_index(n, states, 0, cnt, u, out)
