@@ -624,7 +624,8 @@ QSB_PASS void qsb_do_remap(Env& env, int m, const qsb_desc* d) {
 #pragma unroll
     for (int e = 0; e < QSB_REMAP_REGS; ++e) {
       int g = base + e * env.W + env.wid;
-      if (g < cnt) val[e] = tile[QSB_SLOT(qsb_ins0(g, lb) | ((1 - mybit) << lb))];
+      g = g < cnt ? g : cnt - 1;
+      val[e] = tile[QSB_SLOT(qsb_ins0(g, lb) | ((1 - mybit) << lb))];
     }
     env.cluster_sync_w();
 #pragma unroll
@@ -638,17 +639,24 @@ QSB_PASS void qsb_do_remap(Env& env, int m, const qsb_desc* d) {
   // Round r pulls the partner's groups g and then overwrites OUR groups g (the ones the partner pulls
   // in the same round), so one cluster barrier between the two halves of a round is enough.
   for (int base = 0; base < cnt; base += QSB_REMAP_REGS * env.W) {
+    const unsigned long long q0 = env.prof_on() ? env.clock() : 0;
 #pragma unroll
     for (int e = 0; e < QSB_REMAP_REGS; ++e) {
+      // unconditional (index clamped): a conditionally written val[] is demoted to local memory and the
+      // remote loads then run one at a time
       int g = base + e * env.W + env.wid;
-      if (g < cnt) val[e] = peer[QSB_SLOT(qsb_ins0(g, lb) | (mybit << lb))];
+      g = g < cnt ? g : cnt - 1;
+      val[e] = peer[QSB_SLOT(qsb_ins0(g, lb) | (mybit << lb))];
     }
+    const unsigned long long q1 = env.prof_on() ? env.clock() : 0;
     env.cluster_sync_w();
+    const unsigned long long q2 = env.prof_on() ? env.clock() : 0;
 #pragma unroll
     for (int e = 0; e < QSB_REMAP_REGS; ++e) {
       int g = base + e * env.W + env.wid;
       if (g < cnt) tile[QSB_SLOT(qsb_ins0(g, lb) | ((1 - mybit) << lb))] = val[e];
     }
+    if (env.prof_on()) { env.prof_add(121, q1 - q0); env.prof_add(122, q2 - q1); env.prof_add(123, env.clock() - q2); env.prof_add(124 + (lb < 3 ? lb : 3), 1); }
   }
 #endif
 }
@@ -673,7 +681,8 @@ QSB_PASS void qsb_do_gflush(Env& env, int m, const qsb_desc* d) {
 #pragma unroll
     for (int e = 0; e < QSB_REMAP_REGS; ++e) {
       int i = base + e * env.W + env.wid;
-      if (i < cnt) val[e] = qsb_fma(po, peer[i], qsb_mul(pm, tile[i]));      // same slot on both sides
+      i = i < cnt ? i : cnt - 1;                                            // clamped, see qsb_do_remap
+      val[e] = qsb_fma(po, peer[i], qsb_mul(pm, tile[i]));                  // same slot on both sides
     }
     env.cluster_sync_w();
 #pragma unroll

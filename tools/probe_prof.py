@@ -39,6 +39,9 @@ def prof(label, prog, T):
         if p0[64 + key]:
             print(f"      sweep k={key // 8} gate={G[key % 8]:6s} n={p0[64 + key]:7.1f}  {p0[32 + key] / p0[64 + key]:8.0f} / desc")
     print(f"      remap: first cluster barrier {p0[120] / max(p0[12], 1):8.0f} / remap")
+    nr = max(p0[12], 1)
+    print(f"      remap: pull issue {p0[121] / nr:8.0f}  second barrier {p0[122] / nr:8.0f}  write {p0[123] / nr:8.0f};  lb=0/1/2/3+: "
+          f"{p0[124]:.0f} {p0[125]:.0f} {p0[126]:.0f} {p0[127]:.0f}")
     print("      per-warp busy:", " ".join(f"{p0[104 + w]:9.0f}" for w in range(8)))
     print("      per-warp wait:", " ".join(f"{p0[112 + w]:9.0f}" for w in range(8)))
     for nd in range(4):
@@ -48,4 +51,4 @@ def prof(label, prog, T):
 
 noise = config3_noise()
 prof("16q noisy", prog_for(16, 64, noise), 150)
-prof("16q noiseless", prog_for(16, 64, None), 150)
+
