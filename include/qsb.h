@@ -95,7 +95,8 @@ enum {
   QSB_OP_KRAUS_PAULI = 30,  /* cdata: c0 c1 c2 (cdf of choice()), then 4 Pauli codes 0..3 as doubles */
   QSB_OP_KRAUS_AD = 31,     /* cdata: gamma, sqrt(1-gamma), sqrt(gamma)                   */
   QSB_OP_KRAUS_GEN = 32,    /* cdata: nK, then per K: 8 doubles K, 4 doubles K^dag K (e00,e11,re e01,im e01) */
-  /* cluster data movement: swap rank bit b0 (0..log2 C-1) with local slot bit b1 */
+  /* cluster data movement: swap rank bit b0 (0..log2 C-1) with local slot bit b1; b2 = number of FURTHER
+   * (rank bit, local bit) pairs exchanged in the same pass, packed in aux as g1 | l1 << 8 | g2 << 16 | l2 << 24 */
   QSB_OP_REMAP = 40,
   /* copy the (normalised) state to snapshot slot b0 with bit permutation idata[aux..aux+n) */
   QSB_OP_SNAPSHOT = 50

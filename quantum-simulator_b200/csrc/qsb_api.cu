@@ -420,8 +420,20 @@ int qsb_program_create(qsb_ctx* ctx, int32_t n, int32_t m, const qsb_op* ops, in
       case QSB_OP_KRAUS_AD: nb = 1; need = 3; break;
       case QSB_OP_KRAUS_GEN: nb = 1; need = 1; break;
       case QSB_OP_REMAP:
-        if (o.b0 < 0 || o.b0 >= gbits || o.b1 < 0 || o.b1 >= m)
+        if (o.b0 < 0 || o.b0 >= gbits || o.b1 < 0 || o.b1 >= m || o.b2 < 0 || o.b2 > 2)
           return fail(ctx, QSB_E_INVAL, "op %lld: remap bits (%d, %d) invalid", (long long)i, o.b0, o.b1);
+        {
+          // further pairs of the same exchange: g1 | l1 << 8 | g2 << 16 | l2 << 24; all rank bits and all local
+          // bits of one op must be distinct
+          int gs[3] = {o.b0, o.aux & 255, (o.aux >> 16) & 255}, ls[3] = {o.b1, (o.aux >> 8) & 255, (o.aux >> 24) & 255};
+          for (int j = 1; j <= o.b2; ++j) {
+            if (gs[j] >= gbits || ls[j] >= m)
+              return fail(ctx, QSB_E_INVAL, "op %lld: remap pair %d (%d, %d) invalid", (long long)i, j, gs[j], ls[j]);
+            for (int q = 0; q < j; ++q)
+              if (gs[q] == gs[j] || ls[q] == ls[j])
+                return fail(ctx, QSB_E_INVAL, "op %lld: remap pairs %d and %d overlap", (long long)i, q, j);
+          }
+        }
         break;
       case QSB_OP_SNAPSHOT:
         if (o.b0 < 0 || o.b0 >= n_snapshots || o.aux < 0 || o.aux + n > n_idata || !is_perm(idata + o.aux, n))
@@ -651,7 +663,7 @@ int qsb_run(qsb_program* p, const qsb_run_args* r) {
   int workers = 1 << (p->m > 4 ? p->m - 4 : 1);       // 16 amplitudes per worker per pass
   if (workers < 32) workers = 32;
   if (workers > QSB_MAX_WORKERS) workers = QSB_MAX_WORKERS;
-  const int threads = workers + QSB_CTL_THREADS;
+  const int threads = workers + QSB_CTL_THREADS + QSB_DEC_THREADS;
   const bool c64m = p->amp_bytes == 8;
   const size_t smem = ((size_t)p->amp_bytes << p->m) + QSB_SMEM_EXTRA;
   int grid = 0;

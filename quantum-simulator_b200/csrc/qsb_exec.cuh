@@ -35,6 +35,7 @@
 
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "qsb.h"
 
@@ -56,7 +57,9 @@ struct alignas(8) c64 { float x, y; };
 #if defined(__CUDA_ARCH__)
 #define QSB_CTZ(x) (__ffs((int)(x)) - 1)
 #define QSB_MSB(x) (31 - __clz((int)(x)))
+#define QSB_POPC(x) __popc((unsigned)(x))
 #else
+#define QSB_POPC(x) __builtin_popcount((unsigned)(x))
 #define QSB_CTZ(x) __builtin_ctz((unsigned)(x))
 #define QSB_MSB(x) (31 - __builtin_clz((unsigned)(x)))
 #endif
@@ -134,7 +137,17 @@ struct alignas(16) qsb_dec {
   int32_t b;               // slot bit
   int32_t ucls;            // structure class of U
   int32_t next;            // MUL: index (in the chunk) of the next MUL op on the same slot, or QSB_CHUNK
-  c128 U[4];
+  c128 U[4];               // MUL: the matrix.  Multi-qubit gate ops (SLOW): U[0] holds the sweep's group order
+};                         //   (bits of pos in .x, hmask in .y), worked out during the lane-parallel decode
+
+// one staged chunk of the op list: filled by the decode warp (records, uniforms, decoded form, per-slot lists,
+// SLOW-op mask), consumed by the control warp; two of them so that decoding runs one chunk ahead
+struct alignas(16) qsb_chunk {
+  qsb_op ops[QSB_CHUNK];       // staged op records ...
+  double u[QSB_CHUNK];         // ... the uniform each Kraus op consumes
+  qsb_dec dec[QSB_CHUNK];      // ... and their decoded form
+  int32_t head[32];            // first MUL op of each slot in the chunk (QSB_CHUNK = none)
+  uint32_t slowmask[QSB_CHUNK / 32];   // bit i: op i needs the SLOW path
 };
 
 // per-CTA control block that lives behind the tile in shared memory
@@ -142,15 +155,13 @@ struct qsb_ctl {
   uint32_t perm[1024];         // bit-permutation byte tables (workers: INIT / STORE)
   c128 pend[32][4];            // pending 2x2 per slot bit (row-major); written by the control warp only
   qsb_desc ring[QSB_RING];
-  qsb_op ops[QSB_CHUNK];       // staged op records ...
-  double u[QSB_CHUNK];         // ... the uniform each Kraus op consumes
-  qsb_dec dec[QSB_CHUNK];      // ... and their decoded form (control warp, lane-parallel decode)
+  qsb_chunk chunk[2];
   double wpart[32 * 4];        // per-warp partial sums (workers)
   double red[2][4];            // this CTA's contribution to a cluster reduction, double-buffered
   double red_total[4];         // cluster-wide result handed to the control warp (RDM1)
-  int32_t head[32];            // first MUL op of each slot in the staged chunk (QSB_CHUNK = none)
   double wtab[256];            // weighted marginal: products of diagonal-pending weights over index bits 0..6 | 7..13
   unsigned long long xbar;     // mbarrier of the workers-only cluster barrier (device)
+  unsigned long long dbar[4];  // decode warp <-> control warp: chunk[b] full (b), chunk[b] empty (2 + b) (device)
 };
 
 // ---- small helpers ---------------------------------------------------------------
@@ -161,6 +172,14 @@ QSB_HD int qsb_slot(int i) { return i ^ ((i >> 3) & 7); }
 QSB_HD int qsb_ins0(int g, int b) { return ((g >> b) << (b + 1)) | (g & ((1 << b) - 1)); }
 
 QSB_HD c128 qsb_c(double x, double y) { c128 r; r.x = x; r.y = y; return r; }
+// bit casts (a 64-bit group order rides in a double field of the decode record)
+#if defined(__CUDA_ARCH__)
+QSB_HD double qsb_u64_as_double(uint64_t v) { return __longlong_as_double((long long)v); }
+QSB_HD uint64_t qsb_double_as_u64(double v) { return (uint64_t)__double_as_longlong(v); }
+#else
+QSB_HD double qsb_u64_as_double(uint64_t v) { double d; memcpy(&d, &v, 8); return d; }
+QSB_HD uint64_t qsb_double_as_u64(double v) { uint64_t u; memcpy(&u, &v, 8); return u; }
+#endif
 QSB_HD c128 qsb_mul(c128 a, c128 b) { return qsb_c(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 QSB_HD c128 qsb_fma(c128 a, c128 b, c128 c) {   // a*b + c
   return qsb_c(fma(a.x, b.x, fma(-a.y, b.y, c.x)), fma(a.x, b.y, fma(a.y, b.x, c.y)));
@@ -266,6 +285,39 @@ QSB_HD uint64_t qsb_group_order(int m, uint32_t used, int wbits, int nfree, int 
   }
   *hmask = hm;
   return pos;
+}
+// the same result computed by the lanes of the control warp together: the (at most `sw`) conflict-avoiding
+// positions serially, then index bit q finds its own place among the remaining ones with a population count and
+// the lanes OR their nibbles together
+template <class Env>
+QSB_CTL uint64_t qsb_group_order_lanes(Env& env, int m, uint32_t used, int wbits, int nfree, int sw, int* hmask) {
+  const uint32_t all = m >= 32 ? 0xffffffffu : ((1u << m) - 1u);
+  uint32_t plo = 0, phi = 0, hm = 0;
+  int cnt = 0;
+  for (int j = 0; j < sw; ++j) {
+    int q = -1;
+    if (j < m && !((used >> j) & 1u)) q = j;
+    else if (j + sw < m && !((used >> (j + sw)) & 1u)) q = j + sw;
+    if (q >= 0) {
+      if (env.lead) {
+        if (cnt < 8) plo |= (uint32_t)q << (4 * cnt); else phi |= (uint32_t)q << (4 * (cnt - 8));
+        if (cnt >= wbits && cnt < nfree) hm |= 1u << q;
+      }
+      ++cnt;
+      used |= 1u << q;
+    }
+  }
+  const uint32_t rest = ~used & all;
+  for (int q = env.clane; q < 32; q += env.CL) {
+    if (!((rest >> q) & 1u)) continue;
+    const int c = cnt + QSB_POPC(rest & ((1u << q) - 1u));
+    if (c >= 16) continue;
+    if (c < 8) plo |= (uint32_t)q << (4 * c); else phi |= (uint32_t)q << (4 * (c - 8));
+    if (c >= wbits && c < nfree) hm |= 1u << q;
+  }
+  plo = env.or_reduce(plo); phi = env.or_reduce(phi); hm = env.or_reduce(hm);
+  *hmask = (int)hm;
+  return ((uint64_t)phi << 32) | plo;
 }
 // deposit the low `nbits` bits of g onto the positions packed in `pos`
 QSB_HD int qsb_deposit(int g, uint64_t pos, int nbits) {
@@ -601,68 +653,64 @@ QSB_PASS void qsb_do_store(Env& env, const qsb_exec_args& a, const qsb_desc* d, 
   }
 }
 
-// swap cluster-rank bit gb with local slot bit lb: pull the partner's half, then overwrite ours.
+// Exchange k <= 3 cluster-rank bits g_j with local slot bits l_j in ONE pass (d->b[j] = g_j, d->cls[j] = l_j, d->k = k).
+// With r_j = bit g_j of my rank and x_j = bit l_j of a local index, new[base | x] = old of CTA (rank with g_j := x_j)
+// at [base | r]: the 2^-k of the tile with x == r stays, the rest is pulled from the 2^k - 1 peers, so k bits cost
+// (1 - 2^-k) tile volumes instead of k/2.  Element q = (xv - 1) * 2^(m-k) + base number, xv = x ^ r != 0; every CTA
+// enumerates q the same way, so the positions a CTA overwrites in a round are the ones its peers pulled in that
+// round and one cluster barrier between the two halves of a round is enough.
 // Pending matrices travel with their qubits (control-warp bookkeeping), so nothing is flushed here.
 template <class Env>
 QSB_PASS void qsb_do_remap(Env& env, int m, const qsb_desc* d) {
   typedef typename Env::amp A;
   A* tile = env.tile();
-  const int gb = d->b[0], lb = d->b[1];
-  const int mybit = (env.rank >> gb) & 1;
-  const A* peer = env.peer_tile(env.rank ^ (1 << gb));
+  const int k = d->k;
+  int gb[3], lb[3], sl[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) { gb[j] = j < k ? d->b[j] : 0; lb[j] = j < k ? d->cls[j] : 0; sl[j] = lb[j]; }
+  // ascending local bits for the zero insertion
+  if (k > 1 && sl[0] > sl[1]) { int t = sl[0]; sl[0] = sl[1]; sl[1] = t; }
+  if (k > 2 && sl[1] > sl[2]) { int t = sl[1]; sl[1] = sl[2]; sl[2] = t; }
+  if (k > 2 && sl[0] > sl[1]) { int t = sl[0]; sl[0] = sl[1]; sl[1] = t; }
+  int rmask = 0;                                  // my rank bits laid onto the local bits
+#pragma unroll
+  for (int j = 0; j < 3; ++j) if (j < k) rmask |= ((env.rank >> gb[j]) & 1) << lb[j];
   A val[QSB_REMAP_REGS];
-  const int cnt = 1 << (m - 1);
+  const int sh = m - k, cnt = 1 << sh;
+  const int total = ((1 << k) - 1) << sh;
   const unsigned long long pt0 = env.prof_on() ? env.clock() : 0;
   env.cluster_sync_w();                       // every CTA finished the sweeps before the exchange
   if (env.prof_on()) env.prof_add(120, env.clock() - pt0);
-#if QSB_REMAP_PUSH
-  // Push: read OUR outgoing half into registers (local), barrier (the partner has its outgoing half -- the
-  // positions we are about to overwrite -- in registers too), store into the PARTNER's tile (posted DSMEM
-  // stores instead of latency-bound DSMEM loads), barrier before anyone reads its tile again.
-  A* peer_w = const_cast<A*>(peer);
-  for (int base = 0; base < cnt; base += QSB_REMAP_REGS * env.W) {
-#pragma unroll
-    for (int e = 0; e < QSB_REMAP_REGS; ++e) {
-      int g = base + e * env.W + env.wid;
-      g = g < cnt ? g : cnt - 1;
-      val[e] = tile[QSB_SLOT(qsb_ins0(g, lb) | ((1 - mybit) << lb))];
-    }
-    env.cluster_sync_w();
-#pragma unroll
-    for (int e = 0; e < QSB_REMAP_REGS; ++e) {
-      int g = base + e * env.W + env.wid;
-      if (g < cnt) peer_w[QSB_SLOT(qsb_ins0(g, lb) | (mybit << lb))] = val[e];
-    }
-  }
-  env.cluster_sync_w();
-#else
-  // Round r pulls the partner's groups g and then overwrites OUR groups g (the ones the partner pulls
-  // in the same round), so one cluster barrier between the two halves of a round is enough.
-  for (int base = 0; base < cnt; base += QSB_REMAP_REGS * env.W) {
+  for (int base = 0; base < total; base += QSB_REMAP_REGS * env.W) {
     const unsigned long long q0 = env.prof_on() ? env.clock() : 0;
+    int mine[QSB_REMAP_REGS];
 #pragma unroll
     for (int e = 0; e < QSB_REMAP_REGS; ++e) {
       // unconditional (index clamped): a conditionally written val[] is demoted to local memory and the
       // remote loads then run one at a time
-      int g = base + e * env.W + env.wid;
-      g = g < cnt ? g : cnt - 1;
-      val[e] = peer[QSB_SLOT(qsb_ins0(g, lb) | (mybit << lb))];
+      int q = base + e * env.W + env.wid;
+      q = q < total ? q : total - 1;
+      const int xv = 1 + (q >> sh);
+      int bs = q & (cnt - 1);
+      bs = qsb_ins0(bs, sl[0]);
+      if (k > 1) bs = qsb_ins0(bs, sl[1]);
+      if (k > 2) bs = qsb_ins0(bs, sl[2]);
+      int dr = 0, dl = 0;                        // xv spread onto the rank bits / the local bits
+#pragma unroll
+      for (int j = 0; j < 3; ++j) if (j < k) { dr |= ((xv >> j) & 1) << gb[j]; dl |= ((xv >> j) & 1) << lb[j]; }
+      mine[e] = bs | (rmask ^ dl);
+      val[e] = env.peer_tile(env.rank ^ dr)[QSB_SLOT(bs | rmask)];
     }
     const unsigned long long q1 = env.prof_on() ? env.clock() : 0;
     env.cluster_sync_w();
     const unsigned long long q2 = env.prof_on() ? env.clock() : 0;
 #pragma unroll
     for (int e = 0; e < QSB_REMAP_REGS; ++e) {
-      int g = base + e * env.W + env.wid;
-      if (g < cnt) tile[QSB_SLOT(qsb_ins0(g, lb) | ((1 - mybit) << lb))] = val[e];
+      const int q = base + e * env.W + env.wid;
+      if (q < total) tile[QSB_SLOT(mine[e])] = val[e];
     }
-    if (env.prof_on()) { env.prof_add(121, q1 - q0); env.prof_add(122, q2 - q1); env.prof_add(123, env.clock() - q2); env.prof_add(124 + (lb < 3 ? lb : 3), 1); }
+    if (env.prof_on()) { env.prof_add(121, q1 - q0); env.prof_add(122, q2 - q1); env.prof_add(123, env.clock() - q2); env.prof_add(124 + k, 1); }
   }
-#endif
-}
-QSB_HD int qsb_remap_syncs(int m, int W) {
-  const int cnt = 1 << (m - 1), per = QSB_REMAP_REGS * W;
-  return 1 + (cnt + per - 1) / per;
 }
 
 // apply the pending 2x2 of cluster-rank bit gb: mine' = P[my][my] mine + P[my][other] partner
@@ -691,10 +739,6 @@ QSB_PASS void qsb_do_gflush(Env& env, int m, const qsb_desc* d) {
       if (i < cnt) tile[i] = val[e];
     }
   }
-}
-QSB_HD int qsb_gflush_syncs(int m, int W) {
-  const int cnt = 1 << m, per = QSB_REMAP_REGS * W;
-  return 1 + (cnt + per - 1) / per;
 }
 
 // worker main loop: consume descriptors until EXIT
@@ -781,6 +825,7 @@ QSB_HD void qsb_worker_loop(Env& env, const qsb_exec_args& a) {
 // much arithmetic a pending matrix needs.
 struct qsb_cstate {
   uint32_t seq;                    // descriptors published so far
+  uint32_t gchunk;                 // chunks consumed (control) / produced (decode warp) so far, over all units
   uint64_t clsword;                // 2-bit structure class per slot bit
   int parity;
   // per-unit constants
@@ -790,6 +835,7 @@ struct qsb_cstate {
   unsigned long long ring_wait;    // cycles blocked on a full ring
   unsigned long long t_decode, t_fold, t_slow, n_slow;   // control-warp cycles per phase (profiling only)
   unsigned long long t_emit_body, t_emit_pub, n_emit;
+  unsigned long long t_e[4];
 };
 
 // class word: two bit planes, bit b of the low word = class bit 0 of slot b, bit b of the high word = class bit 1
@@ -830,27 +876,35 @@ QSB_HD void qsb_desc_end(Env& env, qsb_cstate& st) {
 // publish one sweep over `nb` local bits (bits[0] = MSB of the gate index) and reset their pending matrices.
 // The lanes of the control warp share the copies: entry e of bit k goes through lane 4k + e.
 template <class Env>
-QSB_CTL void qsb_emit_sweep(Env& env, qsb_cstate& st, int m, int gate, int nb, int b0, int b1, int b2, const c128* mat_src) {
+QSB_CTL void qsb_emit_sweep(Env& env, qsb_cstate& st, int m, int gate, int nb, int b0, int b1, int b2, const c128* mat_src,
+                            const qsb_dec* order = nullptr) {
   qsb_desc* d = qsb_desc_begin(env, st);
   qsb_ctl* ctl = env.ctl();
   const unsigned long long pe0 = st.prof ? env.clock() : 0;
   const uint64_t w = st.clsword;
   env.sync_control();                          // the fold's pending matrices are visible to every lane
+  const unsigned long long pq0 = st.prof ? env.clock() : 0;
   for (int e = env.clane; e < 4 * nb; e += env.CL) {
     const int k = e >> 2, j = e & 3;
     const int b = k == 0 ? b0 : (k == 1 ? b1 : b2);
     d->P[k][j] = ctl->pend[b][j];
     ctl->pend[b][j] = qsb_c((j == 0 || j == 3) ? 1.0 : 0.0, 0.0);
   }
+  const unsigned long long pq1 = st.prof ? env.clock() : 0;
+  uint32_t used = 1u << b0;
+  if (nb > 1) used |= 1u << b1;
+  if (nb > 2) used |= 1u << b2;
+  int hm;
+  uint64_t pos;
+  if (order) { pos = qsb_double_as_u64(order->U[0].x); hm = (int)order->U[0].y; }
+  else pos = qsb_group_order_lanes(env, m, used, env.wbits, m - nb, (int)qsb_amp<typename Env::amp>::SW, &hm);
+  const unsigned long long pq2 = st.prof ? env.clock() : 0;
+  if (st.prof) { st.t_e[0] += pq0 - pe0; st.t_e[1] += pq1 - pq0; st.t_e[2] += pq2 - pq1; }
   if (env.lead) {
     d->kind = QSB_D_SWEEP; d->gate = gate; d->k = nb; d->flags = 0;
     d->b[0] = b0; d->b[1] = b1; d->b[2] = b2;
     d->cls[0] = qsb_cls_of(w, b0); d->cls[1] = nb > 1 ? qsb_cls_of(w, b1) : 0; d->cls[2] = nb > 2 ? qsb_cls_of(w, b2) : 0;
-    uint32_t used = 1u << b0;
-    if (nb > 1) used |= 1u << b1;
-    if (nb > 2) used |= 1u << b2;
-    int hm;
-    d->pos = qsb_group_order(m, used, env.wbits, m - nb, (int)qsb_amp<typename Env::amp>::SW, &hm);
+    d->pos = pos;
     d->hmask = hm;
   }
   if (mat_src) {
@@ -997,6 +1051,21 @@ QSB_HD void qsb_decode_op(Env& env, const qsb_exec_args& a, const qsb_cstate& st
       } else type = QSB_DEC_SLOW;
       break;
     }
+    case QSB_OP_CX: case QSB_OP_CZ: case QSB_OP_SWAP: case QSB_OP_U2:
+    case QSB_OP_CCX: case QSB_OP_CSWAP: case QSB_OP_U3Q: {
+      // group order of the sweep (depends on the target bits only): ~100 dependent instructions that the serial part
+      // of the control warp would otherwise run once per sweep
+      type = QSB_DEC_SLOW;
+      const int nb = (op.kind == QSB_OP_CCX || op.kind == QSB_OP_CSWAP || op.kind == QSB_OP_U3Q) ? 3 : 2;
+      uint32_t used = (1u << op.b0) | (1u << op.b1);
+      if (nb > 2) used |= 1u << op.b2;
+      int hm;
+      const uint64_t pos = qsb_group_order(a.m, used, env.wbits, a.m - nb, (int)qsb_amp<typename Env::amp>::SW, &hm);
+      U[0].x = qsb_u64_as_double(pos);
+      U[0].y = (double)hm;
+      d->U[0] = U[0];
+      break;
+    }
     default: type = QSB_DEC_SLOW; break;
   }
   d->type = type; d->b = op.b0; d->ucls = ucls;
@@ -1006,16 +1075,16 @@ QSB_HD void qsb_decode_op(Env& env, const qsb_exec_args& a, const qsb_cstate& st
 
 // ---- ops that need the descriptor ring or the state (whole control warp) --------------------------
 template <class Env>
-QSB_CTL void qsb_control_slow(Env& env, const qsb_exec_args& a, qsb_cstate& st, int i) {
+QSB_CTL void qsb_control_slow(Env& env, const qsb_exec_args& a, qsb_cstate& st, qsb_chunk* ck, int i) {
   qsb_ctl* ctl = env.ctl();
   const int m = a.m, n = a.n;
-  const qsb_op op = ctl->ops[i];
+  const qsb_op op = ck->ops[i];
   const uint32_t all_bits = n >= 32 ? 0xffffffffu : ((1u << n) - 1u);
   const int b = op.b0;
   switch (op.kind) {
     case QSB_OP_KRAUS_AD: {               // the draw fell in [1-g, 1): the branch depends on P(q=1)
       const double* cd = a.cdata + op.data;
-      const double u = ctl->u[i], gam = cd[0];
+      const double u = ck->u[i], gam = cd[0];
       double v[4];
       // only DENSE pending matrices have to be applied before the marginal is taken: diagonal ones (the K0's of
       // earlier draws, Rz / phase gates) just reweight |amplitude|^2 and ride along as weights
@@ -1036,7 +1105,7 @@ QSB_CTL void qsb_control_slow(Env& env, const qsb_exec_args& a, qsb_cstate& st, 
       break;
     }
     case QSB_OP_KRAUS_GEN: {              // target is a local bit (host compiler remaps it in)
-      const double u = ctl->u[i];
+      const double u = ck->u[i];
       const double* g = a.cdata + op.data;
       const int nk = (int)g[0];
       double v[4], p[8];
@@ -1060,24 +1129,34 @@ QSB_CTL void qsb_control_slow(Env& env, const qsb_exec_args& a, qsb_cstate& st, 
     case QSB_OP_CX: case QSB_OP_CZ: case QSB_OP_SWAP: case QSB_OP_U2: {
       const int g = op.kind == QSB_OP_CX ? QSB_G_CX : op.kind == QSB_OP_CZ ? QSB_G_CZ :
                     op.kind == QSB_OP_SWAP ? QSB_G_SWAP : QSB_G_DENSE;
-      qsb_emit_sweep(env, st, m, g, 2, op.b0, op.b1, 0, op.kind == QSB_OP_U2 ? (const c128*)(a.cdata + op.data) : (const c128*)nullptr);
+      qsb_emit_sweep(env, st, m, g, 2, op.b0, op.b1, 0, op.kind == QSB_OP_U2 ? (const c128*)(a.cdata + op.data) : (const c128*)nullptr,
+                     &ck->dec[i]);
       break;
     }
     case QSB_OP_CCX: case QSB_OP_CSWAP: case QSB_OP_U3Q: {
       const int g = op.kind == QSB_OP_CCX ? QSB_G_CCX : op.kind == QSB_OP_CSWAP ? QSB_G_CSWAP : QSB_G_DENSE;
-      qsb_emit_sweep(env, st, m, g, 3, op.b0, op.b1, op.b2, op.kind == QSB_OP_U3Q ? (const c128*)(a.cdata + op.data) : (const c128*)nullptr);
+      qsb_emit_sweep(env, st, m, g, 3, op.b0, op.b1, op.b2, op.kind == QSB_OP_U3Q ? (const c128*)(a.cdata + op.data) : (const c128*)nullptr,
+                     &ck->dec[i]);
       break;
     }
     case QSB_OP_REMAP: {
-      // swap cluster-rank bit b0 with local slot bit b1; the pending matrices move with their qubits
-      const int gb = op.b0, lb = op.b1;
+      // swap cluster-rank bit b0 with local slot bit b1 (and, in the same pass, the b2 further pairs packed in aux:
+      // g1 | l1 << 8 | g2 << 16 | l2 << 24); the pending matrices move with their qubits
+      const int k = 1 + op.b2;
+      int gbs[3] = {op.b0, op.aux & 255, (op.aux >> 16) & 255}, lbs[3] = {op.b1, (op.aux >> 8) & 255, (op.aux >> 24) & 255};
       qsb_desc* d = qsb_desc_begin(env, st);
-      if (env.lead) { d->kind = QSB_D_REMAP; d->k = 2; d->b[0] = gb; d->b[1] = lb; }
+      if (env.lead) {
+        d->kind = QSB_D_REMAP; d->k = k;
+        for (int j = 0; j < k; ++j) { d->b[j] = gbs[j]; d->cls[j] = lbs[j]; }
+      }
       qsb_desc_end(env, st);
-      const int ca = qsb_cls_of(st.clsword, lb), cb = qsb_cls_of(st.clsword, m + gb);
-      if (env.lead)
-        for (int e = 0; e < 4; ++e) { c128 x = ctl->pend[lb][e]; ctl->pend[lb][e] = ctl->pend[m + gb][e]; ctl->pend[m + gb][e] = x; }
-      st.clsword = qsb_cls_set(qsb_cls_set(st.clsword, lb, cb), m + gb, ca);
+      for (int j = 0; j < k; ++j) {
+        const int gb = gbs[j], lb = lbs[j];
+        const int ca = qsb_cls_of(st.clsword, lb), cb = qsb_cls_of(st.clsword, m + gb);
+        if (env.lead)
+          for (int e = 0; e < 4; ++e) { c128 x = ctl->pend[lb][e]; ctl->pend[lb][e] = ctl->pend[m + gb][e]; ctl->pend[m + gb][e] = x; }
+        st.clsword = qsb_cls_set(qsb_cls_set(st.clsword, lb, cb), m + gb, ca);
+      }
       break;
     }
     case QSB_OP_SNAPSHOT: {
@@ -1095,7 +1174,7 @@ QSB_CTL void qsb_control_slow(Env& env, const qsb_exec_args& a, qsb_cstate& st, 
 // none).  Device: 32 ops per step, __match_any_sync groups the lanes by slot; the windows are walked from the
 // last to the first so that each op can point at the first op of its slot in the later windows.
 template <class Env>
-QSB_HD void qsb_link_chunk(Env& env, qsb_ctl* ctl, int len) {
+QSB_HD void qsb_link_chunk(Env& env, qsb_chunk* ctl, int len) {
   env.sync_control();
   for (int slot = env.clane; slot < 32; slot += env.CL) ctl->head[slot] = QSB_CHUNK;
   env.sync_control();
@@ -1133,10 +1212,6 @@ QSB_HD void qsb_control_unit(Env& env, qsb_cstate& st, const qsb_exec_args& a, i
   st.dim = (int64_t)1 << n;
   st.record = a.branches != nullptr && env.rank == 0;
   st.clsword = 0;
-  const qsb_op* ops = a.ops + t * a.ops_stride;
-  const double* prm = a.params ? a.params + t * a.params_stride : nullptr;
-  const double* uni = a.uniforms ? a.uniforms + t * a.uniforms_stride : nullptr;
-  const uint64_t tglob = (uint64_t)(a.traj_offset + t);
   const uint32_t all_bits = n >= 32 ? 0xffffffffu : ((1u << n) - 1u);
   const bool lead = env.lead;
 
@@ -1155,26 +1230,19 @@ QSB_HD void qsb_control_unit(Env& env, qsb_cstate& st, const qsb_exec_args& a, i
 
   for (int64_t pc0 = 0; pc0 < a.n_ops; pc0 += QSB_CHUNK) {
     const int len = (int)((a.n_ops - pc0) < QSB_CHUNK ? (a.n_ops - pc0) : QSB_CHUNK);
-    // ---- phase A: the lanes decode a chunk in parallel (op records, uniforms, angles, matrices)
-    env.sync_control();
+    // ---- the decode warp staged this chunk (records, uniforms, decoded ops, per-slot MUL lists, SLOW mask)
+    const int cb = (int)(st.gchunk & 1u);
+    qsb_chunk* ck = &ctl->chunk[cb];
     unsigned long long pc_t0 = st.prof ? env.clock() : 0;
-    for (int i = env.clane; i < len; i += env.CL) {
-      const qsb_op op = ops[pc0 + i];
-      double u = 0.0;
-      if (op.draw >= 0) u = uni ? uni[op.draw] : qsb_philox_uniform(a.seed, tglob, (uint32_t)op.draw);
-      ctl->ops[i] = op;
-      ctl->u[i] = u;
-      qsb_decode_op(env, a, st, op, u, prm, &ctl->dec[i]);
-    }
-    env.sync_control();
-    if (st.prof) st.t_decode += env.clock() - pc_t0;
-
-    // ---- phase A2: link the MUL records of each slot into a list (head[slot], dec[].next), lane-parallel
-    qsb_link_chunk(env, ctl, len);
+    env.dec_wait_full(cb, (st.gchunk >> 1) & 1u);
+    if (st.prof) st.t_decode += env.clock() - pc_t0;     // cycles the control warp waited for the decode warp
+    uint32_t slowmask[QSB_CHUNK / 32];
+#pragma unroll
+    for (int r = 0; r < QSB_CHUNK / 32; ++r) slowmask[r] = ck->slowmask[r];
     int cur[(32 + Env::CL - 1) / Env::CL];              // next unapplied op of the slot(s) this lane owns
     {
       int q = 0;
-      for (int slot = env.clane; slot < 32; slot += env.CL) cur[q++] = ctl->head[slot];
+      for (int slot = env.clane; slot < 32; slot += env.CL) cur[q++] = ck->head[slot];
     }
 
     // ---- phase B: fold the MUL records up to the next SLOW op.  Control lane L owns slot L and walks that slot's
@@ -1183,8 +1251,12 @@ QSB_HD void qsb_control_unit(Env& env, qsb_cstate& st, const qsb_exec_args& a, i
     while (i < len) {
       pc_t0 = st.prof ? env.clock() : 0;
       env.sync_control();
-      int stop = i;
-      while (stop < len && ctl->dec[stop].type != QSB_DEC_SLOW) ++stop;
+      int stop = len;                                      // next SLOW op at or after i
+#pragma unroll
+      for (int r = QSB_CHUNK / 32 - 1; r >= 0; --r) {
+        const uint32_t w32 = slowmask[r] & (r == (i >> 5) ? (0xffffffffu << (i & 31)) : (r > (i >> 5) ? 0xffffffffu : 0u));
+        if (w32) stop = 32 * r + QSB_CTZ(w32);
+      }
       uint64_t w = st.clsword;
       uint32_t lo = 0, hi = 0;                            // class bit planes rebuilt from the lanes
       {
@@ -1195,7 +1267,7 @@ QSB_HD void qsb_control_unit(Env& env, qsb_cstate& st, const qsb_exec_args& a, i
             c128 p0 = ctl->pend[slot][0], p1 = ctl->pend[slot][1], p2 = ctl->pend[slot][2], p3 = ctl->pend[slot][3];
             int j = cur[q];
             while (j < stop) {
-              const qsb_dec* d = &ctl->dec[j];
+              const qsb_dec* d = &ck->dec[j];
               const c128 u0 = d->U[0], u1 = d->U[1], u2 = d->U[2], u3 = d->U[3];
               const c128 n0 = qsb_fma(u1, p2, qsb_mul(u0, p0)), n1 = qsb_fma(u1, p3, qsb_mul(u0, p1));
               const c128 n2 = qsb_fma(u3, p2, qsb_mul(u2, p0)), n3 = qsb_fma(u3, p3, qsb_mul(u2, p1));
@@ -1217,11 +1289,13 @@ QSB_HD void qsb_control_unit(Env& env, qsb_cstate& st, const qsb_exec_args& a, i
       if (i < len) {
         pc_t0 = st.prof ? env.clock() : 0;
         const unsigned long long rw0 = st.ring_wait;
-        qsb_control_slow(env, a, st, i);
+        qsb_control_slow(env, a, st, ck, i);
         if (st.prof) { st.t_slow += env.clock() - pc_t0 - (st.ring_wait - rw0); st.n_slow += 1; }
         ++i;
       }
     }
+    env.dec_release(cb);                                 // the decode warp may refill this buffer
+    ++st.gchunk;
   }
 
   // ---- epilogue
@@ -1233,14 +1307,74 @@ QSB_HD void qsb_control_unit(Env& env, qsb_cstate& st, const qsb_exec_args& a, i
                    (a.flags & QSB_RUN_ACCUM_PROBS) ? a.probs_accum : nullptr);
 }
 
+// ---- decode warp: stages the op list one chunk ahead of the control warp -------------------------------------
+// Lane-parallel and stateless with respect to the pending matrices: op records, the uniform of each draw, rotation
+// matrices, "certain K0" tests, sweep group orders, the per-slot MUL lists and the SLOW-op mask.
+template <class Env>
+QSB_HD void qsb_decode_loop(Env& env, const qsb_exec_args& a, int64_t first, int64_t stride) {
+  qsb_ctl* ctl = env.ctl();
+  qsb_cstate st;
+  st.seq = 0; st.gchunk = 0; st.prof = a.prof != nullptr;
+  unsigned long long t_dec = 0, t_wait = 0;
+  const int64_t total = a.count << a.tile_bits;
+  for (int64_t unit = first; unit < total; unit += stride) {
+    const int64_t t = unit >> a.tile_bits;
+    st.t = t;
+    st.record = a.branches != nullptr && env.rank == 0;
+    const qsb_op* ops = a.ops + t * a.ops_stride;
+    const double* prm = a.params ? a.params + t * a.params_stride : nullptr;
+    const double* uni = a.uniforms ? a.uniforms + t * a.uniforms_stride : nullptr;
+    const uint64_t tglob = (uint64_t)(a.traj_offset + t);
+    for (int64_t pc0 = 0; pc0 < a.n_ops; pc0 += QSB_CHUNK) {
+      const int len = (int)((a.n_ops - pc0) < QSB_CHUNK ? (a.n_ops - pc0) : QSB_CHUNK);
+      const int cb = (int)(st.gchunk & 1u);
+      qsb_chunk* ck = &ctl->chunk[cb];
+      unsigned long long c0 = st.prof ? env.clock() : 0;
+      if (st.gchunk >= 2) env.dec_wait_empty(cb, ((st.gchunk >> 1) - 1u) & 1u);
+      unsigned long long c1 = st.prof ? env.clock() : 0;
+      uint32_t slowmask[QSB_CHUNK / 32];
+#pragma unroll
+      for (int r = 0; r < QSB_CHUNK / 32; ++r) slowmask[r] = 0;
+      for (int base = 0; base < len; base += env.CL) {
+        const int i = base + env.clane;
+        int slow = 0;
+        if (i < len) {
+          const qsb_op op = ops[pc0 + i];
+          double u = 0.0;
+          if (op.draw >= 0) u = uni ? uni[op.draw] : qsb_philox_uniform(a.seed, tglob, (uint32_t)op.draw);
+          ck->ops[i] = op;
+          ck->u[i] = u;
+          qsb_decode_op(env, a, st, op, u, prm, &ck->dec[i]);
+          slow = ck->dec[i].type == QSB_DEC_SLOW;
+        }
+        const uint32_t bal = env.ballot_slot(slow, i & 31);
+#pragma unroll
+        for (int r = 0; r < QSB_CHUNK / 32; ++r) if (r == (i >> 5)) slowmask[r] |= bal;
+      }
+      if (env.lead)
+        for (int r = 0; r < QSB_CHUNK / 32; ++r) ck->slowmask[r] = slowmask[r];
+      qsb_link_chunk(env, ck, len);
+      env.dec_publish(cb);
+      ++st.gchunk;
+      if (st.prof) { t_wait += c1 - c0; t_dec += env.clock() - c1; }
+    }
+  }
+  if (st.prof && env.lead) {
+    unsigned long long* o = a.prof + (size_t)env.cta_id() * QSB_PROF_WORDS;
+    o[30] = t_dec; o[31] = t_wait;
+  }
+  if (env.C > 1) env.cluster_exit();
+}
+
 // control main loop over the units [first, total) of this CTA (stride = number of resident clusters / CTAs)
 template <class Env>
 QSB_HD void qsb_control_loop(Env& env, const qsb_exec_args& a, int64_t first, int64_t stride) {
   qsb_cstate st;
-  st.seq = 0; st.clsword = 0; st.parity = 0;
+  st.seq = 0; st.gchunk = 0; st.clsword = 0; st.parity = 0;
   st.prof = a.prof != nullptr; st.ring_wait = 0;
   st.t_decode = st.t_fold = st.t_slow = st.n_slow = 0;
   st.t_emit_body = st.t_emit_pub = st.n_emit = 0;
+  st.t_e[0] = st.t_e[1] = st.t_e[2] = st.t_e[3] = 0;
   const unsigned long long c0 = st.prof ? env.clock() : 0;
   const int64_t total = a.count << a.tile_bits;
   for (int64_t u = first; u < total; u += stride) qsb_control_unit(env, st, a, u);
@@ -1251,6 +1385,7 @@ QSB_HD void qsb_control_loop(Env& env, const qsb_exec_args& a, int64_t first, in
     o[19] = st.seq;
     o[20] = st.t_decode; o[21] = st.t_fold; o[22] = st.t_slow; o[23] = st.n_slow;
     o[24] = st.t_emit_body; o[25] = st.t_emit_pub; o[26] = st.n_emit;
+    o[27] = st.t_e[0]; o[28] = st.t_e[1]; o[29] = st.t_e[2];
   }
   qsb_desc* d = qsb_desc_begin(env, st);
   if (env.lead) d->kind = QSB_D_EXIT;

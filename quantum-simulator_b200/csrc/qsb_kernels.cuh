@@ -11,6 +11,7 @@ namespace cg = cooperative_groups;
 
 #define QSB_MAX_WORKERS 256
 #define QSB_CTL_THREADS 32
+#define QSB_DEC_THREADS 32       // decode warp: stages the op list one chunk ahead of the control warp
 #define QSB_SMEM_EXTRA (sizeof(qsb_ctl))
 
 // the one dynamic shared-memory block of the executor kernel: [tile | qsb_ctl]
@@ -35,7 +36,7 @@ __device__ __forceinline__ void qsb_cluster_wait() {
   asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
 }
 
-// threads [0, W) are workers, [W, W + 32) is the control warp
+// threads [0, W) are workers, [W, W + 32) is the control warp, [W + 32, W + 64) the decode warp
 template <int CS, class A = c128>
 struct DeviceEnv {
   typedef A amp;
@@ -45,17 +46,19 @@ struct DeviceEnv {
   int lane, warp, nwarps;      // worker warp geometry
   int clane;                   // lane inside the control warp
   bool lead;                   // the control lane that writes shared state
+  int role;                    // 0 worker, 1 control warp, 2 decode warp
 
   __device__ DeviceEnv(int m) {
-    W = (int)blockDim.x - QSB_CTL_THREADS;      // a power of two >= 32
+    W = (int)blockDim.x - QSB_CTL_THREADS - QSB_DEC_THREADS;      // a power of two >= 32
     wbits = 31 - __clz(W);
     const int tid = threadIdx.x;
     wid = tid < W ? tid : -1;
     lane = tid & 31;
     warp = tid >> 5;
     nwarps = W >> 5;
-    clane = tid - W;
+    clane = (tid - W) & 31;                      // lane inside the control warp / the decode warp
     lead = clane == 0;
+    role = tid < W ? 0 : (tid < W + QSB_CTL_THREADS ? 1 : 2);
     rank = (CS > 1) ? (int)cg::this_cluster().block_rank() : 0;
     m_ = m;
   }
@@ -83,12 +86,36 @@ struct DeviceEnv {
   // control-warp collectives: lanes with the same key; bit `slot` of the result = this lane's predicate (lane == slot)
   __device__ __forceinline__ uint32_t match_any(int key) { return __match_any_sync(0xffffffffu, key); }
   __device__ __forceinline__ uint32_t ballot_slot(int pred, int slot) { (void)slot; return __ballot_sync(0xffffffffu, pred); }
+  __device__ __forceinline__ uint32_t or_reduce(uint32_t x) { return __reduce_or_sync(0xffffffffu, x); }
   // lane 0 of the control warp -> every lane
   __device__ __forceinline__ int bcast_i(int x) { return __shfl_sync(0xffffffffu, x, 0); }
   __device__ __forceinline__ uint64_t bcast_u64(uint64_t x) {
     const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)x, 0), hi = __shfl_sync(0xffffffffu, (uint32_t)(x >> 32), 0);
     return ((uint64_t)hi << 32) | lo;
   }
+  // ---- decode warp <-> control warp: one mbarrier per chunk buffer and direction (count 1: the lead lane arrives
+  // after a __syncwarp, every lane of the other warp polls the phase)
+  __device__ __forceinline__ uint32_t dbar_addr(int k) { return (uint32_t)__cvta_generic_to_shared(&ctl()->dbar[k]); }
+  __device__ __forceinline__ void dbar_arrive(int k) {
+    __syncwarp();
+    if (lead) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(dbar_addr(k)) : "memory");
+  }
+  __device__ __forceinline__ void dbar_wait(int k, uint32_t parity) {
+    const uint32_t addr = dbar_addr(k);
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    }
+    __syncwarp();
+  }
+  __device__ __forceinline__ void dec_publish(int b) { dbar_arrive(b); }
+  __device__ __forceinline__ void dec_wait_full(int b, uint32_t parity) { dbar_wait(b, parity); }
+  __device__ __forceinline__ void dec_release(int b) { dbar_arrive(2 + b); }
+  __device__ __forceinline__ void dec_wait_empty(int b, uint32_t parity) { dbar_wait(2 + b, parity); }
   // ---- descriptor ring
   __device__ __forceinline__ void ring_wait_empty(int s) { __syncwarp(); qsb_bar_sync(QSB_BAR_EMPTY + s, W + QSB_CTL_THREADS); }
   __device__ __forceinline__ void ring_publish(int s) {
@@ -137,25 +164,23 @@ struct DeviceEnv {
 };
 
 template <int CS, class A>
-__global__ void __launch_bounds__(QSB_MAX_WORKERS + QSB_CTL_THREADS, 1)
+__global__ void __launch_bounds__(QSB_MAX_WORKERS + QSB_CTL_THREADS + QSB_DEC_THREADS, 1)
 qsb_traj_kernel(const __grid_constant__ qsb_exec_args a) {
   DeviceEnv<CS, A> env(a.m);
   env.prof_ = a.prof;
   env.xphase = 0;
-  if (CS > 1) {
-    if (threadIdx.x == 0) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(env.xbar_addr()), "r"(CS) : "memory");
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    env.cluster_exit();                       // every mbarrier of the cluster is initialised before its first use
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < 4; ++k) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(env.dbar_addr(k)) : "memory");
+    if (CS > 1) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(env.xbar_addr()), "r"(CS) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (env.wid >= 0) {
-    qsb_worker_loop(env, a);
-  } else {
-    const int64_t first = a.tile_bits ? (int64_t)blockIdx.x : (int64_t)(blockIdx.x / CS);
-    const int64_t stride = a.tile_bits ? (int64_t)gridDim.x : (int64_t)(gridDim.x / CS);
-    qsb_control_loop(env, a, first, stride);
-  }
+  __syncthreads();
+  if (CS > 1) env.cluster_exit();             // every mbarrier of the cluster is initialised before its first use
+  const int64_t first = a.tile_bits ? (int64_t)blockIdx.x : (int64_t)(blockIdx.x / CS);
+  const int64_t stride = a.tile_bits ? (int64_t)gridDim.x : (int64_t)(gridDim.x / CS);
+  if (env.role == 0) qsb_worker_loop(env, a);
+  else if (env.role == 1) qsb_control_loop(env, a, first, stride);
+  else qsb_decode_loop(env, a, first, stride);
 }
 
 // ---------------------------------------------------------------------------------------

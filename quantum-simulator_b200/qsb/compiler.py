@@ -328,8 +328,9 @@ class Lowering:
                           n_draws=self.n_draws, n_params=self.n_params)
 
     # -- slot placement + emission ------------------------------------------------------
-    def finish(self, local_bits=None, max_local_bits=MAX_LOCAL_BITS):
-        """max_local_bits: 13 for complex128 tiles, 14 in the context's complex64 mode (twice the amplitudes per CTA)."""
+    def finish(self, local_bits=None, max_local_bits=MAX_LOCAL_BITS, multi_remap=True):
+        """max_local_bits: 13 for complex128 tiles, 14 in the context's complex64 mode (twice the amplitudes per CTA).
+        multi_remap: let one REMAP op exchange up to three (rank bit, local bit) pairs."""
         n = self.n
         if n > MAX_QUBITS:
             raise NotImplementedError(f"the resident executor holds at most {MAX_QUBITS} qubits, got {n}")
@@ -386,13 +387,38 @@ class Lowering:
                 idata += perm_for(snap_axes)
                 ops.append((SNAPSHOT, data, 0, 0, -1, -1, -1, off))
                 continue
-            for b in pbits:
-                if slot_of[b] >= m and needs_local(kind, pbits):
-                    cand = [c for c in range(n) if slot_of[c] < m and c not in pbits]
-                    victim = max(cand, key=lambda c: (next_use(c, i), -slot_of[c]))
-                    ops.append((REMAP, slot_of[b] - m, slot_of[victim], 0, -1, -1, -1, 0))
-                    slot_of[b], slot_of[victim] = slot_of[victim], slot_of[b]
-                    n_remaps += 1
+            if needs_local(kind, pbits) and any(slot_of[b] >= m for b in pbits):
+                # One exchange op moves every rank-bit qubit this op needs into the tile and, while the data is moving
+                # anyway, every other rank-bit qubit that is needed sooner than the local qubit it would displace
+                # (k bits in one pass cost 1 - 2^-k tile volumes instead of k / 2).  Victims: farthest next use.
+                pairs = []                                   # (incoming qubit, outgoing qubit)
+                taken = set(pbits)
+                def farthest():
+                    cand = [c for c in range(n) if slot_of[c] < m and c not in taken]
+                    return max(cand, key=lambda c: (next_use(c, i), -slot_of[c]))
+                for b in pbits:
+                    if slot_of[b] >= m:
+                        v = farthest()
+                        pairs.append((b, v))
+                        taken.add(v)
+                if multi_remap:
+                    others = sorted((c for c in range(n) if slot_of[c] >= m and c not in taken),
+                                    key=lambda c: next_use(c, i))
+                    for x in others:
+                        if len(pairs) >= 3 or not any(slot_of[c] < m and c not in taken for c in range(n)):
+                            break
+                        v = farthest()
+                        if next_use(x, i) >= next_use(v, i):
+                            break
+                        pairs.append((x, v))
+                        taken.update((x, v))
+                aux = 0
+                for j, (b, v) in enumerate(pairs[1:]):
+                    aux |= ((slot_of[b] - m) | (slot_of[v] << 8)) << (16 * j)
+                ops.append((REMAP, slot_of[pairs[0][0]] - m, slot_of[pairs[0][1]], len(pairs) - 1, -1, -1, -1, aux))
+                for b, v in pairs:
+                    slot_of[b], slot_of[v] = slot_of[v], slot_of[b]
+                n_remaps += 1
             sb = [slot_of[b] for b in pbits] + [0, 0, 0]
             ops.append((kind, sb[0], sb[1], sb[2], data, param, draw, 0))
         store_off = len(idata)

@@ -21,6 +21,7 @@ struct Cta {
   std::vector<c128> tile;
   qsb_ctl ctl;
   std::unique_ptr<std::barrier<>> full[QSB_RING], empty[QSB_RING], workers, all;
+  std::unique_ptr<std::barrier<>> dfull[2], dempty[2];   // decode thread <-> control thread, per chunk buffer
 };
 
 struct Shared {
@@ -54,8 +55,13 @@ struct HostEnv {
   int cta_id() { return cta; }
   uint32_t match_any(int) { return 1u; }
   uint32_t ballot_slot(int pred, int slot) { return pred ? (1u << slot) : 0u; }
+  uint32_t or_reduce(uint32_t x) { return x; }
   int bcast_i(int x) { return x; }
   uint64_t bcast_u64(uint64_t x) { return x; }
+  void dec_publish(int b) { (void)me().dfull[b]->arrive(); }
+  void dec_wait_full(int b, uint32_t) { me().dfull[b]->arrive_and_wait(); }
+  void dec_release(int b) { (void)me().dempty[b]->arrive(); }
+  void dec_wait_empty(int b, uint32_t) { me().dempty[b]->arrive_and_wait(); }
   void ring_wait_empty(int s) { me().empty[s]->arrive_and_wait(); }
   void ring_publish(int s) { (void)me().full[s]->arrive(); }
   void ring_wait_full(int s) { me().full[s]->arrive_and_wait(); }
@@ -90,12 +96,13 @@ extern "C" int emu_run(int n, int m, int T, const qsb_op* ops, int64_t n_ops, in
     for (int s = 0; s < QSB_RING; ++s) {
       c.full[s].reset(new std::barrier<>(T + 1));
       c.empty[s].reset(new std::barrier<>(T + 1));
+      if (s < 2) { c.dfull[s].reset(new std::barrier<>(2)); c.dempty[s].reset(new std::barrier<>(2)); }
     }
     c.workers.reset(new std::barrier<>(T));
     c.all.reset(new std::barrier<>(T + 1));
   }
   sh.cluster.reset(new std::barrier<>(sh.C * T));
-  sh.cluster_all.reset(new std::barrier<>(sh.C * (T + 1)));
+  sh.cluster_all.reset(new std::barrier<>(sh.C * (T + 2)));
 
   qsb_exec_args a;
   memset(&a, 0, sizeof a);
@@ -113,15 +120,15 @@ extern "C" int emu_run(int n, int m, int T, const qsb_op* ops, int64_t n_ops, in
 
   std::vector<std::thread> th;
   for (int r = 0; r < n_cta; ++r)
-    for (int t = 0; t <= T; ++t)
+    for (int t = 0; t <= T + 1; ++t)          // T workers, the control thread, the decode thread
       th.emplace_back([&sh, &a, r, t, T, streaming, n_cta]() {
         HostEnv env;
         env.sh = &sh; env.cta = r; env.rank = streaming ? 0 : r; env.C = sh.C; env.W = T; env.wbits = T == 8 ? 3 : T == 16 ? 4 : 5;
         env.wid = t < T ? t : -1;
         env.lane = 0; env.warp = t; env.nwarps = T; env.clane = 0; env.lead = true;
         if (env.wid >= 0) qsb_worker_loop(env, a);
-        else if (streaming) qsb_control_loop(env, a, r, n_cta);
-        else qsb_control_loop(env, a, 0, 1);
+        else if (t == T) { if (streaming) qsb_control_loop(env, a, r, n_cta); else qsb_control_loop(env, a, 0, 1); }
+        else { if (streaming) qsb_decode_loop(env, a, r, n_cta); else qsb_decode_loop(env, a, 0, 1); }
       });
   for (auto& x : th) x.join();
   return 0;

@@ -289,3 +289,34 @@ def test_c64_noisy_16q_cluster4_and_reductions():
         assert np.max(np.abs(ov.download(np.complex128, (3,)) - np.sum(np.abs(psi.astype(np.complex128)) ** 2, axis=1))) < 1e-12
     finally:
         ctx.set_precision("c128")
+
+
+# ---- REMAP ops that exchange several (rank bit, local bit) pairs in one pass ------------------------------------
+@pytest.mark.parametrize("gbits", [2, 3])
+def test_multi_pair_remaps(run, gbits):
+    """Layered noisy circuit on clusters of 4 / 8: the planner packs up to three pair swaps into one REMAP op; the
+    result equals the oracle and the single-pair plan (same draws, same branches)."""
+    from qsb.compiler import REMAP
+    n = 9
+    m = n - gbits
+    gates = layered_circuit(n, 12, 77)
+    noise = config3_noise()
+    qc = make_circuit(n, gates)
+    lw_args = (n, qc.get_ordered_gates(), REG, channels_of_factory(noise))
+    prog, _ = lower_circuit(*lw_args, local_bits=m)
+    k = [int(o["b2"]) + 1 for o in prog.ops if int(o["kind"]) == REMAP]
+    assert k and max(k) >= 2, k                     # at least one exchange moves two or three pairs at once
+    if gbits == 3:
+        assert max(k) == 3, k
+    for o in prog.ops:
+        if int(o["kind"]) == REMAP and int(o["b2"]) >= 1:
+            aux = int(o["aux"])
+            g = [int(o["b0"]), aux & 255, (aux >> 16) & 255][:int(o["b2"]) + 1]
+            l = [int(o["b1"]), (aux >> 8) & 255, (aux >> 24) & 255][:int(o["b2"]) + 1]
+            assert len(set(g)) == len(g) and len(set(l)) == len(l) and max(g) < gbits and max(l) < m
+    draws = np.random.default_rng(3).random((2, prog.n_draws))
+    out = run(prog, count=2, T=2, uniforms=draws, want_branches=True)
+    for t in range(2):
+        psi, _, br, _ = O.run_state(n, gates, None, noise, draws[t])
+        assert out["branches"][t][:len(br)].tolist() == br
+        assert np.max(np.abs(out["states"][t] - psi)) < TOL

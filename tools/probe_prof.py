@@ -30,6 +30,8 @@ def prof(label, prog, T):
     print(f"   control total {p0[18]:10.0f}   ring-full wait {p0[17]:10.0f}   descriptors {p0[19]:7.1f}")
     print(f"   control: decode {p0[20]:10.0f}  fold {p0[21]:10.0f}  slow ops {p0[22]:10.0f} (n={p0[23]:6.1f}, {p0[22] / max(p0[23], 1):6.0f} each, excl. ring wait)")
     print(f"   control emit_sweep: n={p0[26]:6.1f} body {p0[24] / max(p0[26], 1):7.0f}  publish {p0[25] / max(p0[26], 1):7.0f} cycles each")
+    ne = max(p0[26], 1)
+    print(f"      emit body split: syncwarp {p0[27] / ne:6.0f}  pending copy {p0[28] / ne:6.0f}  group order {p0[29] / ne:6.0f}  rest {(p0[24] - p0[27] - p0[28] - p0[29]) / ne:6.0f}")
     print(f"   worker wait   {p0[0]:10.0f}")
     for k, name in enumerate(KINDS):
         if p0[9 + k]:
@@ -40,8 +42,8 @@ def prof(label, prog, T):
             print(f"      sweep k={key // 8} gate={G[key % 8]:6s} n={p0[64 + key]:7.1f}  {p0[32 + key] / p0[64 + key]:8.0f} / desc")
     print(f"      remap: first cluster barrier {p0[120] / max(p0[12], 1):8.0f} / remap")
     nr = max(p0[12], 1)
-    print(f"      remap: pull issue {p0[121] / nr:8.0f}  second barrier {p0[122] / nr:8.0f}  write {p0[123] / nr:8.0f};  lb=0/1/2/3+: "
-          f"{p0[124]:.0f} {p0[125]:.0f} {p0[126]:.0f} {p0[127]:.0f}")
+    print(f"      remap: pull issue {p0[121] / nr:8.0f}  second barrier {p0[122] / nr:8.0f}  write {p0[123] / nr:8.0f};  rounds with 1/2/3 pairs: "
+          f"{p0[125]:.0f} {p0[126]:.0f} {p0[127]:.0f}")
     print("      per-warp busy:", " ".join(f"{p0[104 + w]:9.0f}" for w in range(8)))
     print("      per-warp wait:", " ".join(f"{p0[112 + w]:9.0f}" for w in range(8)))
     for nd in range(4):
