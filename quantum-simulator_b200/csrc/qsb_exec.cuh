@@ -348,6 +348,7 @@ template <int K, bool DG, class Env>
 QSB_PASS void qsb_sweep(Env& env, int m, const qsb_desc* d) {
   typedef typename Env::amp A;
   A* tile = env.tile();             // re-derived here so device code keeps the shared address space (LDS/STS)
+  const unsigned long long sq0 = env.prof_on() ? env.clock() : 0;
   constexpr int D = 1 << K;
   constexpr int NG = DG ? (K == 2 ? 2 : 1) : (K == 3 ? 1 : 16 / D);
   const int G = d->gate;
@@ -382,6 +383,7 @@ QSB_PASS void qsb_sweep(Env& env, int m, const qsb_desc* d) {
     for (int e = 0; e < 4; ++e) P[k][e] = qsb_cvt<A>(d->P[k][e]);
   }
   const int cnt = 1 << (m - K);
+  if (env.prof_on()) env.prof_add(124, env.clock() - sq0);      // sweep set-up (descriptor fields, offsets, matrices)
   for (int g0 = env.wid; g0 < cnt; g0 += NG * env.W) {
     A a[NG][D];
     int base[NG];

@@ -19,7 +19,8 @@ def run(label, n, build, T, reps=3, m=None, nops=None):
     states = ctx.alloc(T * (1 << n) * 16)
     kw = {}
     if prog.n_draws:
-        kw.update(uniforms=ctx.to_device(np.random.default_rng(0).random((T, prog.n_draws))), uniforms_stride=prog.n_draws)
+        u = np.full((T, prog.n_draws), 0.5) if label.startswith("certain") else np.random.default_rng(0).random((T, prog.n_draws))
+        kw.update(uniforms=ctx.to_device(u), uniforms_stride=prog.n_draws)
     best = 1e9
     for r in range(reps):
         ctx.timer_start()
@@ -63,6 +64,26 @@ def u2(lw):
     m = np.linalg.qr(rng.normal(size=(4, 4)) + 1j * rng.normal(size=(4, 4)))[0]
     for i in range(N): lw.matrix(m, [i % lw.n, (i + 1) % lw.n])
 
+def ad_cx(lw):            # K0 = diag(1, s) pending on both qubits of every CX (uniforms 0.5: always the certain branch)
+    for i in range(N // 3):
+        lw.kraus("amplitude_damping", 0.02, 0); lw.kraus("amplitude_damping", 0.02, 1); lw.gate("CNOT", [0, 1])
+def ad1_cx(lw):
+    for i in range(N // 2):
+        lw.kraus("amplitude_damping", 0.02, 1); lw.gate("CNOT", [0, 1])
+def h2_cx(lw):
+    for i in range(N // 3):
+        lw.matrix(G.H_MATRIX, [0]); lw.matrix(G.H_MATRIX, [1]); lw.gate("CNOT", [0, 1])
+def ad_h_ad_cx(lw):       # the noisy workload's typical pending: K0 . U . K0 on one qubit, K0 on the other
+    for i in range(N // 5):
+        lw.kraus("amplitude_damping", 0.02, 0); lw.matrix(G.H_MATRIX, [0]); lw.kraus("amplitude_damping", 0.02, 0)
+        lw.kraus("amplitude_damping", 0.02, 1); lw.gate("CNOT", [0, 1])
+for n, T in ((13, 148),):
+    run("certain: (AD, AD, CX) x 133", n, ad_cx, T)
+    run("certain: (AD, CX) x 200", n, ad1_cx, T)
+    run("(H, H, CX) x 133", n, h2_cx, T)
+    run("certain: (AD H AD, AD, CX) x 80", n, ad_h_ad_cx, T)
+    run("400 CX same qubits", n, cx_far, T)
+import sys; sys.exit(0)
 for n, T in ((13, 148), (16, 15)):
     run("empty (init+store)", n, empty, T, nops=1)
     run("400 H (scalar pending path)", n, only_h, T)

@@ -36,6 +36,7 @@ def prof(label, prog, T):
     for k, name in enumerate(KINDS):
         if p0[9 + k]:
             print(f"   {name:7s} n={p0[9 + k]:7.1f}  busy {p0[1 + k]:10.0f}  ({p0[1 + k] / p0[9 + k]:8.0f} / desc)")
+    print(f"      sweep set-up before the first load: {p0[124] / max(p0[11], 1):6.0f} cycles / sweep")
     G = ["none", "cx", "cz", "swap", "ccx", "cswap", "dense", "?"]
     for key in range(32):
         if p0[64 + key]:
