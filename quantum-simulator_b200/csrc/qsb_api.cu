@@ -526,9 +526,9 @@ int qsb_program_free(qsb_program* p) {
 
 }  // extern "C"
 
-template <int C, class A>
-static cudaError_t launch_traj(qsb_ctx* ctx, const qsb_exec_args& a, int threads, size_t smem, int* grid_out) {
-  auto kern = qsb_traj_kernel<C, A>;
+template <int C, class A, bool PF>
+static cudaError_t launch_traj_pf(qsb_ctx* ctx, const qsb_exec_args& a, int threads, size_t smem, int* grid_out) {
+  auto kern = qsb_traj_kernel<C, A, PF>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg;
@@ -563,6 +563,13 @@ static cudaError_t launch_traj(qsb_ctx* ctx, const qsb_exec_args& a, int threads
   cfg.gridDim = dim3((unsigned)(units * C), 1, 1);
   *grid_out = (int)(units * C);
   return cudaLaunchKernelEx(&cfg, kern, a);
+}
+
+// the profiling instantiation (cycle counters compiled in) is launched only while qsb_debug_profile is enabled
+template <int C, class A>
+static cudaError_t launch_traj(qsb_ctx* ctx, const qsb_exec_args& a, int threads, size_t smem, int* grid_out) {
+  return a.prof ? launch_traj_pf<C, A, true>(ctx, a, threads, smem, grid_out)
+                : launch_traj_pf<C, A, false>(ctx, a, threads, smem, grid_out);
 }
 
 extern "C" {

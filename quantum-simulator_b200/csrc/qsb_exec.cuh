@@ -748,8 +748,8 @@ template <class Env>
 QSB_HD void qsb_worker_loop(Env& env, const qsb_exec_args& a) {
   const int m = a.m;
   int parity = 0;
-  const bool prof = a.prof != nullptr && env.wid == 0;
-  const bool wprof = a.prof != nullptr && env.lane == 0;      // per-warp busy / wait cycles
+  const bool prof = Env::PROF && a.prof != nullptr && env.wid == 0;
+  const bool wprof = Env::PROF && a.prof != nullptr && env.lane == 0;      // per-warp busy / wait cycles
   unsigned long long wb = 0, ww = 0, w0 = 0, w1 = 0;
   unsigned long long pw = 0, pb[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pn[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t0 = 0, t1 = 0;
   for (uint32_t seq = 0;; ++seq) {
@@ -1316,7 +1316,7 @@ template <class Env>
 QSB_HD void qsb_decode_loop(Env& env, const qsb_exec_args& a, int64_t first, int64_t stride) {
   qsb_ctl* ctl = env.ctl();
   qsb_cstate st;
-  st.seq = 0; st.gchunk = 0; st.prof = a.prof != nullptr;
+  st.seq = 0; st.gchunk = 0; st.prof = Env::PROF && a.prof != nullptr;
   unsigned long long t_dec = 0, t_wait = 0;
   const int64_t total = a.count << a.tile_bits;
   for (int64_t unit = first; unit < total; unit += stride) {
@@ -1373,7 +1373,7 @@ template <class Env>
 QSB_HD void qsb_control_loop(Env& env, const qsb_exec_args& a, int64_t first, int64_t stride) {
   qsb_cstate st;
   st.seq = 0; st.gchunk = 0; st.clsword = 0; st.parity = 0;
-  st.prof = a.prof != nullptr; st.ring_wait = 0;
+  st.prof = Env::PROF && a.prof != nullptr; st.ring_wait = 0;
   st.t_decode = st.t_fold = st.t_slow = st.n_slow = 0;
   st.t_emit_body = st.t_emit_pub = st.n_emit = 0;
   st.t_e[0] = st.t_e[1] = st.t_e[2] = st.t_e[3] = 0;

@@ -37,10 +37,13 @@ __device__ __forceinline__ void qsb_cluster_wait() {
 }
 
 // threads [0, W) are workers, [W, W + 32) is the control warp, [W + 32, W + 64) the decode warp
-template <int CS, class A = c128>
+// PF: the cycle counters of qsb_debug_profile are compiled in (a separate instantiation, launched only while
+// profiling is enabled: the counters cost registers, local memory and ~2 % of the run time)
+template <int CS, class A = c128, bool PF = false>
 struct DeviceEnv {
   typedef A amp;
   static constexpr int C = CS;
+  static constexpr bool PROF = PF;
   static constexpr int CL = QSB_CTL_THREADS;
   int wid, W, wbits, rank, m_;
   int lane, warp, nwarps;      // worker warp geometry
@@ -80,7 +83,7 @@ struct DeviceEnv {
   }
   __device__ __forceinline__ unsigned long long clock() { return (unsigned long long)clock64(); }
   unsigned long long* prof_;
-  __device__ __forceinline__ bool prof_on() { return prof_ != nullptr && threadIdx.x == 0; }
+  __device__ __forceinline__ bool prof_on() { return PF && prof_ != nullptr && threadIdx.x == 0; }
   __device__ __forceinline__ void prof_add(int slot, unsigned long long v) { prof_[(size_t)blockIdx.x * QSB_PROF_WORDS + slot] += v; }
   __device__ __forceinline__ int cta_id() { return (int)blockIdx.x; }
   // control-warp collectives: lanes with the same key; bit `slot` of the result = this lane's predicate (lane == slot)
@@ -163,10 +166,10 @@ struct DeviceEnv {
   __device__ __forceinline__ void handoff_c() { __syncwarp(); qsb_bar_sync(QSB_BAR_ALL, W + QSB_CTL_THREADS); }
 };
 
-template <int CS, class A>
+template <int CS, class A, bool PF>
 __global__ void __launch_bounds__(QSB_MAX_WORKERS + QSB_CTL_THREADS + QSB_DEC_THREADS, 1)
 qsb_traj_kernel(const __grid_constant__ qsb_exec_args a) {
-  DeviceEnv<CS, A> env(a.m);
+  DeviceEnv<CS, A, PF> env(a.m);
   env.prof_ = a.prof;
   env.xphase = 0;
   if (threadIdx.x == 0) {

@@ -35,6 +35,7 @@ struct Shared {
 struct HostEnv {
   typedef c128 amp;
   static constexpr int CL = 1;
+  static constexpr bool PROF = false;
   int wid, W, wbits, rank, C;
   int cta;                      // index of this CTA's storage (== rank in cluster mode)
   int lane, warp, nwarps, clane;

@@ -77,7 +77,20 @@ def ad_h_ad_cx(lw):       # the noisy workload's typical pending: K0 . U . K0 on
     for i in range(N // 5):
         lw.kraus("amplitude_damping", 0.02, 0); lw.matrix(G.H_MATRIX, [0]); lw.kraus("amplitude_damping", 0.02, 0)
         lw.kraus("amplitude_damping", 0.02, 1); lw.gate("CNOT", [0, 1])
+def cx_pairs(lw):          # adjacent CX on disjoint bits: fused into K = 4 sweeps
+    for i in range(N // 2):
+        lw.gate("CNOT", [0, 1]); lw.gate("CNOT", [2, 3])
+def cx_pairs_low(lw):
+    for i in range(N // 2):
+        lw.gate("CNOT", [12, 11]); lw.gate("CNOT", [10, 9])
+def h4_cx_pairs(lw):
+    for i in range(N // 6):
+        for q in range(4): lw.matrix(G.H_MATRIX, [q])
+        lw.gate("CNOT", [0, 1]); lw.gate("CNOT", [2, 3])
 for n, T in ((13, 148),):
+    run("200 x (CX, CX) disjoint, high bits", n, cx_pairs, T)
+    run("200 x (CX, CX) disjoint, low bits", n, cx_pairs_low, T)
+    run("(H x4, CX, CX) x 66", n, h4_cx_pairs, T)
     run("certain: (AD, AD, CX) x 133", n, ad_cx, T)
     run("certain: (AD, CX) x 200", n, ad1_cx, T)
     run("(H, H, CX) x 133", n, h2_cx, T)
