@@ -42,8 +42,8 @@ def algorithmic_bytes_per_trajectory(n, gates, k_pauli, k_ad):
 
 
 # DRAM bytes one trajectory really moves (ncu dram__bytes_read.sum + dram__bytes_write.sum of the trajectory
-# kernel divided by its trajectories: profiles/r01e_traj_kernel_ncu_full_traj480.csv, 474.3 MB / 480)
-MEASURED_DRAM_BYTES_PER_TRAJECTORY = (12124672 + 462198016) / 480
+# kernel divided by its trajectories: profiles/r01f_traj_kernel_ncu_full_traj480.csv, 466.2 MB / 480)
+MEASURED_DRAM_BYTES_PER_TRAJECTORY = (11251712 + 454993152) / 480
 
 
 def measured_peak():
@@ -300,7 +300,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": f"qsb_traj_kernel<{1 << (prog.n - prog.m)}>",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": MEASURED_DRAM_BYTES_PER_TRAJECTORY * T,
-                         "traffic_source": "ncu dram bytes per trajectory (profiles/r01e_traj_kernel_ncu_full_traj480.csv) x trajectories per launch",
+                         "traffic_source": "ncu dram bytes per trajectory (profiles/r01f_traj_kernel_ncu_full_traj480.csv) x trajectories per launch",
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes * T, "kernel_ms": kms,
                          "note": "trajectories are resident in cluster shared memory; algorithmic bytes count "
