@@ -443,14 +443,114 @@ def case_debugger():
     print("debugger golden written")
 
 
+# ---------------------------------------------------------------- edge cases (golden_edges.*)
+def case_edges():
+    """Smallest / largest registers, empty and measure-only circuits, shots = 0, probabilities 0 and 1, collapse
+    sequences, error texts."""
+    JE, AE = {}, {}
+
+    def run_case(tag, n, gates, initial=None, shots=64, seed=5, noise=None, noise_seed=None, basis="Z"):
+        qc = circuit(n, gates, initial)
+        nm = noise_model(noise, noise_seed) if noise else None
+        res = Simulator(nm).run(qc, shots=shots, seed=seed, record_steps=True, measurement_basis=MeasurementBasis[basis])
+        AE[tag] = res.final_state.data
+        JE[tag] = {"n": n, "gates": gates, "initial": initial, "shots": shots, "seed": seed, "noise": noise,
+                   "noise_seed": noise_seed, "basis": basis, "counts": res.measurement_counts,
+                   "n_steps": len(res.step_states) if res.step_states is not None else None}
+        if res.step_states:
+            AE[tag + "_steps"] = np.array([s.data for s in res.step_states])
+
+    run_case("one_qubit", 1, [("H", [0], [], 0), ("Rz", [0], [0.3], 1), ("Measure", [0], [], 2)], shots=100)
+    run_case("one_qubit_y", 1, [("Rx", [0], [1.1], 0)], shots=50, basis="Y")
+    run_case("empty", 4, [], initial=[1, 0, 1, 1], shots=10)
+    run_case("empty_shots0", 3, [], shots=0)
+    run_case("measure_only", 3, [("Measure", [1], [], 0), ("Barrier", [0], [], 1)], initial=[0, 1, 0], shots=7)
+    run_case("measure_shots0", 2, [("H", [0], [], 0), ("Measure", [0], [], 1)], shots=0)
+    ghz16 = [("H", [0], [], 0)] + [("CNOT", [0, q], [], q) for q in range(1, 16)]
+    run_case("ghz16", 16, ghz16, shots=200, seed=9)
+    run_case("max16_layer", 16, layered_circuit(16, 3, 5), initial=[i % 2 for i in range(16)], shots=32, seed=3)
+    run_case("sparse_columns", 3, [("X", [2], [], 5), ("H", [0], [], 5), ("CNOT", [0, 1], [], 40), ("Y", [1], [], 2)], shots=20)
+    run_case("p0_noise", 3, ghz(3), noise={"global": [("depolarizing", 0.0), ("amplitude_damping", 0.0), ("bit_flip", 0.0)]},
+             noise_seed=1, shots=30)
+    run_case("p1_bitflip", 3, ghz(3), noise={"global": [("bit_flip", 1.0)]}, noise_seed=2, shots=30)
+    run_case("p1_phaseflip", 2, [("H", [0], [], 0), ("H", [1], [], 0)], noise={"global": [("phase_flip", 1.0)]}, noise_seed=2, shots=30)
+    run_case("gamma1_damping", 3, [("X", [0], [], 0), ("H", [1], [], 0), ("CNOT", [1, 2], [], 1)],
+             noise={"global": [("amplitude_damping", 1.0)]}, noise_seed=3, shots=30)
+    run_case("p1_depol", 2, [("H", [0], [], 0), ("CNOT", [0, 1], [], 1)], noise={"global": [("depolarizing", 1.0)]},
+             noise_seed=4, shots=30)
+    run_case("gate_noise_only", 3, ghz(3) + [("H", [2], [], 5)], noise={"gate": {"H": [("bit_flip", 0.5)], "CNOT": [("amplitude_damping", 0.5)]}},
+             noise_seed=6, shots=30)
+    run_case("readout_extremes", 2, [("X", [0], [], 0)], noise={"readout": (1.0, 0.0)}, shots=16)
+
+    # run_with_noise with shots = 0 and 1
+    qc = circuit(3, ghz(3))
+    for shots in (0, 1, 5):
+        nm = noise_model({"global": [("depolarizing", 0.2)]}, 11)
+        r = Simulator(nm).run_with_noise(qc, shots=shots, seed=12)
+        JE[f"rwn_{shots}"] = {"counts": r.measurement_counts, "num_shots": r.num_shots}
+    # ensemble with 0 / 1 trials, with and without noise
+    for tag, nm in (("ens_nonoise", None), ("ens_noise", noise_model({"global": [("depolarizing", 0.3)]}, 1))):
+        for trials in (1, 3):
+            AE[f"{tag}_{trials}"] = Simulator(nm).ensemble_density_matrix(qc, n_trials=trials, seed=8)
+
+    # collapse sequences
+    rng = np.random.default_rng(77)
+    sv = StateVector(4)
+    sv.data = rand_state(np.random.default_rng(1), 4)
+    seq = []
+    for q in (2, 0, 3, 1, 2):
+        seq.append(int(sv.measure_qubit(q, rng)))
+        AE[f"collapse_{len(seq)}"] = sv.data.copy()
+    JE["collapse_outcomes"] = seq
+    sv = StateVector(3)
+    sv.data = rand_state(np.random.default_rng(2), 3)
+    JE["measure_all"] = sv.measure_all(np.random.default_rng(3))
+    AE["measure_all_state"] = sv.data.copy()
+    sv = StateVector.from_initial_states([1, 1, 0, 1])
+    AE["from_initial"] = sv.data.copy()
+    sv.reset()
+    AE["reset_default"] = sv.data.copy()
+    sv.reset([0, 1, 1, 0])
+    AE["reset_states"] = sv.data.copy()
+    JE["bloch"] = [list(map(float, StateVector.from_initial_states([0, 1]).get_bloch_coordinates(q))) for q in (0, 1)]
+
+    # error texts
+    errs = {}
+    def err(tag, fn):
+        try:
+            fn()
+            errs[tag] = None
+        except Exception as e:
+            errs[tag] = [type(e).__name__, str(e)]
+    err("sv_0", lambda: StateVector(0))
+    err("sv_17", lambda: StateVector(17))
+    err("data_shape", lambda: setattr(StateVector(2), "data", np.zeros(3, dtype=complex)))
+    err("qubit_range", lambda: StateVector(2).apply_gate(np.eye(2, dtype=complex), [2]))
+    err("qubit_negative", lambda: StateVector(2).apply_gate(np.eye(2, dtype=complex), [-1]))
+    err("unknown_gate", lambda: Simulator().run(circuit(2, [("Nope", [0], [], 0)]), shots=0))
+    err("noise_p", lambda: DepolarizingNoise(1.5))
+    err("noise_p_neg", lambda: AmplitudeDampingNoise(-0.1))
+    err("readout_p", lambda: ReadoutError(2.0, 0.0))
+    JE["errors"] = errs
+    JE["_meta"] = {"numpy": np.__version__, "generator": "tests/golden/make_golden.py --edges"}
+    with open(os.path.join(HERE, "golden_edges.json"), "w") as f:
+        json.dump(JE, f, indent=1)
+    np.savez_compressed(os.path.join(HERE, "golden_edges.npz"), **AE)
+    print("edge-case golden written:", len(JE), "json entries,", len(AE), "arrays")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--debugger", action="store_true", help="only (re)write golden_debugger.*")
+    ap.add_argument("--edges", action="store_true", help="only (re)write golden_edges.*")
     ap.add_argument("--slow", action="store_true")
     ap.add_argument("--only-slow", action="store_true")
     args = ap.parse_args()
     if args.debugger:
         case_debugger()
+        return
+    if args.edges:
+        case_edges()
         return
     if not args.only_slow:
         for fn in (case_ghz3, case_sigma, case_random_circuits, case_layered16, case_noisy,
