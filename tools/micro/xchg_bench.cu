@@ -152,6 +152,52 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(256, 1) xchg(int rep
 #pragma unroll
         for (int e = 0; e < REGS; ++e) tile[base + e * T + tid] = val[e];
       }
+    } else if (V == 10) {
+      // swap by halves: each CTA of a pair swaps HALF of the groups in both directions (remote load + remote store),
+      // so 32 KB flow in and 32 KB flow out per CTA instead of 64 KB in; no barrier between load and store
+      const int lb = chunk_bytes;
+      const int mine = (int)(rank > (uint32_t)peer);              // which half of the groups this CTA handles
+      c128 vr[8], vl[8];
+      cl_sync();
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        int g = 2 * (e * T + tid) + mine;                          // interleaved split of the 4096 groups
+        int b = (((g >> lb) << (lb + 1)) | (g & ((1 << lb) - 1)));
+        int isrc = b | (mybit << lb), idst = b | ((1 - mybit) << lb);
+        vr[e] = ld_cluster(peer_tile + 16u * (isrc ^ ((isrc >> 3) & 7)));
+        vl[e] = tile[idst ^ ((idst >> 3) & 7)];
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        int g = 2 * (e * T + tid) + mine;
+        int b = (((g >> lb) << (lb + 1)) | (g & ((1 << lb) - 1)));
+        int isrc = b | (mybit << lb), idst = b | ((1 - mybit) << lb);
+        tile[idst ^ ((idst >> 3) & 7)] = vr[e];
+        st_cluster(peer_tile + 16u * (isrc ^ ((isrc >> 3) & 7)), vl[e]);
+      }
+      cl_sync();
+    } else if (V == 11) {
+      // rank-bit flush by halves: a' and b' for half of the indices, one remote load + one remote store each
+      const int mine = (int)(rank > (uint32_t)peer);
+      const c128 p00 = make_double2(0.6, 0.1), p01 = make_double2(0.3, -0.2), p10 = make_double2(-0.3, -0.2), p11 = make_double2(0.6, -0.1);
+      cl_sync();
+      for (int base = 0; base < HALF; base += 8 * T) {
+        c128 va[8], vb[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          int i = mine * HALF + base + e * T + tid;
+          va[e] = tile[i];
+          vb[e] = ld_cluster(peer_tile + 16u * i);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          int i = mine * HALF + base + e * T + tid;
+          c128 a = va[e], b = vb[e];
+          tile[i] = make_double2(p00.x * a.x - p00.y * a.y + p01.x * b.x - p01.y * b.y, p00.x * a.y + p00.y * a.x + p01.x * b.y + p01.y * b.x);
+          st_cluster(peer_tile + 16u * i, make_double2(p10.x * a.x - p10.y * a.y + p11.x * b.x - p11.y * b.y, p10.x * a.y + p10.y * a.x + p11.x * b.y + p11.y * b.x));
+        }
+      }
+      cl_sync();
     } else if (V == 2) {
       cl_sync();
       c128 val[REGS];
@@ -202,6 +248,8 @@ int main() {
       for (int lb : {0, 1, 2, 3, 5, 8, 12}) run<4>("exec-remap", gb, lb, grid);
       run<6>("exec-gflush", gb, 0, grid);
       for (int lb : {0, 3, 12}) run<5>("remap-mbar", gb, lb, grid);
+      for (int lb : {0, 3, 12}) run<10>("swap-halves", gb, lb, grid);
+      run<11>("gflush-halves", gb, 0, grid);
       run<8>("4x mbar sync", gb, 0, grid);
       run<9>("4x hw sync", gb, 0, grid);
     }
