@@ -545,6 +545,30 @@ class QECSimulator:
             results.append(self._point(p, r, n_trials))
         return results
 
+    def threshold_sweep_sharded(self, noise_probs: list, n_trials: int = 100, noise_type: str = "bit_flip", seed=None,
+                                _run_cycles=None) -> list:
+        """`threshold_sweep` with the trials of every point split over the ranks of the default process group (one
+        process per GPU, launched by torchrun).  The seed chain is sequential (qec.py:574-586), so every rank walks the
+        whole chain and keeps its contiguous slice; the per-trial scalars meet in one gather per point and every rank
+        sums them in trial order -- the result equals the single-process sweep bit for bit.  No data-path collective.
+        `_run_cycles` lets the CPU gloo test stand in for the device (tests only)."""
+        from qsb import distributed as D
+        world, rank = D.world_info()
+        run = _run_cycles or self.run_cycles
+        rng = np.random.default_rng(seed)
+        results = []
+        for p in noise_probs:
+            seeds = [int(rng.integers(0, 2 ** 63)) for _ in range(n_trials)]
+            lo, hi = D.shard_bounds(n_trials, world, rank)
+            r = run([t % 2 for t in range(lo, hi)], noise_type, p, seeds[lo:hi]) if hi > lo else \
+                {"fidelity_after": np.empty(0), "z_exp": np.empty(0), "logical_error": np.empty(0, dtype=bool)}
+            packed = np.stack([np.asarray(r["fidelity_after"], dtype=np.float64), np.asarray(r["z_exp"], dtype=np.float64),
+                               np.asarray(r["logical_error"], dtype=np.float64)], axis=1).reshape(-1)
+            allp = D.gather_concat(packed).reshape(n_trials, 3)
+            merged = {"fidelity_after": allp[:, 0], "z_exp": allp[:, 1], "logical_error": allp[:, 2] != 0.0}
+            results.append(self._point(p, merged, n_trials))
+        return results
+
     @staticmethod
     def _point(p, r, n_trials):
         # the reference accumulates trial by trial in Python floats; do the same so the sums round identically

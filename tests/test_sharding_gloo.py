@@ -145,3 +145,41 @@ def test_world2_gloo_sharded_state_with_qubit_exchanges():
         assert p.exitcode == 0
     assert n_ex >= 1
     assert err < 1e-12
+
+
+def _qec_worker(rank, world, port, out_q):
+    """threshold_sweep_sharded with the device stood in for by the oracle's cycle (the sharding, the seed chain and
+    the gather are what is under test)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from quantum_sim.engine.qec import QECSimulator, SteaneCode
+
+    def run_cycles(logicals, noise_type, p, seeds):
+        rs = [O.qec_cycle("steane", l, noise_type, p, s) for l, s in zip(logicals, seeds)]
+        return {"fidelity_after": np.array([r["fidelity_after"] for r in rs]), "z_exp": np.array([r["z_exp"] for r in rs]),
+                "logical_error": np.array([r["logical_error"] for r in rs], dtype=bool)}
+
+    sim = QECSimulator.__new__(QECSimulator)          # no device: only the sharded driver is exercised
+    sim._code = None
+    pts = sim.threshold_sweep_sharded([0.02, 0.1], n_trials=9, noise_type="depolarizing", seed=42, _run_cycles=run_cycles)
+    if rank == 0:
+        out_q.put([(pt.physical_rate, pt.logical_rate, pt.success_rate, pt.avg_fidelity, pt.logical_z_fidelity,
+                    pt.decoder_success_rate, pt.projection_logical_rate) for pt in pts])
+    dist.destroy_process_group()
+
+
+def test_world2_gloo_sharded_threshold_sweep_is_bit_identical():
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_qec_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    want = O.threshold_sweep("steane", [0.02, 0.1], 9, "depolarizing", 42)       # single loop, odd trial count
+    for g, w in zip(got, want):
+        assert g == (w["physical_rate"], w["logical_rate"], w["success_rate"], w["avg_fidelity"], w["logical_z_fidelity"],
+                     w["decoder_success_rate"], w["projection_logical_rate"])
