@@ -63,6 +63,8 @@ def gather_concat(array: np.ndarray, device=None):
     if world == 1:
         return array
     t = torch.from_numpy(np.ascontiguousarray(array))
+    if device is None and dist.get_backend() == "nccl":     # NCCL moves device tensors only
+        device = torch.device("cuda", torch.cuda.current_device())
     if device is not None:
         t = t.to(device)
     sizes = torch.zeros(world, dtype=torch.int64, device=t.device)
