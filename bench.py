@@ -44,6 +44,9 @@ def algorithmic_bytes_per_trajectory(n, gates, k_pauli, k_ad):
 # DRAM bytes one trajectory really moves (ncu dram__bytes_read.sum + dram__bytes_write.sum of the trajectory
 # kernel divided by its trajectories: profiles/r01f_traj_kernel_ncu_full_traj480.csv, 466.2 MB / 480)
 MEASURED_DRAM_BYTES_PER_TRAJECTORY = (11251712 + 454993152) / 480
+# shared-memory wavefronts (128 B each) one trajectory costs, same capture
+# (l1tex__data_pipe_lsu_wavefronts_mem_shared.sum = 3 437 491 693 per 480 trajectories)
+MEASURED_SMEM_WAVEFRONTS_PER_TRAJECTORY = 3437491693 / 480
 
 
 def measured_peak():
@@ -305,7 +308,16 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": alg_bytes * T, "kernel_ms": kms,
                          "note": "trajectories are resident in cluster shared memory; algorithmic bytes count "
                                  "every gate/Kraus sweep (SURVEY 8d), real DRAM traffic is ~1 MiB/trajectory "
-                                 "(see profiles/), so frac > 1 is expected"},
+                                 "(see profiles/), so frac > 1 is expected; `onchip` is the physical bound",
+                         # where the kernel really stands: shared-memory bytes per SM-clock against 128 B/clk/SM
+                         "onchip": (lambda clk_hz, sms: {
+                             "bound": "shared memory", "unit": "B/clk/SM", "peak": 128.0,
+                             "achieved": MEASURED_SMEM_WAVEFRONTS_PER_TRAJECTORY * 128.0 * T / (kms * 1e-3 * clk_hz * sms),
+                             "frac": MEASURED_SMEM_WAVEFRONTS_PER_TRAJECTORY * T / (kms * 1e-3 * clk_hz * sms),
+                             "sms_holding_clusters": sms, "sm_mhz": clk_hz / 1e6,
+                             "source": "ncu shared-memory wavefronts per trajectory (profiles/r01f_*) x trajectories / "
+                                       "(kernel time x SM clock x SMs that can hold clusters of 8)"})(
+                             float(clocks.get("sm_mhz") or 1965.0) * 1e6, 120)},
             "e2e": {"value": e2e_value, "unit": "trajectories/s",
                     "h2d_bytes_per_step": e2e_T * (D + 1) * 8, "d2h_bytes_per_step": e2e_T * 8,
                     "api": "quantum_sim.engine.simulator.Simulator.run_with_noise", "shots": e2e_T,
