@@ -239,6 +239,15 @@ int qsb_rho_accumulate(qsb_ctx* ctx, int32_t n, qsb_buffer* states, int64_t firs
 int qsb_readout_transform(qsb_ctx* ctx, int32_t n, qsb_buffer* probs, int64_t count,
                           double p01, double p10);
 
+/* StateVector.apply_gate for a dense k-qubit operator with k > 3 that is not a Kronecker product
+ * (state_vector.py:41-74 accepts any k; every registered gate has k <= 3 and Pauli strings factorise, so this is the
+ * rare path): out-of-place on states at rest, target_bits[j] = index bit (n-1-qubit) of targets[j], matrix =
+ * complex128[2^k][2^k] on the host (targets[0] = most significant bit of its index), out_perm[b] = destination bit
+ * of index bit b (the reference's axis scramble) or NULL for none.  1 <= k <= min(n, 8). */
+int qsb_apply_dense(qsb_ctx* ctx, int32_t n, qsb_buffer* in, int64_t first, int64_t count, qsb_buffer* out,
+                    int64_t out_first, int32_t k, const int32_t* target_bits, const double* matrix,
+                    const int32_t* out_perm);
+
 #ifdef __cplusplus
 }
 #endif

@@ -954,4 +954,48 @@ int qsb_readout_transform(qsb_ctx* ctx, int32_t n, qsb_buffer* probs, int64_t co
   return after_launch(ctx, "readout_transform");
 }
 
+int qsb_apply_dense(qsb_ctx* ctx, int32_t n, qsb_buffer* in, int64_t first, int64_t count, qsb_buffer* out, int64_t out_first,
+                    int32_t k, const int32_t* target_bits, const double* matrix, const int32_t* out_perm) {
+  CHECK_N(ctx, n);
+  const int64_t dim = (int64_t)1 << n;
+  int rc;
+  if (count <= 0) return count == 0 ? QSB_OK : fail(ctx, QSB_E_INVAL, "negative count");
+  if (k < 1 || k > n || k > 8) return fail(ctx, QSB_E_INVAL, "qsb_apply_dense: k = %d outside [1, min(n, 8)]", k);
+  if (!target_bits || !matrix) return fail(ctx, QSB_E_INVAL, "qsb_apply_dense: NULL argument");
+  if (first < 0 || out_first < 0) return fail(ctx, QSB_E_INVAL, "negative offset");
+  if (in == out) return fail(ctx, QSB_E_INVAL, "qsb_apply_dense works out of place");
+  uint32_t seen = 0;
+  for (int j = 0; j < k; ++j) {
+    if (target_bits[j] < 0 || target_bits[j] >= n || ((seen >> target_bits[j]) & 1u))
+      return fail(ctx, QSB_E_INVAL, "qsb_apply_dense: bad target bit list");
+    seen |= 1u << target_bits[j];
+  }
+  int perm[32];
+  for (int b = 0; b < n; ++b) perm[b] = out_perm ? out_perm[b] : b;
+  if (!is_perm(perm, n)) return fail(ctx, QSB_E_INVAL, "qsb_apply_dense: out_perm is not a permutation");
+  if ((rc = need(ctx, in, (first + count) * dim * ctx->amp_bytes, "input states"))) return rc;
+  if ((rc = need(ctx, out, (out_first + count) * dim * ctx->amp_bytes, "output states"))) return rc;
+  CU(ctx, cudaSetDevice(ctx->device));
+  const size_t mbytes = (size_t)16 << (2 * k);
+  void* scratch = nullptr;
+  CU(ctx, cudaMallocFromPoolAsync(&scratch, mbytes + 64 * sizeof(int), ctx->pool, ctx->stream));
+  int meta[64];
+  for (int j = 0; j < 16; ++j) meta[j] = j < k ? target_bits[j] : 0;
+  for (int b = 0; b < 32; ++b) meta[16 + b] = b < n ? perm[b] : 0;
+  cudaError_t e = cudaMemcpyAsync(scratch, matrix, mbytes, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync((char*)scratch + mbytes, meta, sizeof(int) * 48, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);        // `matrix` and `meta` are borrowed host memory
+  if (e != cudaSuccess) { cudaFreeAsync(scratch, ctx->stream); return fail(ctx, QSB_E_CUDA, "qsb_apply_dense: %s", cudaGetErrorString(e)); }
+  const c128* dM = (const c128*)scratch;
+  const int* dtb = (const int*)((char*)scratch + mbytes);
+  const int* dperm = dtb + 16;
+  const unsigned grid = grid_for(ctx, count * dim, 256);
+  QSB_BY_AMP(ctx, (qsb_dense_kernel<A><<<grid, 256, 0, ctx->stream>>>(
+      (const A*)in->ptr + first * dim, (A*)out->ptr + out_first * dim, n, k, count, dM, dtb, dperm)));
+  ctx->launches += 1;
+  rc = after_launch(ctx, "apply_dense");
+  cudaFreeAsync(scratch, ctx->stream);
+  return rc;
+}
+
 }  // extern "C"

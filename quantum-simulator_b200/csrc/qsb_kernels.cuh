@@ -655,3 +655,44 @@ __global__ void qsb_normalize_dist_kernel(double* __restrict__ p, int64_t dim) {
   if (v[0] > 1e-15)
     for (int64_t i = threadIdx.x; i < dim; i += blockDim.x) q[i] = q[i] / v[0];
 }
+
+
+// Generic dense k-qubit operator on states at rest in HBM (state_vector.py:41-74 for k > 3, where the tile executor
+// has no sweep): out[perm(x)] = sum_c M[r(x)][c] * in[x with the target bits set to c].  tb[j] = index bit of
+// targets[j] (targets[0] is the most significant bit of the matrix index); perm[b] = destination bit of index bit b
+// (the reference's axis scramble, or the identity).  One thread per output amplitude; 2^k loads each come from L2.
+template <class A>
+__global__ void qsb_dense_kernel(const A* __restrict__ in, A* __restrict__ out, int n, int k, int64_t count,
+                                 const c128* __restrict__ M, const int* __restrict__ tb, const int* __restrict__ perm) {
+  __shared__ int s_tb[16], s_perm[32];
+  if (threadIdx.x < k) s_tb[threadIdx.x] = tb[threadIdx.x];
+  if (threadIdx.x < n) s_perm[threadIdx.x] = perm[threadIdx.x];
+  __syncthreads();
+  const int64_t dim = (int64_t)1 << n, total = count * dim;
+  const int D = 1 << k;
+  for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = g >> n;
+    const uint32_t x = (uint32_t)(g & (dim - 1));
+    uint32_t base = x, r = 0;
+    for (int j = 0; j < k; ++j) {
+      const int b = s_tb[j];
+      r = (r << 1) | ((x >> b) & 1u);
+      base &= ~(1u << b);
+    }
+    const A* src = in + t * dim;
+    const c128* row = M + (size_t)r * D;
+    double ax = 0.0, ay = 0.0;
+    for (int c = 0; c < D; ++c) {
+      uint32_t idx = base;
+      for (int j = 0; j < k; ++j) idx |= ((uint32_t)(c >> (k - 1 - j)) & 1u) << s_tb[j];
+      const c128 v = qsb_wide(src[idx]);
+      const c128 mv = row[c];
+      ax = fma(mv.x, v.x, fma(-mv.y, v.y, ax));
+      ay = fma(mv.x, v.y, fma(mv.y, v.x, ay));
+    }
+    uint32_t y = 0;
+    for (int b = 0; b < n; ++b) y |= ((x >> b) & 1u) << s_perm[b];
+    c128 res; res.x = ax; res.y = ay;
+    out[t * dim + y] = qsb_cvt<A>(res);
+  }
+}

@@ -23,7 +23,7 @@ RUN_LOAD, RUN_STORE, RUN_NORMALIZE, RUN_ASYNC, RUN_ACCUM_PROBS, RUN_LOAD_BROADCA
 SYMBOLS = [
     "qsb_version", "qsb_device_count", "qsb_ctx_create", "qsb_ctx_destroy", "qsb_ctx_set_stream",
     "qsb_ctx_sync", "qsb_ctx_set_precision", "qsb_ctx_trim", "qsb_buffer_upload_async",
-    "qsb_event_create", "qsb_event_record", "qsb_event_wait", "qsb_event_free", "qsb_last_error", "qsb_ctx_info", "qsb_timer_start", "qsb_timer_stop",
+    "qsb_event_create", "qsb_event_record", "qsb_event_wait", "qsb_event_free", "qsb_apply_dense", "qsb_last_error", "qsb_ctx_info", "qsb_timer_start", "qsb_timer_stop",
     "qsb_launch_count", "qsb_buffer_alloc", "qsb_buffer_wrap", "qsb_buffer_free", "qsb_buffer_upload",
     "qsb_buffer_download", "qsb_buffer_zero", "qsb_buffer_copy", "qsb_buffer_ptr", "qsb_buffer_bytes",
     "qsb_host_alloc", "qsb_host_free", "qsb_program_create", "qsb_program_free", "qsb_run",
@@ -78,6 +78,7 @@ def load_library():
             "qsb_event_record": (C.c_int, [vp]),
             "qsb_event_wait": (C.c_int, [vp]),
             "qsb_event_free": (C.c_int, [vp]),
+            "qsb_apply_dense": (C.c_int, [vp, i32, vp, i64, i64, vp, i64, i32, P(i32), vp, P(i32)]),
             "qsb_last_error": (C.c_char_p, [vp]),
             "qsb_ctx_info": (C.c_int, [vp, P(i32), P(i32), P(i32), P(i64)]),
             "qsb_timer_start": (C.c_int, [vp]),
@@ -276,6 +277,15 @@ class Context:
     def to_device(self, arr):
         arr = np.ascontiguousarray(arr)
         return self.alloc(max(arr.nbytes, 16)).upload(arr)
+
+    def apply_dense(self, n, states, first, count, out, out_first, target_bits, matrix, out_perm=None):
+        """Dense k-qubit operator (k <= 8) on states at rest, out of place (qsb_apply_dense)."""
+        k = len(target_bits)
+        tb = (C.c_int32 * k)(*[int(b) for b in target_bits])
+        m = np.ascontiguousarray(matrix, dtype=np.complex128).reshape(2 ** k, 2 ** k)
+        perm = (C.c_int32 * n)(*[int(b) for b in out_perm]) if out_perm is not None else None
+        _check(self.lib.qsb_apply_dense(self.handle, n, states.handle, first, count, out.handle, out_first, k, tb,
+                                        _hostptr(m), perm), self.handle)
 
     def trim(self):
         """Give the cached device blocks of this context's pool back to the driver."""

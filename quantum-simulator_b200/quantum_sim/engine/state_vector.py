@@ -12,7 +12,7 @@ from __future__ import annotations
 import numpy as np
 
 from qsb import runtime
-from qsb.compiler import Lowering
+from qsb.compiler import Lowering, sigma, _kron_factors
 
 MAX_QUBITS = 16
 
@@ -112,6 +112,11 @@ class StateVector:
             if q < 0 or q >= n:
                 raise ValueError(f"Qubit index {q} out of range [0, {n-1}]")
         layout = self.layout
+        k = len(targets)
+        if k > 3 and len(set(targets)) == k:
+            mat = np.asarray(gate_matrix, dtype=np.complex128)
+            if mat.size == 4 ** k and _kron_factors(mat.reshape(2 ** k, 2 ** k), k) is None:
+                return self._apply_dense_big(mat.reshape(2 ** k, 2 ** k), targets)
 
         def build():
             lw = Lowering(n, layout=layout)
@@ -120,6 +125,26 @@ class StateVector:
 
         dp = runtime.cached_program(("apply", n, layout, tuple(targets), runtime.matrix_key(gate_matrix)), build)
         runtime.run_single(n, self._device(), dp)
+        self._touched_on_device()
+
+    def _apply_dense_big(self, mat, targets):
+        """k > 3 operator that is not a Kronecker product: one out-of-place pass over the state at rest
+        (`qsb_apply_dense`, k <= 8); the reference's axis scramble rides on the store."""
+        n = self._num_qubits
+        if len(targets) > 8:
+            raise NotImplementedError("dense operators on more than 8 qubits are not supported by the device path")
+        c = runtime.ctx()
+        perm = None
+        if self.layout == "reference":
+            sg = sigma(n, targets)                     # afterwards array axis i holds textbook qubit sg[i]
+            perm = [0] * n
+            for i in range(n):
+                perm[n - 1 - sg[i]] = n - 1 - i
+        src = self._device()
+        out = c.alloc(16 << n)
+        c.apply_dense(n, src, 0, 1, out, 0, [n - 1 - q for q in targets], mat, perm)
+        self._dev = out
+        self._dev_valid = True
         self._touched_on_device()
 
     def measure_qubit(self, qubit: int, rng: np.random.Generator | None = None) -> int:

@@ -115,3 +115,38 @@ def test_error_classes_and_texts(E, edges):
         except Exception as e:                               # noqa: BLE001
             got = [type(e).__name__, str(e)]
         assert got == want, (tag, got, want)
+
+
+@pytest.mark.gpu
+def test_dense_operators_on_more_than_three_qubits(E):
+    """apply_gate with dense k = 4..8 qubit matrices that are not Kronecker products (the reference accepts any k):
+    `qsb_apply_dense`, scramble included, against the real reference (tests/golden/make_golden_densek.py)."""
+    sys_path = os.path.join(HERE, "golden")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_densek", os.path.join(sys_path, "make_golden_densek.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    gold = np.load(os.path.join(sys_path, "golden_densek.npz"))
+    for ci, (n, targets, m, psi) in enumerate(mod.densek_inputs()):
+        sv = sv_of(E, psi, n)
+        sv.apply_gate(m, targets)
+        scale = np.max(np.abs(gold[f"c{ci}_out"]))
+        assert np.max(np.abs(sv.data - gold[f"c{ci}_out"])) < 1e-12 * scale, (n, targets)
+        sv.apply_gate(m.conj().T, targets[::-1])
+        scale = np.max(np.abs(gold[f"c{ci}_out2"]))
+        assert np.max(np.abs(sv.data - gold[f"c{ci}_out2"])) < 1e-12 * scale, (n, targets)
+    # textbook layout: plain tensor action, no scramble
+    n, targets, m, psi = mod.densek_inputs()[1]
+    E.StateVector.layout = "textbook"
+    try:
+        sv = sv_of(E, psi, n)
+        sv.apply_gate(m, targets)
+        t = psi.reshape([2] * n)
+        k = len(targets)
+        want = np.tensordot(m.reshape([2] * (2 * k)), t, axes=(list(range(k, 2 * k)), targets))
+        want = np.moveaxis(want, list(range(k)), targets).reshape(-1)
+        assert np.max(np.abs(sv.data - want)) < 1e-12 * np.max(np.abs(want))
+    finally:
+        E.StateVector.layout = "reference"
+    with pytest.raises(NotImplementedError):
+        sv_of(E, np.ones(2 ** 10) / 32.0, 10).apply_gate(np.random.default_rng(0).normal(size=(512, 512)), list(range(9)))
