@@ -180,6 +180,16 @@ class StateAnalysis:
         sab = _entropy_bits_batch(r2[pair_index(n, qubit_a, qubit_b)][None])[0]
         return float(max(0.0, s[0] + s[1] - sab))
 
+    @staticmethod
+    def concurrence(state: StateVector, qubit_a: int, qubit_b: int) -> float:
+        """Wootters concurrence of the pair (analysis.py:194-219): the 4x4 RDM comes from the device, the 4x4 algebra
+        (spin flip, eigenvalues of rho * rho~) stays on the host like the reference's."""
+        rho = StateAnalysis.partial_trace(state, [qubit_a, qubit_b])
+        flip = np.kron(Y_MATRIX, Y_MATRIX)
+        ev = np.real(np.linalg.eigvals(rho @ (flip @ rho.conj() @ flip)))
+        lam = np.sort(np.sqrt(np.maximum(ev, 0.0)))[::-1]
+        return float(max(0.0, lam[0] - np.sum(lam[1:])))
+
     # ---- expectation values -----------------------------------------------------------------------------
     @staticmethod
     def expectation_value(state: StateVector, observable: np.ndarray, target_qubits: list) -> complex:
@@ -196,3 +206,203 @@ class StateAnalysis:
         if pauli.upper() not in _PAULI:
             raise ValueError(f"Unknown Pauli: {pauli}. Use 'X', 'Y', or 'Z'.")
         return float(np.real(StateAnalysis.expectation_value(state, _PAULI[pauli.upper()], [qubit])))
+
+
+
+# =================================================================================================
+# Entanglement events (analysis.py:255-413): pairwise I(A:B) per step, hysteresis, persistence
+# =================================================================================================
+class EntanglementEventType(Enum):
+    CREATION = "creation"
+    DISENTANGLEMENT = "disentanglement"
+    INCREASE = "increase"
+    DECREASE = "decrease"
+
+
+@dataclass
+class EntanglementEvent:
+    step: int
+    qubit_pair: tuple
+    event_type: EntanglementEventType
+    magnitude: float
+    entropy_before: float
+    entropy_after: float
+
+
+class EntanglementEventDetector:
+    """Same state machine as the reference's detector; the n(n-1)/2 mutual informations of a step come from ONE pass
+    over the state on the device (`all_pairs_mutual_information`) instead of three `partial_trace` calls per pair."""
+
+    def __init__(self, epsilon: float = 0.01, epsilon_on: float | None = None, epsilon_off: float | None = None,
+                 persistence: int = 1):
+        self.epsilon_on = epsilon if epsilon_on is None else epsilon_on
+        self.epsilon_off = epsilon * 0.5 if epsilon_off is None else epsilon_off
+        self.epsilon = epsilon
+        self.persistence = max(1, persistence)
+        self._prev_mi: dict = {}
+        self._entangled: dict = {}
+        self._pending: dict = {}
+        self._pending_type: dict = {}
+        self._events: list = []
+        self._pair_history: dict = {}
+
+    def _classify(self, pair, mi, delta):
+        linked = self._entangled.get(pair, False)
+        if not linked and mi >= self.epsilon_on:
+            return EntanglementEventType.CREATION
+        if linked and mi < self.epsilon_off:
+            return EntanglementEventType.DISENTANGLEMENT
+        if abs(delta) > self.epsilon:
+            return EntanglementEventType.INCREASE if delta > 0 else EntanglementEventType.DECREASE
+        return None
+
+    def process_step(self, state: StateVector, step_index: int) -> list:
+        n = state.num_qubits
+        mis = all_pairs_mutual_information(state)
+        fired = []
+        k = 0
+        for i in range(n):
+            for j in range(i + 1, n):
+                pair, mi = (i, j), float(mis[k])
+                k += 1
+                self._pair_history.setdefault(pair, []).append((step_index, mi))
+                before = self._prev_mi.get(pair, 0.0)
+                delta = mi - before
+                kind = self._classify(pair, mi, delta)
+                if kind is None:
+                    self._pending.pop(pair, None)
+                    self._pending_type.pop(pair, None)
+                else:
+                    if self._pending_type.get(pair) == kind:
+                        self._pending[pair] = self._pending.get(pair, 0) + 1
+                    else:
+                        self._pending[pair] = 1
+                        self._pending_type[pair] = kind
+                    if self._pending.get(pair, 0) >= self.persistence:
+                        if kind is EntanglementEventType.CREATION:
+                            self._entangled[pair] = True
+                        elif kind is EntanglementEventType.DISENTANGLEMENT:
+                            self._entangled[pair] = False
+                        ev = EntanglementEvent(step=step_index, qubit_pair=pair, event_type=kind, magnitude=abs(delta),
+                                               entropy_before=before, entropy_after=mi)
+                        fired.append(ev)
+                        self._events.append(ev)
+                        self._pending[pair] = 0
+                        self._pending_type.pop(pair, None)
+                self._prev_mi[pair] = mi
+        return fired
+
+    def get_timeline(self) -> list:
+        return list(self._events)
+
+    def get_pair_history(self, qa: int, qb: int) -> list:
+        return list(self._pair_history.get((min(qa, qb), max(qa, qb)), []))
+
+    def get_all_pair_histories(self) -> dict:
+        return dict(self._pair_history)
+
+    def reset(self) -> None:
+        # like the reference (analysis.py:409-413): history and last values only; the entangled flags and the
+        # persistence counters survive a reset
+        self._prev_mi.clear()
+        self._events.clear()
+        self._pair_history.clear()
+
+
+# =================================================================================================
+# Shot-count convergence (analysis.py:420-497) and benchmarks (analysis.py:500-621)
+# =================================================================================================
+class ConvergenceAnalysis:
+    @staticmethod
+    def _empirical(ideal_probs, counts, total_shots):
+        dim = len(ideal_probs)
+        width = int(np.log2(dim))
+        emp = np.zeros(dim)
+        for key, c in counts.items():
+            if len(key) == width:
+                try:
+                    emp[int(key, 2)] = c / total_shots
+                except ValueError:
+                    pass
+        return emp
+
+    @staticmethod
+    def tvd(ideal_probs: np.ndarray, empirical_counts: dict, total_shots: int) -> float:
+        """0.5 * sum_i |p_i - count_i / shots|, accumulated in index order like the reference's loop."""
+        emp = ConvergenceAnalysis._empirical(ideal_probs, empirical_counts, total_shots)
+        acc = 0.0
+        for d in np.abs(np.asarray(ideal_probs, dtype=np.float64) - emp).tolist():
+            acc += d
+        return float(0.5 * acc)
+
+    @staticmethod
+    def kl_divergence(ideal_probs: np.ndarray, empirical_counts: dict, total_shots: int, epsilon: float = 1e-10) -> float:
+        """D_KL(ideal || empirical) in bits with epsilon smoothing of the empirical side."""
+        p = np.asarray(ideal_probs, dtype=np.float64)
+        q = ConvergenceAnalysis._empirical(p, empirical_counts, total_shots) + epsilon
+        acc = 0.0
+        for pi, qi in zip(p.tolist(), q.tolist()):
+            if pi >= epsilon:
+                acc += pi * np.log2(pi / qi)
+        return float(max(0.0, acc))
+
+    @staticmethod
+    def shot_convergence(state: StateVector, shot_counts: list, seed: int | None = None) -> list:
+        from .measurement import MeasurementEngine
+        ideal = state.probabilities
+        rng = np.random.default_rng(seed)
+        rows = []
+        for shots in shot_counts:
+            child = np.random.default_rng(rng.integers(0, 2 ** 63))
+            counts = MeasurementEngine.sample(state, shots, rng=child)
+            rows.append({"shots": shots, "tvd": ConvergenceAnalysis.tvd(ideal, counts, shots),
+                         "kl_divergence": ConvergenceAnalysis.kl_divergence(ideal, counts, shots)})
+        return rows
+
+
+class BenchmarkAnalysis:
+    @staticmethod
+    def gate_timing(num_qubits_range, gate_matrix: np.ndarray, target_qubits_func, repetitions: int = 20) -> list:
+        """Wall time of `apply_gate` on a fresh |0..0> per width (includes the device launch and synchronisation)."""
+        import time
+        rows = []
+        for nq in num_qubits_range:
+            targets = target_qubits_func(nq)
+            ms = []
+            for _ in range(repetitions):
+                sv = StateVector(nq)
+                t0 = time.perf_counter()
+                sv.apply_gate(gate_matrix, targets)
+                runtime.ctx().sync()
+                ms.append((time.perf_counter() - t0) * 1000)
+            rows.append({"num_qubits": nq, "mean_time_ms": float(np.mean(ms)), "std_time_ms": float(np.std(ms))})
+        return rows
+
+    @staticmethod
+    def quantum_volume(max_qubits: int = 8, num_trials: int = 100, noise_model: object | None = None,
+                       seed: int | None = None) -> dict:
+        """Heavy-output test on the reference's random Rz-Ry-Rz layer circuits (widths 2..min(max_qubits, 8))."""
+        from .circuit import GateInstance, QuantumCircuit
+        from .simulator import Simulator
+        rng = np.random.default_rng(seed)
+        per_width, best = [], 1
+        for m in range(2, min(max_qubits + 1, 9)):
+            heavy = 0
+            for _ in range(num_trials):
+                qc = QuantumCircuit(num_qubits=m)
+                for col in range(m):
+                    for q in range(m):
+                        a, b, c = rng.uniform(0, 2 * np.pi, 3)
+                        for off, (name, ang) in enumerate((("Rz", a), ("Ry", b), ("Rz", c))):
+                            qc.add_gate(GateInstance(name, [q], [ang], col * 3 + off))
+                ideal = Simulator().run(qc, shots=0).final_state.probabilities
+                actual = ideal if noise_model is None else \
+                    Simulator(noise_model=noise_model).run(qc, shots=0).final_state.probabilities
+                if float(np.sum(actual[ideal > float(np.median(ideal))])) > 2.0 / 3.0:
+                    heavy += 1
+            rate = heavy / num_trials
+            ok = rate > 2.0 / 3.0
+            per_width.append({"width": m, "success_rate": rate, "passed": ok})
+            if ok:
+                best = m
+        return {"quantum_volume": 2 ** best, "log2_qv": best, "results_per_width": per_width}
