@@ -72,6 +72,10 @@ struct DeviceEnv {
     if (CS > 1) return cg::this_cluster().map_shared_rank(tile(), r);
     return tile();
   }
+  __device__ __forceinline__ A* peer_tile_w(int r) {
+    if (CS > 1) return cg::this_cluster().map_shared_rank(tile(), r);
+    return tile();
+  }
   __device__ __forceinline__ const qsb_ctl* peer_ctl(int r) {
     if (CS > 1) return cg::this_cluster().map_shared_rank(ctl(), r);
     return ctl();
