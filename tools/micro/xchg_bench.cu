@@ -161,7 +161,7 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(256, 1) xchg(int rep
       cl_sync();
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        int g = 2 * (e * T + tid) + mine;                          // interleaved split of the 4096 groups
+        int g = mine * (HALF / 2) + e * T + tid;                   // contiguous split of the 4096 groups
         int b = (((g >> lb) << (lb + 1)) | (g & ((1 << lb) - 1)));
         int isrc = b | (mybit << lb), idst = b | ((1 - mybit) << lb);
         vr[e] = ld_cluster(peer_tile + 16u * (isrc ^ ((isrc >> 3) & 7)));
@@ -169,7 +169,7 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(256, 1) xchg(int rep
       }
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        int g = 2 * (e * T + tid) + mine;
+        int g = mine * (HALF / 2) + e * T + tid;
         int b = (((g >> lb) << (lb + 1)) | (g & ((1 << lb) - 1)));
         int isrc = b | (mybit << lb), idst = b | ((1 - mybit) << lb);
         tile[idst ^ ((idst >> 3) & 7)] = vr[e];
