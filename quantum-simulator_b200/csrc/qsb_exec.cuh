@@ -697,13 +697,16 @@ QSB_PASS void qsb_do_remap(Env& env, int m, const qsb_desc* d) {
     constexpr int R = QSB_REMAP_REGS / 2;
     for (int base = 0; base < E; base += R * env.W) {
       const unsigned long long q0 = env.prof_on() ? env.clock() : 0;
+      const bool tiny = E - base < env.W;
       A vl[R], vr[R];
       int mine[R], theirs[R], peer_rank[R];
 #pragma unroll
       for (int e = 0; e < R; ++e) {
         int q = base + e * env.W + env.wid;
         const bool in_range = q < E;
-        q = in_range ? q : E - 1;                     // clamped: the arrays are written unconditionally (see above)
+        // out of range: the arrays are still written unconditionally (see above) -- with this worker's own first
+        // element of the round (nobody else stores there), or the last element when the round is shorter than W
+        q = in_range ? q : (tiny ? E - 1 : base + env.wid);
         const int xv = 1 + (q >> shh);
         int dr = 0, dl = 0;                           // xv spread onto the rank bits / the local bits
 #pragma unroll
@@ -721,7 +724,7 @@ QSB_PASS void qsb_do_remap(Env& env, int m, const qsb_desc* d) {
         vr[e] = env.peer_tile(pr)[theirs[e]];
       }
       const unsigned long long q1 = env.prof_on() ? env.clock() : 0;
-      env.sync_workers();     // the clamped (discarded) loads of a short tile read slots other workers are about to store
+      if (tiny) env.sync_workers();   // the discarded loads read a slot another worker is about to store
       const unsigned long long q2 = env.prof_on() ? env.clock() : 0;
 #pragma unroll
       for (int e = 0; e < R; ++e) {
@@ -792,16 +795,17 @@ QSB_PASS void qsb_do_gflush(Env& env, int m, const qsb_desc* d) {
   constexpr int R = QSB_REMAP_REGS / 2;
   env.cluster_sync_w();
   for (int base = 0; base < half; base += R * env.W) {
+    const bool tiny = half - base < env.W;
     A va[R], vb[R];
 #pragma unroll
     for (int e = 0; e < R; ++e) {
       int i = base + e * env.W + env.wid;
-      i = lo + (i < half ? i : half - 1);                       // clamped, see qsb_do_remap
+      i = lo + (i < half ? i : (tiny ? half - 1 : base + env.wid));   // out of range: see qsb_do_remap
       const A mine = tile[i], theirs = peer[i];                 // same slot on both sides
       va[e] = mybit ? theirs : mine;                            // a lives where the rank bit is clear
       vb[e] = mybit ? mine : theirs;
     }
-    env.sync_workers();       // the clamped (discarded) loads of a short tile read slots other workers are about to store
+    if (tiny) env.sync_workers();     // the discarded loads read a slot another worker is about to store
 #pragma unroll
     for (int e = 0; e < R; ++e) {
       const int j = base + e * env.W + env.wid;
