@@ -42,11 +42,11 @@ def algorithmic_bytes_per_trajectory(n, gates, k_pauli, k_ad):
 
 
 # DRAM bytes one trajectory really moves (ncu dram__bytes_read.sum + dram__bytes_write.sum of the trajectory
-# kernel divided by its trajectories: profiles/r01f_traj_kernel_ncu_full_traj480.csv, 466.2 MB / 480)
-MEASURED_DRAM_BYTES_PER_TRAJECTORY = (11251712 + 454993152) / 480
+# kernel divided by its trajectories: profiles/r01g_traj_kernel_ncu_full_traj480.csv, 468.3 MB / 480)
+MEASURED_DRAM_BYTES_PER_TRAJECTORY = (11614464 + 456644096) / 480
 # shared-memory wavefronts (128 B each) one trajectory costs, same capture
-# (l1tex__data_pipe_lsu_wavefronts_mem_shared.sum = 3 437 491 693 per 480 trajectories)
-MEASURED_SMEM_WAVEFRONTS_PER_TRAJECTORY = 3437491693 / 480
+# (l1tex__data_pipe_lsu_wavefronts_mem_shared.sum = 3 367 032 907 per 480 trajectories)
+MEASURED_SMEM_WAVEFRONTS_PER_TRAJECTORY = 3367032907 / 480
 
 
 def measured_peak():
@@ -303,7 +303,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": f"qsb_traj_kernel<{1 << (prog.n - prog.m)}>",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": MEASURED_DRAM_BYTES_PER_TRAJECTORY * T,
-                         "traffic_source": "ncu dram bytes per trajectory (profiles/r01f_traj_kernel_ncu_full_traj480.csv) x trajectories per launch",
+                         "traffic_source": "ncu dram bytes per trajectory (profiles/r01g_traj_kernel_ncu_full_traj480.csv) x trajectories per launch",
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes * T, "kernel_ms": kms,
                          "note": "trajectories are resident in cluster shared memory; algorithmic bytes count "
@@ -315,7 +315,7 @@ def run_ours(args):
                              "achieved": MEASURED_SMEM_WAVEFRONTS_PER_TRAJECTORY * 128.0 * T / (kms * 1e-3 * clk_hz * sms),
                              "frac": MEASURED_SMEM_WAVEFRONTS_PER_TRAJECTORY * T / (kms * 1e-3 * clk_hz * sms),
                              "sms_holding_clusters": sms, "sm_mhz": clk_hz / 1e6,
-                             "source": "ncu shared-memory wavefronts per trajectory (profiles/r01f_*) x trajectories / "
+                             "source": "ncu shared-memory wavefronts per trajectory (profiles/r01g_*) x trajectories / "
                                        "(kernel time x SM clock x SMs that can hold clusters of 8)"})(
                              float(clocks.get("sm_mhz") or 1965.0) * 1e6, 120)},
             "e2e": {"value": e2e_value, "unit": "trajectories/s",
