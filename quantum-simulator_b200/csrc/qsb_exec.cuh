@@ -735,7 +735,8 @@ QSB_PASS void qsb_do_remap(Env& env, int m, const qsb_desc* d) {
       }
       if (env.prof_on()) { env.prof_add(121, q1 - q0); env.prof_add(122, q2 - q1); env.prof_add(123, env.clock() - q2); env.prof_add(124 + k, 1); }
     }
-    env.cluster_sync_w();                             // nobody sweeps before the peers' stores have landed
+    env.fence_cluster();                              // this worker's remote stores are performed at cluster scope ...
+    env.cluster_sync_w();                             // ... and nobody sweeps before the peers' stores have landed
   }
 #else
   A val[QSB_REMAP_REGS];
@@ -816,6 +817,7 @@ QSB_PASS void qsb_do_gflush(Env& env, int m, const qsb_desc* d) {
       }
     }
   }
+  env.fence_cluster();
   env.cluster_sync_w();                                          // nobody sweeps before the partner's stores landed
 #else
   const A* peer = env.peer_tile(env.rank ^ (1 << gb));

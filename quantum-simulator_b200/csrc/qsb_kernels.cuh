@@ -72,6 +72,7 @@ struct DeviceEnv {
     if (CS > 1) return cg::this_cluster().map_shared_rank(tile(), r);
     return tile();
   }
+  __device__ __forceinline__ void fence_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
   __device__ __forceinline__ A* peer_tile_w(int r) {
     if (CS > 1) return cg::this_cluster().map_shared_rank(tile(), r);
     return tile();
