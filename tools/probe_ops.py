@@ -96,7 +96,6 @@ for n, T in ((13, 148),):
     run("(H, H, CX) x 133", n, h2_cx, T)
     run("certain: (AD H AD, AD, CX) x 80", n, ad_h_ad_cx, T)
     run("400 CX same qubits", n, cx_far, T)
-import sys; sys.exit(0)
 for n, T in ((13, 148), (16, 15)):
     run("empty (init+store)", n, empty, T, nops=1)
     run("400 H (scalar pending path)", n, only_h, T)
