@@ -667,7 +667,7 @@ int qsb_run(qsb_program* p, const qsb_run_args* r) {
 
   CU(ctx, cudaSetDevice(ctx->device));
   const int C = p->tile_bits ? 1 : 1 << (p->n - p->m);
-  int workers = 1 << (p->m > 4 ? p->m - 4 : 1);       // 16 amplitudes per worker per pass
+  int workers = 1 << (p->m > 4 ? p->m - 4 : 1);       // at least 16 amplitudes per worker per pass
   if (workers < 32) workers = 32;
   if (workers > QSB_MAX_WORKERS) workers = QSB_MAX_WORKERS;
   const int threads = workers + QSB_CTL_THREADS + QSB_DEC_THREADS;

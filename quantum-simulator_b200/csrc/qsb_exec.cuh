@@ -70,7 +70,9 @@ struct alignas(8) c64 { float x, y; };
 #define QSB_MAX_LOCAL_BITS_C64 14
 #define QSB_AD_MARGIN 1e-10
 #define QSB_CHUNK 128          // ops staged in shared memory per refill
+#ifndef QSB_REMAP_REGS
 #define QSB_REMAP_REGS 16      // amplitudes a thread stages per remap / rank-bit flush round
+#endif
 #ifndef QSB_GROUP_POS
 #define QSB_GROUP_POS 1        // 1: bank-conflict-free group order (qsb_group_order), 0: ascending free bits
 #endif
@@ -79,6 +81,9 @@ struct alignas(8) c64 { float x, y; };
 #endif
 #ifndef QSB_REMAP_HALVES
 #define QSB_REMAP_HALVES 1     // exchanges as swaps split between the two CTAs of every pair (remote load + remote store)
+#endif
+#ifndef QSB_AMPS
+#define QSB_AMPS 16           // amplitudes a worker keeps in registers per sweep step (K <= 2)
 #endif
 #define QSB_PROF_WORDS 128
 #define QSB_RING 6             // descriptors in flight between control warp and workers
@@ -353,7 +358,7 @@ QSB_PASS void qsb_sweep(Env& env, int m, const qsb_desc* d) {
   A* tile = env.tile();             // re-derived here so device code keeps the shared address space (LDS/STS)
   const unsigned long long sq0 = env.prof_on() ? env.clock() : 0;
   constexpr int D = 1 << K;
-  constexpr int NG = DG ? (K == 2 ? 2 : 1) : (K == 3 ? 1 : 16 / D);
+  constexpr int NG = DG ? (K == 2 && QSB_AMPS >= 16 ? 2 : 1) : (K == 3 ? 1 : (QSB_AMPS / D > 0 ? QSB_AMPS / D : 1));
   const int G = d->gate;
   int bits[K], cls[K];
 #pragma unroll

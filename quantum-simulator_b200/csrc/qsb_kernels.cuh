@@ -9,7 +9,9 @@
 
 namespace cg = cooperative_groups;
 
+#ifndef QSB_MAX_WORKERS
 #define QSB_MAX_WORKERS 256
+#endif
 #define QSB_CTL_THREADS 32
 #define QSB_DEC_THREADS 32       // decode warp: stages the op list one chunk ahead of the control warp
 #define QSB_SMEM_EXTRA (sizeof(qsb_ctl))
