@@ -195,6 +195,83 @@ class Simulator:
         final_state = StateVector.from_initial_states(circuit.initial_states)   # placeholder, as in the reference
         return SimulationResult(final_state=final_state, measurement_counts=counts, num_shots=shots, seed=seed)
 
+    # ---- sharded over the ranks of the default process group (one process per GPU, torchrun) ---------------------
+    def _shot_indices(self, circuit, uniforms, measure_u):
+        """Device leg of a shard of shots: trajectories for the rows of `uniforms`, one sampled basis index each."""
+        cnt = len(measure_u)
+        n = circuit.num_qubits
+        c = runtime.ctx()
+        _, states = self._trajectory_batch(circuit, uniforms, cnt)
+        out = c.alloc(max(cnt, 1) * 8)
+        c.sample_index(n, states, 0, cnt, c.to_device(np.ascontiguousarray(measure_u)), out)
+        return out.download(np.int64, (cnt,))
+
+    def run_with_noise_sharded(self, circuit: QuantumCircuit, shots: int = 1024, seed: int | None = None,
+                               rng: np.random.Generator | None = None, _indices_fn=None) -> SimulationResult:
+        """`run_with_noise` with the shots split over the ranks.  Both generators are POSITIONED, not replayed: rank r
+        jumps the noise stream over the lo*d doubles and the measurement stream over the lo doubles that earlier shots
+        consume (PCG64 `advance`), so every shot draws exactly what the reference's single loop gives it
+        (simulator.py:134-145); the per-shot indices meet in one gather and the counts dict is rebuilt in shot order.
+        Identical to `run_with_noise` on one process, key order included.  `_indices_fn` is for the CPU gloo test."""
+        from qsb import distributed as D
+        if self._noise_model is None:
+            return self.run(circuit, shots, seed=seed, rng=rng)
+        world, rank = D.world_info()
+        n = circuit.num_qubits
+        d = self._program(circuit)[0].prog.n_draws if _indices_fn is None else _indices_fn.n_draws
+        lo, hi = D.shard_bounds(shots, world, rank)
+        noise_rng = D.positioned_rng(self._noise_model._rng, lo * d)
+        meas_rng = D.positioned_rng(rng if rng is not None else seed, lo)
+        cnt = hi - lo
+        uniforms = noise_rng.random(cnt * d).reshape(cnt, d) if d else None
+        measure_u = meas_rng.random(cnt)
+        fn = _indices_fn or self._shot_indices
+        idx = np.asarray(fn(circuit, uniforms, measure_u), dtype=np.int64) if cnt else np.zeros(0, dtype=np.int64)
+        all_idx = D.gather_concat(idx)
+        # leave both generators where the single loop would have left them
+        if d:
+            self._noise_model._rng.bit_generator.advance(shots * d)
+        if rng is not None:
+            rng.bit_generator.advance(shots)
+        counts = D.merge_counts_in_shot_order(all_idx, n)
+        final_state = StateVector.from_initial_states(circuit.initial_states)
+        return SimulationResult(final_state=final_state, measurement_counts=counts, num_shots=shots, seed=seed)
+
+    def ensemble_density_matrix_sharded(self, circuit: QuantumCircuit, n_trials: int = 50, seed: int | None = None) -> np.ndarray:
+        """`ensemble_density_matrix` with the trials split over the ranks: every rank walks the child-seed chain
+        (simulator.py:175-182), accumulates its trials on its GPU and ONE all-reduce sums the partial rho's."""
+        import torch
+        from qsb import distributed as D
+        world, rank = D.world_info()
+        rng = np.random.default_rng(seed)
+        n = circuit.num_qubits
+        dim = 2 ** n
+        dp, _ = self._program(circuit)
+        d = dp.prog.n_draws
+        c = runtime.ctx()
+        seeds = [int(rng.integers(0, 2 ** 63)) for _ in range(n_trials)]
+        t_rho = torch.zeros(2 * dim * dim, dtype=torch.float64, device=torch.device("cuda", c.device))
+        torch.cuda.current_stream(t_rho.device).synchronize()
+        rho = c.wrap(t_rho.data_ptr(), 16 * dim * dim)
+        lo_r, hi_r = D.shard_bounds(n_trials, world, rank)
+        chunk = max(1, min(max(hi_r - lo_r, 1), _CHUNK_BYTES // (16 * dim)))
+        for lo in range(lo_r, hi_r, chunk):
+            cnt = min(chunk, hi_r - lo)
+            uniforms = None
+            if d:
+                uniforms = np.empty((cnt, d), dtype=np.float64)
+                for i in range(cnt):
+                    uniforms[i] = np.random.default_rng(seeds[lo + i]).random(d)
+            _, states = self._trajectory_batch(circuit, uniforms, cnt)
+            c.rho_accumulate(n, states, 0, cnt, 1.0 / n_trials, rho)
+        c.sync()
+        D.allreduce_sum_(t_rho)
+        if self._noise_model is not None and n_trials > 0:
+            self._noise_model.set_seed(seeds[-1])
+            if d:
+                self._noise_model._rng.random(d)
+        return t_rho.cpu().numpy().view(np.complex128).reshape(dim, dim)
+
     def ensemble_density_matrix(self, circuit: QuantumCircuit, n_trials: int = 50,
                                 seed: int | None = None) -> np.ndarray:
         """rho = (1/N) sum_i |psi_i><psi_i| over N stochastic trajectories with per-trial child seeds."""

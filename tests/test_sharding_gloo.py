@@ -183,3 +183,51 @@ def test_world2_gloo_sharded_threshold_sweep_is_bit_identical():
     for g, w in zip(got, want):
         assert g == (w["physical_rate"], w["logical_rate"], w["success_rate"], w["avg_fidelity"], w["logical_z_fidelity"],
                      w["decoder_success_rate"], w["projection_logical_rate"])
+
+
+def _rwn_worker(rank, world, port, shots, out_q):
+    """Simulator.run_with_noise_sharded (the product method) with the device leg stood in for by the oracle."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from quantum_sim.engine.circuit import QuantumCircuit, GateInstance
+    from quantum_sim.engine.noise import NoiseModel, DepolarizingNoise
+    from quantum_sim.engine.simulator import Simulator
+    n, gates = 3, ghz(3)
+    noise = {"global": [("depolarizing", 0.1)], "gate": {}}
+    qc = QuantumCircuit(n)
+    for g in gates:
+        qc.add_gate(GateInstance(g[0], list(g[1]), list(g[2]), g[3]))
+    nm = NoiseModel()
+    nm.add_global_noise(DepolarizingNoise(0.1))
+    nm.set_seed(7)
+
+    def indices(circuit, uniforms, measure_u):
+        return [O.measure_all_index(O.run_state(n, gates, None, noise, uniforms[i])[0], measure_u[i])
+                for i in range(len(measure_u))]
+    indices.n_draws = O.draw_count(n, gates, noise)
+
+    sim = Simulator(nm)
+    res = sim.run_with_noise_sharded(qc, shots=shots, seed=42, _indices_fn=indices)
+    # the model's generator ends where the single loop leaves it
+    nxt = float(nm._rng.random())
+    ref = np.random.default_rng(7)
+    ref.random(shots * indices.n_draws)
+    if rank == 0:
+        out_q.put((res.measurement_counts, res.num_shots, nxt == float(ref.random())))
+    dist.destroy_process_group()
+
+
+def test_world2_gloo_run_with_noise_sharded_product_method(golden):
+    j, _ = golden
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_rwn_worker, args=(r, 2, port, 200, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    counts, num, rng_ok = q.get()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert counts == j["ghz3"]["run_with_noise"] and list(counts) == list(j["ghz3"]["run_with_noise"])
+    assert num == 200 and rng_ok
