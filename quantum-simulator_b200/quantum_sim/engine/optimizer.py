@@ -238,6 +238,20 @@ def batch_costs(config: ParameterizedCircuitConfig, cost_fn: Callable, values: n
     return out
 
 
+def batch_costs_sharded(config: ParameterizedCircuitConfig, cost_fn: Callable, values: np.ndarray,
+                        _batch_costs=None) -> np.ndarray:
+    """`batch_costs` with the parameter rows split over the ranks of the default process group (one process per
+    GPU): contiguous row ranges, no data-path collective, one gather of the costs; every rank returns the full
+    vector, equal to the single-process one.  `_batch_costs` lets the CPU gloo test stand in for the device."""
+    from qsb import distributed as D
+    values = np.ascontiguousarray(values, dtype=np.float64).reshape(-1, max(config.num_params, 1))
+    world, rank = D.world_info()
+    lo, hi = D.shard_bounds(values.shape[0], world, rank)
+    fn = _batch_costs or batch_costs
+    mine = np.asarray(fn(config, cost_fn, values[lo:hi]), dtype=np.float64) if hi > lo else np.zeros(0)
+    return D.gather_concat(mine)
+
+
 # ---- gradient estimation ------------------------------------------------------------------------
 class GradientEstimator:
     """Gradients of parameterised circuits (optimizer.py:191-258): all shifted circuits in one batch."""

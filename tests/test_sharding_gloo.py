@@ -231,3 +231,36 @@ def test_world2_gloo_run_with_noise_sharded_product_method(golden):
         assert p.exitcode == 0
     assert counts == j["ghz3"]["run_with_noise"] and list(counts) == list(j["ghz3"]["run_with_noise"])
     assert num == 200 and rng_ok
+
+
+def _costs_worker(rank, world, port, out_q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from quantum_sim.engine.optimizer import batch_costs_sharded
+
+    class Cfg:                                   # only what the sharded driver touches
+        num_params = 3
+
+    def fake(config, cost_fn, rows):             # stands in for the device batch: any row-wise function will do
+        return np.array([cost_fn(r) for r in rows])
+
+    vals = np.random.default_rng(5).uniform(-1, 1, (11, 3))
+    got = batch_costs_sharded(Cfg(), lambda r: float(np.sum(np.cos(r))), vals, _batch_costs=fake)
+    if rank == 1:
+        out_q.put(got)
+    dist.destroy_process_group()
+
+
+def test_world2_gloo_batch_costs_sharded():
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_costs_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    vals = np.random.default_rng(5).uniform(-1, 1, (11, 3))
+    assert np.array_equal(got, np.array([float(np.sum(np.cos(r))) for r in vals]))      # every rank holds all costs
