@@ -133,6 +133,15 @@ typedef struct qsb_run_args {
                                 streamed pass (n - local_bits > 3) stores with a bit permutation other than
                                 the one it loaded with: tiles then read and write different addresses      */
   int64_t out_first;
+  /* Streamed passes on a state sharded over GPUs (config 5): LOAD straight from the peers' shards, which folds the
+   * qubit exchange (rank bits <-> top local bits, the all-to-all of bigstate.py) into the pass that follows it.
+   * peer_table = device array of 2^g device pointers (the peers' shard bases, e.g. from CUDA IPC / torch symmetric
+   * memory), or NULL.  Source element s of the (post-exchange) local shard is read from
+   * peer_table[s >> peer_shift] at offset (s & (2^peer_shift - 1)) | peer_rank_or.  Needs states_out. */
+  qsb_buffer* peer_table;
+  int32_t peer_shift;
+  int32_t reserved2;
+  int64_t peer_rank_or;
 } qsb_run_args;
 
 /* ---- lifecycle --------------------------------------------------------------- */

@@ -655,6 +655,16 @@ int qsb_run(qsb_program* p, const qsb_run_args* r) {
   a.snapshots = (p->n_snapshots > 0 && r->snapshots) ? r->snapshots->ptr : nullptr;
   a.probs_accum = (r->flags & QSB_RUN_ACCUM_PROBS) ? (double*)r->probs_accum->ptr : nullptr;
 
+  a.peer_ptrs = nullptr; a.peer_shift = 0; a.peer_rank_or = 0;
+  if (r->peer_table) {
+    if (!p->tile_bits || !(r->flags & QSB_RUN_LOAD) || !r->states_out || r->count != 1)
+      return fail(ctx, QSB_E_INVAL, "qsb_run: peer_table needs a streamed pass with LOAD, states_out and count = 1");
+    if (r->peer_shift < 1 || r->peer_shift > p->n || r->peer_table->bytes < (int64_t)(sizeof(void*) << (p->n - r->peer_shift)))
+      return fail(ctx, QSB_E_INVAL, "qsb_run: bad peer_shift / peer_table size");
+    a.peer_ptrs = (const void* const*)r->peer_table->ptr;
+    a.peer_shift = r->peer_shift;
+    a.peer_rank_or = r->peer_rank_or;
+  }
   a.prof = ctx->d_prof;
   if (ctx->d_prof) CU(ctx, cudaMemsetAsync(ctx->d_prof, 0, (size_t)8 * 148 * 4 * QSB_PROF_WORDS * sizeof(unsigned long long), ctx->stream));
   a.tile_bits = p->tile_bits;

@@ -112,6 +112,9 @@ struct qsb_exec_args {
   int64_t amp_bytes;      // 16 (complex128) or 8 (complex64): element size of states / snapshots
   double* probs_accum;
   unsigned long long* prof;   // optional cycle counters, QSB_PROF_WORDS per CTA (qsb_debug_profile), or NULL
+  const void* const* peer_ptrs;   // streamed LOAD from the peers' shards (exchange folded into the pass), or NULL
+  int32_t peer_shift;  int32_t pad1;
+  int64_t peer_rank_or;
 };
 
 // ---- descriptors: control warp -> workers ---------------------------------------------
@@ -592,8 +595,17 @@ QSB_PASS void qsb_do_init(Env& env, const qsb_exec_args& a, const qsb_desc* d) {
         const uint32_t x = hi | (uint32_t)(i < (1 << m) ? i : i0);
         s[e] = hoist ? (qsb_permute(tab, x & ~31u) | lo) : qsb_permute(tab, x);
       }
+      if (a.peer_ptrs) {
+        // the shard this tile comes from sits on another GPU: element s of the post-exchange shard = peer
+        // (s >> shift), offset (s & mask) | my rank field -- plain loads over NVLink peer mappings
+        const uint32_t pmask = (1u << a.peer_shift) - 1u;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = src[s[e]];
+        for (int e = 0; e < 8; ++e)
+          v[e] = static_cast<const A*>(a.peer_ptrs[s[e] >> a.peer_shift])[(int64_t)(s[e] & pmask) | a.peer_rank_or];
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = src[s[e]];
+      }
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int i = i0 + e * env.W;

@@ -145,8 +145,12 @@ def exchange_rank_bits(src, dst, group=None):
 class BigState:
     """One n-qubit complex128 state on this rank's GPU (a 2^(n-g) shard when the process group has 2^g ranks)."""
 
-    def __init__(self, n, *, group=None, device=None, layout="reference", local_bits=None, distributed=True):
-        """distributed=False keeps the whole state on this device even when a process group is initialised."""
+    def __init__(self, n, *, group=None, device=None, layout="reference", local_bits=None, distributed=True,
+                 fuse_exchange=True):
+        """distributed=False keeps the whole state on this device even when a process group is initialised.
+        fuse_exchange: fold every qubit exchange into the pass that follows it -- that pass LOADs its tiles straight
+        from the peers' shards over NVLink peer mappings (torch symmetric memory) instead of waiting for an NCCL
+        all-to-all into a second buffer; falls back to the all-to-all when the mappings cannot be set up."""
         import torch
         import torch.distributed as dist
         self.torch = torch
@@ -168,14 +172,47 @@ class BigState:
         torch.cuda.set_device(self.tdev)
         self.ctx.set_stream(torch.cuda.current_stream().cuda_stream)
         dimL = 1 << self.L
-        self.buf = [torch.zeros(2 * dimL, dtype=torch.float64, device=self.tdev), None]
+        self._peer_tables = None
+        if self.world > 1 and fuse_exchange:
+            try:
+                self._setup_symmetric(dimL, dist)
+            except Exception as e:                      # no peer access on this box: keep the NCCL exchange
+                self._peer_tables = None
+                self._symm_error = repr(e)
+        if self._peer_tables is None:
+            self.buf = [torch.zeros(2 * dimL, dtype=torch.float64, device=self.tdev), None]
         self.cur = 0
-        self._wrapped = [self.ctx.wrap(self.buf[0].data_ptr(), dimL * 16), None]
+        self._wrapped = [self.ctx.wrap(self.buf[0].data_ptr(), dimL * 16),
+                         self.ctx.wrap(self.buf[1].data_ptr(), dimL * 16) if self.buf[1] is not None else None]
         self.pos_of = list(range(self.n))        # virtual bit v (= reference-order bit at rest) -> position
         self.bit_of_axis = [self.n - 1 - j for j in range(self.n)]
         if self.rank == 0:
             self.buf[0][0] = 1.0                 # |0...0>
         self.launches = 0
+
+    def _setup_symmetric(self, dimL, dist):
+        """Both shard buffers in symmetric memory; device tables of the peers' base pointers for each."""
+        torch = self.torch
+        import torch.distributed._symmetric_memory as symm
+        grp = self.group if self.group is not None else dist.group.WORLD
+        self.buf, tables = [], []
+        for _ in range(2):
+            t = symm.empty(2 * dimL, dtype=torch.float64, device=self.tdev)
+            h = symm.rendezvous(t, grp.group_name)
+            t.zero_()
+            self.buf.append(t)
+            ptrs = np.array([int(p) for p in h.buffer_ptrs], dtype=np.int64)
+            assert len(ptrs) == self.world and int(ptrs[self.rank]) == t.data_ptr()
+            tables.append(self.ctx.to_device(ptrs))
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        self._peer_tables = tables
+        self._fence = torch.zeros(1, dtype=torch.float32, device=self.tdev)
+
+    def _rank_fence(self):
+        """Stream-ordered barrier over the ranks (a 4-byte all-reduce on the stream the passes run on)."""
+        import torch.distributed as dist
+        dist.all_reduce(self._fence, group=self.group)
 
     # -- buffers ------------------------------------------------------------------------------
     def _other(self):
@@ -203,11 +240,31 @@ class BigState:
         if uniforms is not None:
             u = np.ascontiguousarray(uniforms, dtype=np.float64).reshape(1, -1)
             kw.update(uniforms=self.ctx.to_device(u), uniforms_stride=u.shape[1])
+        pending_exchange = False
         for st in steps:
             if st.kind == "exchange":
-                self._exchange()
+                if self._peer_tables is not None and not pending_exchange:
+                    pending_exchange = True          # folded into the LOAD of the next pass
+                else:
+                    self._exchange()
                 continue
             dp = self.ctx.program(st.prog)
+            if pending_exchange:
+                # every rank has finished writing its shard; then this pass reads the peers' shards directly
+                # (element s of my post-exchange shard = peer s >> (L - g), offset (s & mask) | rank << (L - g))
+                # and stores into my other buffer; nobody may overwrite a shard that a peer is still reading
+                pending_exchange = False
+                o = self._other()
+                self._rank_fence()
+                self.ctx.run(dp, 1, states=self._wrapped[self.cur], load=True, store=True, states_out=self._wrapped[o],
+                             peer_table=self._peer_tables[self.cur], peer_shift=self.L - self.g,
+                             peer_rank_or=self.rank << (self.L - self.g), seed=seed, async_=True, **kw)
+                self._rank_fence()
+                self.cur = o
+                self.launches += 1
+                self.fused_exchanges = getattr(self, "fused_exchanges", 0) + 1
+                self.ctx.sync()
+                continue
             if st.out_of_place:
                 o = self._other()
                 self.ctx.run(dp, 1, states=self._wrapped[self.cur], load=True, store=True, states_out=self._wrapped[o],
@@ -217,6 +274,8 @@ class BigState:
                 self.ctx.run(dp, 1, states=self._wrapped[self.cur], load=True, store=True, seed=seed, async_=True, **kw)
             self.launches += 1
             self.ctx.sync()                        # the program object is freed when `dp` goes out of scope
+        if pending_exchange:                         # an exchange with no pass after it
+            self._exchange()
         # bookkeeping: `moved[p]` = where the data that sat at position p when the program started is now
         self.pos_of = [moved[p] for p in self.pos_of]
         self.bit_of_axis = list(lw.bit_of_axis)

@@ -44,6 +44,7 @@ class RunArgs(C.Structure):
         ("snapshots", C.c_void_p), ("probs_accum", C.c_void_p),
         ("flags", C.c_int32), ("reserved", C.c_int32),
         ("states_out", C.c_void_p), ("out_first", C.c_int64),
+        ("peer_table", C.c_void_p), ("peer_shift", C.c_int32), ("reserved2", C.c_int32), ("peer_rank_or", C.c_int64),
     ]
 
 
@@ -321,7 +322,7 @@ class Context:
     def run(self, dprog, count, *, states=None, first=0, load=False, store=True, params=None, params_stride=0,
             uniforms=None, uniforms_stride=0, seed=0, traj_offset=0, init_basis=None, default_basis=0,
             branches=None, branches_stride=0, snapshots=None, probs_accum=None, async_=False, normalize=None,
-            states_out=None, out_first=0, load_broadcast=False):
+            states_out=None, out_first=0, load_broadcast=False, peer_table=None, peer_shift=0, peer_rank_or=0):
         a = RunArgs()
         a.states = states.handle if states is not None else None
         a.first, a.count = first, count
@@ -338,6 +339,8 @@ class Context:
         a.probs_accum = probs_accum.handle if probs_accum is not None else None
         a.states_out = states_out.handle if states_out is not None else None
         a.out_first = out_first
+        a.peer_table = peer_table.handle if peer_table is not None else None
+        a.peer_shift, a.peer_rank_or = int(peer_shift), int(peer_rank_or)
         norm = dprog.prog.normalize if normalize is None else normalize
         a.flags = ((RUN_LOAD if load else 0) | (RUN_STORE if store and (states is not None or states_out is not None) else 0) |
                    (RUN_NORMALIZE if norm else 0) | (RUN_ASYNC if async_ else 0) |

@@ -17,6 +17,7 @@ def main():
     ap.add_argument("--check-n", type=int, default=22)
     ap.add_argument("--qubits", type=int, default=30)
     ap.add_argument("--depth", type=int, default=20)
+    ap.add_argument("--no-fuse", action="store_true", help="NCCL all-to-all exchanges instead of peer loads folded into the next pass")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -30,7 +31,7 @@ def main():
     # ---- parity against the oracle (reference semantics incl. the axis scramble) at a checkable size
     n = args.check_n
     gl = ordered(n, layered_circuit(n, 3, 7 + n))
-    st = BigState(n)
+    st = BigState(n, fuse_exchange=not args.no_fuse)
     st.apply_gates(gl)
     shard = torch.from_numpy(st.local_shard().view(np.float64).copy()).cuda()
     parts = [torch.empty_like(shard) for _ in range(world)]
@@ -52,7 +53,7 @@ def main():
     # ---- full size, timed on the device (max over ranks)
     n = args.qubits
     gl = ordered(n, layered_circuit(n, args.depth, 2026))
-    st = BigState(n, layout="textbook")
+    st = BigState(n, layout="textbook", fuse_exchange=not args.no_fuse)
     lw = st.lowering()
     from quantum_sim.engine.gate_registry import GateRegistry
     reg = GateRegistry.instance()
@@ -76,7 +77,8 @@ def main():
         ms = float(ms.item())
         out["run"] = {"n": n, "gates": len(gl), "passes": kinds.count("pass"), "reorders": kinds.count("reorder"),
                       "exchanges": kinds.count("exchange"), "ms": ms, "gate_apps_per_s": len(gl) / ms * 1e3,
-                      "algorithmic_GBps_per_gpu": len(gl) * 2 * 16 * 2 ** n / world / ms / 1e6, "norm2": nrm}
+                      "algorithmic_GBps_per_gpu": len(gl) * 2 * 16 * 2 ** n / world / ms / 1e6, "norm2": nrm,
+                      "fused_exchanges": getattr(st, "fused_exchanges", 0), "symm_error": getattr(st, "_symm_error", None)}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
