@@ -131,3 +131,48 @@ def test_streamed_state_inverse_property_26q():
     psi = st.to_reference_order([st.local_shard()])
     assert abs(abs(psi[0]) - 1.0) < 1e-10
     assert np.max(np.abs(psi[1:])) < 1e-10
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("g", [1, 2])
+def test_peer_table_load_folds_the_exchange_into_a_pass(g):
+    """`qsb_run_args.peer_table` on ONE device: 2^g shards stand in for the GPUs of a sharded state.  A streamed pass
+    that loads through the table must equal exchange (rank bits <-> top local bits, the all-to-all of
+    `exchange_rank_bits`) followed by the same pass on the exchanged shard."""
+    from qsb import capi
+    from qsb.lowering import lower_circuit
+    from quantum_sim.engine.circuit import QuantumCircuit, GateInstance
+    from quantum_sim.engine.gate_registry import GateRegistry
+    L, m, world = 11, 5, 1 << g
+    rng = np.random.default_rng(40 + g)
+    shards = rng.normal(size=(world, 2 ** L)) + 1j * rng.normal(size=(world, 2 ** L))
+    gates = layered_circuit(L, 2, 9)
+    qc = QuantumCircuit(L)
+    for x in gates:
+        qc.add_gate(GateInstance(x[0], list(x[1]), list(x[2]), x[3]))
+    plan, _ = lower_circuit(L, qc.get_ordered_gates(), GateRegistry.instance(), local_bits=m, stream=True, layout="textbook")
+    prog = plan.passes[0]
+    ctx = capi.get_context()
+    bufs = [ctx.to_device(np.ascontiguousarray(shards[r])) for r in range(world)]
+    table = ctx.to_device(np.array([b.ptr for b in bufs], dtype=np.int64))
+    dp = ctx.program(prog)
+    chunk = 2 ** (L - g)
+    for r in range(world):
+        # what the all-to-all would leave on rank r: chunk c of the new shard = chunk r of rank c's shard
+        exchanged = np.concatenate([shards[c][r * chunk:(r + 1) * chunk] for c in range(world)])
+        want_buf = ctx.to_device(exchanged)
+        ctx.run(dp, 1, states=want_buf, load=True, store=True)
+        want = want_buf.download(np.complex128, (2 ** L,))
+        out = ctx.alloc(16 << L).zero()
+        ctx.run(dp, 1, states=bufs[r], load=True, store=True, states_out=out, peer_table=table, peer_shift=L - g,
+                peer_rank_or=r << (L - g))
+        got = out.download(np.complex128, (2 ** L,))
+        assert np.array_equal(got, want), (g, r)                # same kernel arithmetic on the same inputs: bit-identical
+    # argument checking: a resident program (no streaming) refuses a peer table
+    from qsb.compiler import Lowering
+    lw = Lowering(4)
+    lw.matrix(np.array([[1, 1], [1, -1]], dtype=np.complex128) / np.sqrt(2), [0])
+    small = ctx.program(lw.finish())
+    st = ctx.alloc(16 << 4).zero()
+    with pytest.raises(ValueError):
+        ctx.run(small, 1, states=st, load=True, store=True, states_out=ctx.alloc(16 << 4), peer_table=table, peer_shift=3)
