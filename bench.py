@@ -375,6 +375,25 @@ def measure_other_paths(ctx, sim, qc16):
     out["config3_ensemble_rho"] = {"qubits": n, "trials": 500, "seconds": dt, "trace": float(np.real(np.trace(rho))),
                                    "purity": float(np.real(np.sum(rho * rho.T))),
                                    "includes": "host draws, 500 trajectories, DMMA rho, 256 MiB d2h"}
+    # the rho accumulation alone (FP64 tensor pipe): rho += (1/N) sum_t psi_t psi_t^dagger over N resident states
+    try:
+        N3 = 2048
+        st3 = ctx.to_device((np.random.default_rng(9).normal(size=(N3, 2 ** n, 2)).view(np.complex128).reshape(N3, 2 ** n)
+                             / np.sqrt(2.0 ** (n + 1))))
+        rho3 = ctx.alloc(16 << (2 * n)).zero()
+        ctx.rho_accumulate(n, st3, 0, N3, 1.0 / N3, rho3)
+        ctx.sync()
+        ctx.timer_start()
+        ctx.rho_accumulate(n, st3, 0, N3, 1.0 / N3, rho3)
+        ms3 = ctx.timer_stop()
+        full = 8.0 * 4.0 ** n * N3 / (ms3 * 1e-3) / 1e12
+        out["config3_rho_kernel"] = {"qubits": n, "states": N3, "ms": ms3, "tflops_full_matrix_convention": full,
+                                     "tflops_executed": full / 2, "fp64_spec_tflops": 37.0, "frac_of_spec": full / 2 / 37.0,
+                                     "note": "Hermitian half computed on DMMA (mma.sync m8n8k4 f64); ncu: DMMA sub-pipe 88 % "
+                                             "active (profiles/r01d_rho_kernel_ncu_full.csv)"}
+        del st3, rho3
+    except Exception as e:
+        out["config3_rho_kernel"] = {"error": repr(e)}
     # config 3, second half: all 66 pair mutual informations of every per-column snapshot of every trajectory
     from quantum_sim.engine.analysis import all_pairs_mutual_information_device
     dp, _ = s12._program(qc, record_steps=True)
