@@ -34,6 +34,19 @@ def cases(draw):
 @settings(max_examples=250, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
 @given(cases())
 def test_random_programs_match_the_oracle(case):
+    _check(case, None)
+
+
+@pytest.mark.gpu
+@settings(max_examples=150, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+@given(cases())
+def test_random_programs_match_the_oracle_on_the_gpu(case):
+    """The same generator through the C ABI and the CUDA kernel (clusters of 1..8 CTAs, tiles of 1..7 bits)."""
+    from gpu_util import gpu_run
+    _check(case, gpu_run)
+
+
+def _check(case, gpu_run):
     n, gbits, seed, n_gates, noisy, workers = case
     rng = np.random.default_rng(seed)
     names = [x for x in ONE + TWO + THREE if x in O._FIXED or x in O.NUM_PARAMS or x in ("CNOT", "CZ", "SWAP", "Toffoli", "Fredkin")]
@@ -57,7 +70,10 @@ def test_random_programs_match_the_oracle(case):
     T = 2
     draws = rng.random((T, max(prog.n_draws, 1)))
     basis = sum(1 << (n - 1 - i) for i, b in enumerate(initial) if b)
-    out = emu_run(prog, count=T, T=workers, uniforms=draws if prog.n_draws else None, default_basis=basis, want_branches=True)
+    if gpu_run is None:
+        out = emu_run(prog, count=T, T=workers, uniforms=draws if prog.n_draws else None, default_basis=basis, want_branches=True)
+    else:
+        out = gpu_run(prog, count=T, uniforms=draws if prog.n_draws else None, default_basis=basis, want_branches=True)
     for t in range(T):
         psi, steps, branches, _ = O.run_state(n, gates, initial, noise, draws[t] if prog.n_draws else None, record_steps=True)
         assert np.max(np.abs(out["states"][t] - psi)) < 1e-12, case
