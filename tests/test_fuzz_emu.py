@@ -46,6 +46,22 @@ def test_random_programs_match_the_oracle_on_the_gpu(case):
     _check(case, gpu_run)
 
 
+@st.composite
+def big_cases(draw):
+    n = draw(st.sampled_from([14, 15, 16]))
+    gbits = n - 13
+    return n, gbits, draw(st.integers(0, 2 ** 31 - 1)), draw(st.integers(15, 45)), draw(st.booleans()), 1
+
+
+@pytest.mark.gpu
+@settings(max_examples=10, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+@given(big_cases())
+def test_random_production_shapes_on_the_gpu(case):
+    """14-16 qubits: 2^13-amplitude tiles, 256 workers, clusters of 2 / 4 / 8 -- the shapes the benchmark runs."""
+    from gpu_util import gpu_run
+    _check(case, gpu_run)
+
+
 def _check(case, gpu_run):
     n, gbits, seed, n_gates, noisy, workers = case
     rng = np.random.default_rng(seed)
