@@ -62,7 +62,17 @@ def test_random_production_shapes_on_the_gpu(case):
     _check(case, gpu_run)
 
 
-def _check(case, gpu_run):
+@pytest.mark.gpu
+@settings(max_examples=80, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+@given(cases())
+def test_random_programs_in_complex64_on_the_gpu(case):
+    """complex64 mode (tolerance 1e-5; a Kraus branch may differ from the complex128 oracle only when a uniform lands
+    within float rounding of a threshold -- such a trajectory is skipped, not compared)."""
+    from gpu_util import gpu_run
+    _check(case, lambda *a, **k: gpu_run(*a, precision="c64", **k), tol=2e-5, strict_branches=False)
+
+
+def _check(case, gpu_run, tol=1e-12, strict_branches=True):
     n, gbits, seed, n_gates, noisy, workers = case
     rng = np.random.default_rng(seed)
     names = [x for x in ONE + TWO + THREE if x in O._FIXED or x in O.NUM_PARAMS or x in ("CNOT", "CZ", "SWAP", "Toffoli", "Fredkin")]
@@ -92,8 +102,11 @@ def _check(case, gpu_run):
         out = gpu_run(prog, count=T, uniforms=draws if prog.n_draws else None, default_basis=basis, want_branches=True)
     for t in range(T):
         psi, steps, branches, _ = O.run_state(n, gates, initial, noise, draws[t] if prog.n_draws else None, record_steps=True)
-        assert np.max(np.abs(out["states"][t] - psi)) < 1e-12, case
         if prog.n_draws:
-            assert out["branches"][t][:len(branches)].tolist() == branches, case
+            same = out["branches"][t][:len(branches)].tolist() == branches
+            assert same or not strict_branches, case
+            if not same:
+                continue
+        assert np.max(np.abs(out["states"][t] - psi)) < tol, case
         if steps is not None and prog.n_snapshots:
-            assert np.max(np.abs(out["snapshots"][t] - np.array(steps))) < 1e-12, case
+            assert np.max(np.abs(out["snapshots"][t] - np.array(steps))) < tol, case
