@@ -57,15 +57,60 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-# ------------------------------------------------------------------------------------ CPU oracle legs
+# ------------------------------------------------------------------------------------ reference (CPU) arm
+# The reference is pure Python + NumPy.  tools/make_baseline_ref.py copies it UNMODIFIED into the git-ignored
+# baseline/_ref/ (it travels to the GPU box with the snapshot); these legs import THAT package -- the reference's
+# own Simulator.run_with_noise (simulator.py:116-153 -> state_vector.py:41-74, noise.py:224-260) -- in worker
+# processes that never import this repo's engine.  If baseline/_ref is missing the oracle port stands in (kind "port").
+REF_ROOT = os.path.join(ROOT, "baseline", "_ref")
+
+
+def reference_available():
+    return os.path.isfile(os.path.join(REF_ROOT, "quantum_sim", "engine", "simulator.py"))
+
+
+def _limit_blas(threads):
+    if threads:
+        os.environ["OPENBLAS_NUM_THREADS"] = str(threads)
+        try:
+            from threadpoolctl import threadpool_limits
+            threadpool_limits(limits=threads)
+        except Exception:
+            pass
+
+
+def _reference_prefix_worker(args):
+    """One noisy trajectory of the first `cols` columns of the headline circuit on the REFERENCE engine:
+    Simulator(noise_model).run_with_noise(circuit, shots=1).  Returns seconds."""
+    cols, seed, blas_threads = args
+    _limit_blas(blas_threads)
+    if REF_ROOT not in sys.path or sys.path.index(REF_ROOT) != 0:
+        sys.path.insert(0, REF_ROOT)
+    import quantum_sim
+    assert os.path.abspath(quantum_sim.__file__).startswith(REF_ROOT), quantum_sim.__file__
+    from quantum_sim.engine.circuit import QuantumCircuit, GateInstance
+    from quantum_sim.engine.noise import NoiseModel, DepolarizingNoise, AmplitudeDampingNoise
+    from quantum_sim.engine.simulator import Simulator
+    from qsb.workloads import layered_circuit
+    qc = QuantumCircuit(N_QUBITS)
+    for name, targets, params, col in layered_circuit(N_QUBITS, DEPTH, CIRCUIT_SEED):
+        if col < cols:
+            qc.add_gate(GateInstance(name, list(targets), list(params), col))
+    nm = NoiseModel()
+    nm.add_global_noise(DepolarizingNoise(0.01))
+    nm.add_global_noise(AmplitudeDampingNoise(0.02))
+    nm.set_seed(seed)
+    sim = Simulator(nm)
+    t0 = time.perf_counter()
+    res = sim.run_with_noise(qc, shots=1, seed=seed)
+    dt = time.perf_counter() - t0
+    assert sum(res.measurement_counts.values()) == 1
+    return dt
+
+
 def _oracle_prefix_worker(args):
-    cols, seed = args
-    os.environ["OPENBLAS_NUM_THREADS"] = "1"
-    try:                                   # forked workers inherit an already initialised BLAS pool: pin it to 1 thread
-        from threadpoolctl import threadpool_limits
-        threadpool_limits(limits=1)
-    except Exception:
-        pass
+    cols, seed, blas_threads = args
+    _limit_blas(blas_threads)
     from oracle import qsim_oracle as O
     from qsb.workloads import layered_circuit, config3_noise
     gates = [g for g in layered_circuit(N_QUBITS, DEPTH, CIRCUIT_SEED) if g[3] < cols]
@@ -76,51 +121,89 @@ def _oracle_prefix_worker(args):
     return time.perf_counter() - t0
 
 
-def cpu_baseline_sample(cols=8, reps=3):
-    """Oracle port, one process / one BLAS thread, on a prefix of `cols` of the 64 columns; trajectories/s
-    extrapolated linearly in depth (every column has the same op mix)."""
-    try:
+def _cpu_worker():
+    return (_reference_prefix_worker, "reference") if reference_available() else (_oracle_prefix_worker, "port")
+
+
+def cpu_baseline_leg():
+    """`bench.py --impl reference --cpu-sample` (a fresh process, started by the GPU arm on rank 0 at N = 1):
+    ONE FULL 16-qubit noisy trajectory (all 64 columns) on one core with one BLAS thread, plus a quarter
+    trajectory with NumPy's default BLAS threading.  Prints one JSON object."""
+    worker, kind = _cpu_worker()
+    worker((2, 1, 1))                                     # warm-up: imports, first-call costs
+    full = worker((DEPTH, 1001, 1))
+    try:                                                  # default threading: lift the limit again
         from threadpoolctl import threadpool_limits
-        limit = threadpool_limits(limits=1)
+        threadpool_limits(limits=os.cpu_count() or 1)
     except Exception:
-        limit = None
-    times = [_oracle_prefix_worker((cols, 1000 + r)) for r in range(reps)]
-    if limit is not None:
-        limit.restore_original_limits()
-    dt = min(times) * DEPTH / cols
-    return {"value": 1.0 / dt, "unit": "trajectories/s", "cores": 1, "kind": "port",
-            "sample": f"{reps} x first {cols}/{DEPTH} columns of one 16-qubit noisy trajectory "
-                      f"(oracle/qsim_oracle.py, NumPy, 1 thread), best time scaled by {DEPTH // cols}"}
+        pass
+    os.environ.pop("OPENBLAS_NUM_THREADS", None)
+    quarter = worker((DEPTH // 4, 1002, 0)) * 4
+    what = ("the UNMODIFIED reference (baseline/_ref): Simulator.run_with_noise(circuit, shots=1)" if kind == "reference"
+            else "oracle/qsim_oracle.py (baseline/_ref missing)")
+    print(json.dumps({"value": 1.0 / full, "unit": "trajectories/s", "cores": 1, "kind": kind,
+                      "sample": f"1 full trajectory of the headline workload (64 columns, 683 gates, 2048 Kraus draws) "
+                                f"on {what}, 1 process, OPENBLAS_NUM_THREADS=1: {full:.2f} s",
+                      "value_default_blas_threads": 1.0 / quarter,
+                      "sample_default_blas_threads": f"first 16/64 columns x 4, 1 process, default BLAS threading "
+                                                     f"({os.cpu_count()} host cores): {quarter:.2f} s per trajectory",
+                      "host_cores": os.cpu_count()}), flush=True)
+
+
+def cpu_baseline_sample():
+    """Run cpu_baseline_leg() in a process of its own (this one has the CUDA engine imported as `quantum_sim`)."""
+    env = {k: v for k, v in os.environ.items() if k not in ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS")}
+    res = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--cpu-sample"],
+                         capture_output=True, text=True, env=env, timeout=600)
+    if res.returncode != 0:
+        return {"error": res.stderr[-400:]}
+    return json.loads(res.stdout.strip().splitlines()[-1])
+
+
+def bench_config(T, world):
+    """The `config` object -- identical in both arms."""
+    return {"workload": WORKLOAD, "n_qubits": N_QUBITS, "gates": 683, "kraus_draws": 2048,
+            "trajectories_per_gpu_per_step": T, "parallelism": f"trajectory shards x{world}",
+            "l2": "256 MiB flush between steps; per-step working set 4 GiB > L2"}
 
 
 def run_reference_arm(args):
-    """`--impl reference`: the CPU path (oracle port -- the reference itself is pure Python and does not
-    travel to the GPU box) on all host cores: one prefix-trajectory per worker process per step."""
+    """`--impl reference`: the reference's own CPU implementation of the path on all host cores -- one worker process
+    per core (the engine's Python layer is single-threaded), one BLAS thread each.  A step = every worker runs the
+    first 16 of the 64 columns of one trajectory through Simulator.run_with_noise; trajectories/s scaled by 4
+    (every column has the same op mix; cpu_baseline times one full trajectory to back that)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.cpu_sample:
+        cpu_baseline_leg()
+        return
     import multiprocessing as mp
-    cols = 4
+    worker, kind = _cpu_worker()
+    cols = 16
     workers = max(1, min(os.cpu_count() or 1, 64))
-    pool = mp.get_context("fork").Pool(workers)
+    pool = mp.get_context("spawn").Pool(workers)
+    pool.map(worker, [(1, w, 1) for w in range(workers)])            # imports in every worker, untimed
     step_times = []
     for s in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        pool.map(_oracle_prefix_worker, [(cols, 10_000 + s * workers + w) for w in range(workers)])
+        pool.map(worker, [(cols, 10_000 + s * workers + w, 1) for w in range(workers)], chunksize=1)
         dt = time.perf_counter() - t0
         if s >= args.warmup:
             step_times.append(dt)
     pool.close()
     ms = 1e3 * sum(step_times) / len(step_times)
     value = workers / (ms * 1e-3 * DEPTH / cols)
-    sample = (f"each step: {workers} worker processes x first {cols}/{DEPTH} columns of one trajectory, "
-              f"scaled by {DEPTH // cols}")
+    what = ("unmodified reference engine from baseline/_ref (Simulator.run_with_noise, shots=1)" if kind == "reference"
+            else "oracle port (baseline/_ref missing)")
+    sample = (f"each step: {workers} worker processes (1 BLAS thread each) x first {cols}/{DEPTH} columns of one "
+              f"trajectory on the {what}, scaled by {DEPTH // cols}")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "trajectories/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "n_qubits": N_QUBITS, "gates": 683, "kraus_draws": 2048},
-            "cpu_baseline": {"value": value, "unit": "trajectories/s", "cores": workers, "kind": "port",
-                             "sample": sample},
+            "config": bench_config(args.traj, args.gpus),
+            "cpu_baseline": {"value": value, "unit": "trajectories/s", "cores": workers, "kind": kind,
+                             "sample": sample, "host_cores": os.cpu_count()},
             "e2e": {"value": value, "unit": "trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -296,10 +379,8 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": "trajectories/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "n_qubits": n, "gates": prog.n_gate_ops, "kraus_draws": D,
-                       "trajectories_per_gpu_per_step": T, "parallelism": f"trajectory shards x{world}",
-                       "l2": "256 MiB flush between steps; per-step working set 4 GiB > L2",
-                       "histogram_total": hist_total},
+            "config": bench_config(T, world),
+            "check": {"histogram_total": hist_total, "gates": prog.n_gate_ops, "kraus_draws": D},
             "roofline": {"bound": "hbm", "kernel": f"qsb_traj_kernel<{1 << (prog.n - prog.m)}>",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": MEASURED_DRAM_BYTES_PER_TRAJECTORY * T,
@@ -499,6 +580,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", action="store_true", help="(internal) print the cpu_baseline object and exit")
     ap.add_argument("--no-extras", action="store_true", help="skip the short secondary measurements (configs 2-5)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -666,7 +666,7 @@ int qsb_run(qsb_program* p, const qsb_run_args* r) {
     a.peer_rank_or = r->peer_rank_or;
   }
   a.prof = ctx->d_prof;
-  if (ctx->d_prof) CU(ctx, cudaMemsetAsync(ctx->d_prof, 0, (size_t)8 * 148 * 4 * QSB_PROF_WORDS * sizeof(unsigned long long), ctx->stream));
+  if (ctx->d_prof) CU(ctx, cudaMemsetAsync(ctx->d_prof, 0, (size_t)8 * ctx->sm_count * 4 * QSB_PROF_WORDS * sizeof(unsigned long long), ctx->stream));
   a.tile_bits = p->tile_bits;
   if (p->tile_bits) {
     if (r->flags & QSB_RUN_NORMALIZE)
@@ -709,7 +709,7 @@ int qsb_run(qsb_program* p, const qsb_run_args* r) {
 int qsb_debug_profile(qsb_ctx* ctx, int enable, unsigned long long* out, int64_t max_ctas) {
   if (!ctx) return fail(nullptr, QSB_E_INVAL, "ctx is NULL");
   CU(ctx, cudaSetDevice(ctx->device));
-  const int64_t cap = 8 * 148 * 4;
+  const int64_t cap = (int64_t)8 * ctx->sm_count * 4;   // every grid qsb_run can launch (<= 8 CTAs x resident units per SM) fits
   if (enable && !ctx->d_prof) {
     CU(ctx, cudaMalloc(&ctx->d_prof, cap * QSB_PROF_WORDS * sizeof(unsigned long long)));
     CU(ctx, cudaMemset(ctx->d_prof, 0, cap * QSB_PROF_WORDS * sizeof(unsigned long long)));
@@ -766,7 +766,9 @@ int qsb_probabilities(qsb_ctx* ctx, int32_t n, qsb_buffer* states, int64_t first
   const int64_t dim = (int64_t)1 << n;
   int rc;
   if (count <= 0) return count == 0 ? QSB_OK : fail(ctx, QSB_E_INVAL, "negative count");
+  if (first < 0) return fail(ctx, QSB_E_INVAL, "negative first");
   if ((rc = need(ctx, states, (first + count) * dim * ctx->amp_bytes, "states"))) return rc;
+  if (out_first < 0) return fail(ctx, QSB_E_INVAL, "negative out_first");
   if ((rc = need(ctx, out, (out_first + count) * dim * 8, "probabilities"))) return rc;
   CU(ctx, cudaSetDevice(ctx->device));
   QSB_BY_AMP(ctx, (qsb_probs_kernel<A><<<grid_for(ctx, count * dim, 256), 256, 0, ctx->stream>>>(
@@ -779,6 +781,7 @@ int qsb_probabilities_sum(qsb_ctx* ctx, int32_t n, qsb_buffer* states, int64_t f
   const int64_t dim = (int64_t)1 << n;
   int rc;
   if (count <= 0) return count == 0 ? QSB_OK : fail(ctx, QSB_E_INVAL, "negative count");
+  if (first < 0) return fail(ctx, QSB_E_INVAL, "negative first");
   if ((rc = need(ctx, states, (first + count) * dim * ctx->amp_bytes, "states"))) return rc;
   if ((rc = need(ctx, out, dim * 8, "probability sum"))) return rc;
   CU(ctx, cudaSetDevice(ctx->device));
@@ -793,6 +796,7 @@ int qsb_sample_index(qsb_ctx* ctx, int32_t n, qsb_buffer* states, int64_t first,
   const int64_t dim = (int64_t)1 << n;
   int rc;
   if (count <= 0) return count == 0 ? QSB_OK : fail(ctx, QSB_E_INVAL, "negative count");
+  if (first < 0) return fail(ctx, QSB_E_INVAL, "negative first");
   if ((rc = need(ctx, states, (first + count) * dim * ctx->amp_bytes, "states"))) return rc;
   if ((rc = need(ctx, uniforms, count * 8, "uniforms"))) return rc;
   if ((rc = need(ctx, out, count * 8, "sample output"))) return rc;
@@ -810,6 +814,7 @@ int qsb_overlap(qsb_ctx* ctx, int32_t n, qsb_buffer* a, int64_t a_first, qsb_buf
   int rc;
   if (count <= 0) return count == 0 ? QSB_OK : fail(ctx, QSB_E_INVAL, "negative count");
   if (b_stride_states != 0 && b_stride_states != 1) return fail(ctx, QSB_E_INVAL, "b_stride_states must be 0 or 1");
+  if (a_first < 0 || b_first < 0) return fail(ctx, QSB_E_INVAL, "negative first");
   if ((rc = need(ctx, a, (a_first + count) * dim * ctx->amp_bytes, "states a"))) return rc;
   if ((rc = need(ctx, b, (b_first + (b_stride_states ? count : 1)) * dim * ctx->amp_bytes, "states b"))) return rc;
   if ((rc = need(ctx, out, count * 16, "overlap output"))) return rc;
@@ -818,7 +823,7 @@ int qsb_overlap(qsb_ctx* ctx, int32_t n, qsb_buffer* a, int64_t a_first, qsb_buf
     // big states: two-stage reduction over many CTAs, one state pair at a time
     const int n_part = ctx->sm_count * 8;
     const int64_t per = (dim + n_part - 1) / n_part;
-    if (!ctx->d_part) CU(ctx, cudaMalloc(&ctx->d_part, sizeof(c128) * 148 * 16));
+    if (!ctx->d_part) CU(ctx, cudaMalloc(&ctx->d_part, sizeof(c128) * (size_t)n_part));
     for (int64_t t = 0; t < count; ++t) {
       QSB_BY_AMP(ctx, (qsb_overlap_partial_kernel<A><<<n_part, 256, 0, ctx->stream>>>(
                           (const A*)a->ptr + (a_first + t) * dim, (const A*)b->ptr + (b_first + t * b_stride_states) * dim,
@@ -857,6 +862,7 @@ int qsb_rdm_all(qsb_ctx* ctx, int32_t n, qsb_buffer* states, int64_t first, int6
   const int npairs = n * (n - 1) / 2;
   int rc;
   if (count <= 0) return count == 0 ? QSB_OK : fail(ctx, QSB_E_INVAL, "negative count");
+  if (first < 0) return fail(ctx, QSB_E_INVAL, "negative first");
   if ((rc = need(ctx, states, (first + count) * dim * ctx->amp_bytes, "states"))) return rc;
   CU(ctx, cudaSetDevice(ctx->device));
   const char* s = (const char*)states->ptr + first * dim * ctx->amp_bytes;
@@ -881,6 +887,7 @@ int qsb_rdm_general(qsb_ctx* ctx, int32_t n, qsb_buffer* states, int64_t first, 
   const int64_t dim = (int64_t)1 << n;
   int rc;
   if (count <= 0) return count == 0 ? QSB_OK : fail(ctx, QSB_E_INVAL, "negative count");
+  if (first < 0) return fail(ctx, QSB_E_INVAL, "negative first");
   if ((rc = need(ctx, states, (first + count) * dim * ctx->amp_bytes, "states"))) return rc;
   if ((rc = need(ctx, out, count * ((int64_t)1 << (2 * k)) * 16, "rdm"))) return rc;
   int host[40];                                     // kept index bits (qubit q = bit n-1-q), then the environment bits
@@ -936,6 +943,7 @@ int qsb_rho_accumulate(qsb_ctx* ctx, int32_t n, qsb_buffer* states, int64_t firs
   const int64_t dim = (int64_t)1 << n;
   int rc;
   if (count <= 0) return count == 0 ? QSB_OK : fail(ctx, QSB_E_INVAL, "negative count");
+  if (first < 0) return fail(ctx, QSB_E_INVAL, "negative first");
   if ((rc = need(ctx, states, (first + count) * dim * ctx->amp_bytes, "states"))) return rc;
   if ((rc = need(ctx, rho, dim * dim * 16, "rho"))) return rc;
   CU(ctx, cudaSetDevice(ctx->device));

@@ -298,7 +298,8 @@ class BigState:
             gd = registry.get(g[0])
             if gd.gate_type.value in ("measurement", "barrier"):
                 continue
-            lw.gate(g[0], list(g[1]), list(g[2]), gd.matrix_func)
+            lw.gate(g[0], list(g[1]), list(g[2]), gd.matrix_func,
+                    builtin=registry.is_builtin(g[0]) if hasattr(registry, "is_builtin") else True)
         self.run(lw)
         return lw.n_gate_ops
 

@@ -134,6 +134,27 @@ def _hostptr(arr):
     return arr.ctypes.data_as(C.c_void_p)
 
 
+class _LockedLib:
+    """libqsb entry points serialised on one lock.  A `qsb_ctx` is single-threaded by contract and ctypes drops the
+    GIL during a call; the reference drives the engine from Qt worker threads (controller/simulation_controller.py:
+    228-256), so the process-wide Context funnels every call of every thread through its lock."""
+
+    def __init__(self, lib, lock):
+        self._lib, self._lock = lib, lock
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+        lock = self._lock
+
+        def call(*args):
+            with lock:
+                return fn(*args)
+
+        call.__name__ = name
+        self.__dict__[name] = call
+        return call
+
+
 class Buffer:
     """Device bytes owned by (or wrapped for) a Context."""
 
@@ -172,7 +193,8 @@ class Buffer:
 
     def free(self):
         if self.handle is not None:
-            self.ctx.lib.qsb_buffer_free(self.handle)
+            if self.ctx.handle is not None:          # a closed context has already released its pool
+                self.ctx.lib.qsb_buffer_free(self.handle)
             self.handle = None
 
     def __del__(self):
@@ -201,7 +223,8 @@ class Event:
     def __del__(self):
         try:
             if self.handle is not None:
-                self.ctx.lib.qsb_event_free(self.handle)
+                if self.ctx.handle is not None:
+                    self.ctx.lib.qsb_event_free(self.handle)
                 self.handle = None
         except Exception:
             pass
@@ -222,7 +245,8 @@ class DeviceProgram:
 
     def free(self):
         if self.handle is not None:
-            self.ctx.lib.qsb_program_free(self.handle)
+            if self.ctx.handle is not None:
+                self.ctx.lib.qsb_program_free(self.handle)
             self.handle = None
 
     def __del__(self):
@@ -233,10 +257,13 @@ class DeviceProgram:
 
 
 class Context:
-    """One CUDA device + stream.  Single-threaded by contract (use one per thread)."""
+    """One CUDA device + stream + memory pool.  The C object is single-threaded by contract; every call made
+    through this wrapper takes `self.lock`, so one Context can be shared by all threads of the process
+    (`get_context`)."""
 
     def __init__(self, device=0):
-        self.lib = load_library()
+        self.lock = threading.RLock()
+        self.lib = _LockedLib(load_library(), self.lock)
         h = C.c_void_p()
         _check(self.lib.qsb_ctx_create(device, C.byref(h)))
         self.handle = h
@@ -416,9 +443,13 @@ class Context:
         _check(self.lib.qsb_readout_transform(self.handle, n, probs.handle, count, p01, p10), self.handle)
 
     def close(self):
-        if self.handle is not None:
-            self.lib.qsb_ctx_destroy(self.handle)
-            self.handle = None
+        """Destroy the C context (stream, events, pool).  Buffers / programs / events still alive afterwards only
+        drop their Python handles (their device memory went with the pool)."""
+        with self.lock:
+            if self.handle is not None:
+                h, self.handle = self.handle, None
+                self._staging.clear()
+                load_library().qsb_ctx_destroy(h)
 
 
 class _Pinned:
@@ -439,7 +470,8 @@ class PinnedArray(np.ndarray):
         self._owner = getattr(obj, "_owner", None)
 
 
-_tls = threading.local()
+_ctx_lock = threading.Lock()
+_contexts = {}          # (device, precision) -> Context, shared by every thread of the process
 
 
 def default_device():
@@ -449,13 +481,32 @@ def default_device():
     return 0
 
 
-def get_context(device=None):
-    """Per-thread, per-device Context (the reference's engine is called from Qt worker threads,
-    controller/simulation_controller.py:228-256; a ctx is single-threaded by contract)."""
+def get_context(device=None, precision="c128"):
+    """The process-wide Context of (device, precision).
+
+    One context per device instead of one per thread: the reference's GUI starts a fresh QThread for every
+    simulation (controller/simulation_controller.py:222-256), and a context per thread would leave a stream, a
+    memory pool with all its cached state batches and a program cache behind for each of them.  Calls are
+    serialised by the context's lock; results created on a worker thread stay valid on any other thread.
+    complex64 users get a context of their own (`precision="c64"`), so the shared complex128 context never changes
+    its element size under the engine classes."""
+    if precision not in ("c128", "c64"):
+        raise ValueError("precision must be 'c128' or 'c64'")
     dev = default_device() if device is None else device
-    cache = getattr(_tls, "ctx", None)
-    if cache is None:
-        cache = _tls.ctx = {}
-    if dev not in cache:
-        cache[dev] = Context(dev)
-    return cache[dev]
+    key = (dev, precision)
+    with _ctx_lock:
+        c = _contexts.get(key)
+        if c is None or c.handle is None:
+            c = Context(dev)
+            if precision == "c64":
+                c.set_precision("c64")
+            _contexts[key] = c
+    return c
+
+
+def close_all():
+    """Destroy every cached context (tests; long-running hosts that want their device memory back)."""
+    with _ctx_lock:
+        for c in list(_contexts.values()):
+            c.close()
+        _contexts.clear()

@@ -212,10 +212,16 @@ class Lowering:
                 self.items.append([U1, [b], self.pool.add(_cplx(f)), -1, -1, None])
         self._advance(targets)
 
-    def gate(self, name, targets, params=(), matrix_func=None):
+    def gate(self, name, targets, params=(), matrix_func=None, builtin=True):
         """One executed GateInstance (simulator.py:110-114).  `matrix_func` is the registry's factory
-        for names this module has no structured form for."""
+        for names this module has no structured form for; `builtin` = the registry still maps `name` to its
+        built-in definition (a re-registered name must run its own matrix, never the structured kernel)."""
         targets = list(targets)
+        if not builtin:
+            if matrix_func is None:
+                raise KeyError(f"Gate '{name}' not found in registry")
+            self.matrix(matrix_func(*params), targets)
+            return
         if name in _STRUCTURED and len(targets) == _STRUCT_ARITY[_STRUCTURED[name]]:
             self._check(targets)
             self.n_gate_ops += 1

@@ -35,10 +35,14 @@ def lower_circuit(n, columns, registry, channels_of=None, *, record_steps=False,
                 continue
             if gtype == "barrier":
                 continue
+            builtin = registry.is_builtin(g.gate_name) if hasattr(registry, "is_builtin") else True
             if param_offsets is not None and id(g) in param_offsets and g.gate_name in _PARAM_COUNT:
+                if not builtin:
+                    raise NotImplementedError(f"gate '{g.gate_name}' was re-registered: its angles cannot be bound on "
+                                              "the device (only the built-in Rx/Ry/Rz/Phase/U3 formulas are)")
                 lw.param_gate(g.gate_name, g.target_qubits, param_offsets[id(g)])
             else:
-                lw.gate(g.gate_name, g.target_qubits, g.params, gd.matrix_func)
+                lw.gate(g.gate_name, g.target_qubits, g.params, gd.matrix_func, builtin=builtin)
             if channels_of is not None:
                 for kind, p, kraus_ops in channels_of(g.gate_name):
                     for q in g.target_qubits:

@@ -13,33 +13,30 @@ import numpy as np
 from . import capi
 from .compiler import Lowering
 
-_tls = threading.local()
 _CACHE_MAX = 256
+_cache_lock = threading.Lock()
+_programs = OrderedDict()       # (device, precision, key) -> DeviceProgram; process-wide like the contexts
 
 
-def ctx():
-    return capi.get_context()
+def ctx(precision="c128"):
+    return capi.get_context(precision=precision)
 
 
-def _cache():
-    c = getattr(_tls, "programs", None)
-    if c is None:
-        c = _tls.programs = OrderedDict()
-    return c
-
-
-def cached_program(key, build):
-    """Device program for `key` (hashable) on this thread's context; `build()` -> compiler.Program."""
-    c = _cache()
-    k = (capi.default_device(), key)
-    dp = c.get(k)
-    if dp is None:
-        dp = ctx().program(build())
-        c[k] = dp
-        if len(c) > _CACHE_MAX:
-            c.popitem(last=False)
-    else:
-        c.move_to_end(k)
+def cached_program(key, build, precision="c128"):
+    """Device program for `key` (hashable) on the process-wide context of this device and precision;
+    `build()` -> compiler.Program.  Evicted programs are freed when their last user drops them."""
+    c = ctx(precision)
+    k = (c.device, precision, key)
+    with _cache_lock:
+        dp = _programs.get(k)
+        if dp is not None and dp.ctx is c and dp.handle is not None:
+            _programs.move_to_end(k)
+            return dp
+    dp = c.program(build())
+    with _cache_lock:
+        _programs[k] = dp
+        if len(_programs) > _CACHE_MAX:
+            _programs.popitem(last=False)
     return dp
 
 

@@ -81,11 +81,15 @@ class StateAnalysis:
         """|<psi|phi>|^2."""
         a = np.ascontiguousarray(psi, dtype=np.complex128).reshape(-1)
         b = np.ascontiguousarray(phi, dtype=np.complex128).reshape(-1)
-        if a.shape != b.shape or a.shape[0] & (a.shape[0] - 1):
-            raise ValueError("state vectors must have the same power-of-two length")
-        n = max(a.shape[0].bit_length() - 1, 1) if a.shape[0] > 1 else 0
-        if n == 0:
-            return float(np.abs(np.vdot(a, b)) ** 2)
+        if a.shape != b.shape:
+            raise ValueError("cannot take the overlap of vectors of different lengths")   # np.vdot raises likewise
+        length = a.shape[0]
+        n = max((length - 1).bit_length(), 1)
+        if length != 1 << n:
+            # the reference takes any pair of equal-length vectors (analysis.py:37-40); zero padding up to the next
+            # power of two leaves vdot unchanged and keeps the arithmetic on the device
+            a = np.concatenate([a, np.zeros((1 << n) - length, dtype=np.complex128)])
+            b = np.concatenate([b, np.zeros((1 << n) - length, dtype=np.complex128)])
         c = runtime.ctx()
         out = c.alloc(16)
         c.overlap(n, c.to_device(a), 0, c.to_device(b), 0, 1, 1, out)

@@ -44,6 +44,8 @@ class GateRegistry:
 
     def __init__(self):
         self._gates: dict[str, GateDefinition] = {}
+        self._builtin_defs: dict[str, GateDefinition] = {}
+        self.generation = 0          # bumped by every register() after the built-ins: keys the device-program caches
 
     @classmethod
     def instance(cls) -> "GateRegistry":
@@ -62,9 +64,20 @@ class GateRegistry:
             self.register(GateDefinition(name=name, display_name=disp, gate_type=typ, num_qubits=nq,
                                          num_params=len(pnames), param_names=pnames, matrix_func=fn,
                                          symbol=sym, color=col, num_controls=nc, num_targets=nt))
+        self._builtin_defs = dict(self._gates)
+        self.generation = 0
 
     def register(self, gate_def: GateDefinition):
         self._gates[gate_def.name] = gate_def
+        self.generation += 1
+
+    def is_builtin(self, name: str) -> bool:
+        """True while `name` still maps to the definition this module registered.  The device compiler only takes its
+        structured kernels (X/Y/Z/CNOT/CZ/SWAP/Toffoli/Fredkin/I, in-kernel Rx/Ry/Rz/Phase/U3) for those; a custom
+        or re-registered gate under a built-in name runs its own `matrix_func(*params)` like in the reference
+        (simulator.py:110-114)."""
+        gd = self._gates.get(name)
+        return gd is not None and gd is self._builtin_defs.get(name)
 
     def get(self, name: str) -> GateDefinition:
         try:

@@ -53,6 +53,15 @@ def readout_shots(counts: dict, readout_error, n: int, rng) -> dict:
     same stream as k scalar calls."""
     if not counts:
         return counts
+    from .noise import ReadoutError
+    if type(readout_error).apply_to_bitstring is not ReadoutError.apply_to_bitstring:
+        # a subclass with its own per-shot corruption: call it shot by shot exactly like measurement.py:121-127
+        out: dict = {}
+        for bitstring, count in counts.items():
+            for _ in range(count):
+                noisy = readout_error.apply_to_bitstring(bitstring, rng)
+                out[noisy] = out.get(noisy, 0) + 1
+        return out
     keys = list(counts.keys())
     reps = np.fromiter((counts[k] for k in keys), dtype=np.int64, count=len(keys))
     bits = np.array([[ch == "1" for ch in k] for k in keys], dtype=bool)

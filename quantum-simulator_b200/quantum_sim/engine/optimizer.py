@@ -101,7 +101,8 @@ class ParameterizedCircuitConfig:
         for gi, slots in by_gate.items():
             g = qc.gates[gi]
             k = _PARAM_COUNT.get(g.gate_name)
-            if k is None or sorted(slots) != list(range(k)) or len(g.target_qubits) != 1:
+            if (k is None or sorted(slots) != list(range(k)) or len(g.target_qubits) != 1
+                    or not GateRegistry.instance().is_builtin(g.gate_name)):
                 return None, None
             offsets[id(g)] = len(row_cols)
             row_cols += [slots[p] for p in range(k)]

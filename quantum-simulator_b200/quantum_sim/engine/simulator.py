@@ -37,7 +37,9 @@ class SimulationResult:
 
 
 def _circuit_key(circuit):
-    return (circuit.num_qubits,
+    # registry generation: any GateRegistry.register() after the built-ins invalidates cached programs (a custom gate
+    # re-registered with a new matrix, or a built-in name overridden, must never hit a stale program)
+    return (circuit.num_qubits, GateRegistry.instance().generation,
             tuple((g.gate_name, tuple(g.target_qubits), tuple(float(p) for p in g.params), g.column)
                   for g in circuit.gates))
 
@@ -113,7 +115,13 @@ class Simulator:
 
     def run_step_by_step(self, circuit: QuantumCircuit,
                          rng: np.random.Generator | None = None) -> Generator:
-        """Yields (state, index) after each non-empty column, starting with (initial, -1)."""
+        """Yields (state, index) after each non-empty column, starting with (initial, -1).
+
+        Evaluation is EAGER where the reference is lazy (simulator.py:93-108): the whole circuit runs as one launch
+        on the first `next()` after the initial state, so all of the noise model's draws are taken from
+        `NoiseModel._rng` at that moment (a caller that interleaves its own draws from that generator between
+        columns sees a different stream), and an unknown gate name in a late column raises before the earlier
+        columns are yielded.  The yielded states and indices are the reference's."""
         yield StateVector.from_initial_states(circuit.initial_states), -1
         n = circuit.num_qubits
         dp, _ = self._program(circuit, record_steps=True)

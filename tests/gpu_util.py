@@ -8,13 +8,9 @@ from qsb import capi
 def gpu_run(prog, count=1, T=None, states=None, params=None, uniforms=None, seed=0, traj_offset=0,
             init_basis=None, default_basis=0, want_branches=False, store=True, accum_probs=False, out_of_place=False,
             precision="c128"):
-    ctx = capi.get_context()
-    ctx.set_precision(precision)
-    try:
-        return _gpu_run(ctx, prog, count, states, params, uniforms, seed, traj_offset, init_basis, default_basis,
-                        want_branches, store, accum_probs, out_of_place)
-    finally:
-        ctx.set_precision("c128")
+    ctx = capi.get_context(precision=precision)      # one process-wide context per (device, precision)
+    return _gpu_run(ctx, prog, count, states, params, uniforms, seed, traj_offset, init_basis, default_basis,
+                    want_branches, store, accum_probs, out_of_place)
 
 
 def _gpu_run(ctx, prog, count, states, params, uniforms, seed, traj_offset, init_basis, default_basis, want_branches,

@@ -276,19 +276,16 @@ def test_c64_noisy_16q_cluster4_and_reductions():
         assert out["branches"][t].tolist() == br
         assert np.max(np.abs(out["states"][t] - psi)) < TOL64
     # reductions on complex64 buffers accumulate in double
-    ctx = capi.get_context()
-    ctx.set_precision("c64")
-    try:
-        psi = out["states"].astype(np.complex64)
-        buf = ctx.to_device(psi)
-        pr = ctx.alloc(3 * 2 ** n * 8)
-        ctx.probabilities(n, buf, 0, 3, pr)
-        assert np.max(np.abs(pr.download(np.float64, (3, 2 ** n)) - np.abs(psi.astype(np.complex128)) ** 2)) < 1e-12
-        ov = ctx.alloc(3 * 16)
-        ctx.overlap(n, buf, 0, buf, 0, 1, 3, ov)
-        assert np.max(np.abs(ov.download(np.complex128, (3,)) - np.sum(np.abs(psi.astype(np.complex128)) ** 2, axis=1))) < 1e-12
-    finally:
-        ctx.set_precision("c128")
+    ctx = capi.get_context(precision="c64")          # complex64 users have a context of their own
+    psi = out["states"].astype(np.complex64)
+    buf = ctx.to_device(psi)
+    pr = ctx.alloc(3 * 2 ** n * 8)
+    ctx.probabilities(n, buf, 0, 3, pr)
+    assert np.max(np.abs(pr.download(np.float64, (3, 2 ** n)) - np.abs(psi.astype(np.complex128)) ** 2)) < 1e-12
+    ov = ctx.alloc(3 * 16)
+    ctx.overlap(n, buf, 0, buf, 0, 1, 3, ov)
+    assert np.max(np.abs(ov.download(np.complex128, (3,)) - np.sum(np.abs(psi.astype(np.complex128)) ** 2, axis=1))) < 1e-12
+    assert capi.get_context().precision == "c128"
 
 
 # ---- REMAP ops that exchange several (rank bit, local bit) pairs in one pass ------------------------------------
