@@ -257,6 +257,67 @@ int qsb_apply_dense(qsb_ctx* ctx, int32_t n, qsb_buffer* in, int64_t first, int6
                     int64_t out_first, int32_t k, const int32_t* target_bits, const double* matrix,
                     const int32_t* out_perm);
 
+/* ---- streamed passes over a state in HBM (n > 16; BASELINE config 5) ---------------------------------------------
+ * StateVector.apply_gate (state_vector.py:41-74) gate by gate on one 2^n state beyond the constructor's 16-qubit cap
+ * (bypassed the way state_vector.py:156-158 does).  A pass = one launch that reads every amplitude once and writes it
+ * once: tiles of 2^m amplitudes are gathered by TMA tensor copies into shared memory (triple buffered: load of tile
+ * j+1 / sweeps of tile j / store of tile j-1 overlap), take every sweep of the pass, and are scattered back.
+ * The host compiler (qsb/stream.py) packs gates into passes, turns every 1-qubit gate into a 2x2 that rides in front
+ * of the next multi-qubit gate on its qubit, and groups consecutive gates whose qubits fit FOUR index bits into one
+ * BLOCK SWEEP: one shared-memory round trip of the tile in which a worker holds the 16 amplitudes of those four bits in
+ * registers and applies the block's whole op list (the round trips, not the arithmetic, bound a pass: ncu, profiles/).
+ *
+ * Slot bits: 0..l-1 = the low index bits (identity: one contiguous 16 * 2^l-byte row); l..l+e-1 ride in the TMA box
+ * as extra dimensions (e <= 3; 16 * 2^(l+e) bytes per TMA op, >= 2 KiB for full bandwidth); l+e..m-1 number the TMA
+ * ops of a tile (m - l - e <= 5); m..n-1 number the tiles.  positions[j] = bit of the amplitude index (of this
+ * device's shard) that slot j stands for.  6 <= m <= 12, 3 <= l, n <= 30.  complex128 only. */
+enum { QSB_CLS_NONE = 0, QSB_CLS_RDIAG = 1 /* diag(1, real) */, QSB_CLS_DIAG = 2, QSB_CLS_DENSE = 3 };
+/* gate applied by a resident-executor sweep after the pending matrices of its bits (internal descriptor field) */
+enum { QSB_G_NONE = 0, QSB_G_CX = 1, QSB_G_CZ = 2, QSB_G_SWAP = 3, QSB_G_CCX = 4, QSB_G_CSWAP = 5, QSB_G_DENSE = 6 };
+/* ops of a block sweep; t[] are LOCAL bits 0..3 of the register block (local bit i = tile slot bit b[i]) */
+enum {
+  QSB_B_MAT1 = 1,     /* 2x2 U (class cls) on local bit t[0]                                           */
+  QSB_B_CX = 2,       /* control t[0], target t[1]                                                    */
+  QSB_B_CZ = 3,       /* t[0], t[1]                                                                   */
+  QSB_B_SWAP = 4,     /* t[0], t[1]                                                                   */
+  QSB_B_CCX = 5,      /* controls t[0] < t[1], target t[2]                                            */
+  QSB_B_CSWAP = 6,    /* control t[0], swapped t[1] < t[2]                                            */
+  QSB_B_DENSE2 = 7,   /* 4x4 at cdata[mat] on local bits (3, 2): local bit 3 = targets[0]              */
+  QSB_B_DENSE3 = 8    /* 8x8 at cdata[mat] on local bits (3, 2, 1)                                     */
+};
+#define QSB_STREAM_MAX_BLOCKS 16
+#define QSB_STREAM_BLOCK_OPS 12
+typedef struct qsb_stream_op {
+  int32_t kind;           /* QSB_B_*                                                                   */
+  int32_t t[3];
+  int32_t cls;            /* QSB_B_MAT1: QSB_CLS_RDIAG | QSB_CLS_DIAG | QSB_CLS_DENSE                  */
+  int32_t pad[3];
+  double U[8];            /* QSB_B_MAT1: row-major (re, im) 2x2                                        */
+} qsb_stream_op;
+typedef struct qsb_stream_block {
+  int32_t n_ops;
+  int32_t b[4];           /* four distinct tile slot bits < m (bits no op uses are filler)             */
+  int32_t mat;            /* offset (doubles, even) of the dense matrix in cdata for DENSE2 / DENSE3 (at most one per block), else -1 */
+  int32_t pad[2];
+  qsb_stream_op ops[QSB_STREAM_BLOCK_OPS];
+} qsb_stream_block;
+typedef struct qsb_stream qsb_stream;
+/* positions_out (NULL = positions): where the store puts slot j -- a pass whose store permutes index positions
+ * (used to bring the qubits that leave in the next exchange to the top local positions) must run out of place. */
+int qsb_stream_create(qsb_ctx* ctx, int32_t n, int32_t m, int32_t l, int32_t e, const int32_t* positions /*[n]*/,
+                      const int32_t* positions_out /*[n] or NULL*/, const qsb_stream_block* blocks,
+                      int32_t n_blocks, const double* cdata, int64_t n_cdata,
+                      qsb_stream** out);
+/* in / out: complex128[>= offset + 2^n] shards (out NULL or == in: in place); offsets in amplitudes, multiples of 8.
+ * flags: QSB_RUN_ASYNC.  With peer_table (see qsb_run_args): tiles are LOADED from the peers' shards -- element s of
+ * this device's post-exchange shard = peer (s >> peer_shift), offset (s & (2^peer_shift - 1)) | peer_rank_or -- which
+ * folds the all-to-all qubit exchange into the pass; peers = host array of 2^(n - peer_shift) device pointers. */
+int qsb_stream_run(qsb_stream* pass, qsb_buffer* in, int64_t in_offset, qsb_buffer* out, int64_t out_offset,
+                   int32_t flags);
+int qsb_stream_run_peers(qsb_stream* pass, const void* const* peers, int32_t n_peers, int32_t peer_shift,
+                         int64_t peer_rank_or, qsb_buffer* out, int64_t out_offset, int32_t flags);
+int qsb_stream_free(qsb_stream* pass);
+
 #ifdef __cplusplus
 }
 #endif

@@ -3,12 +3,14 @@
 // every function that produces numbers launches a kernel from qsb_kernels.cuh.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
 #include <vector>
 
 #include "qsb_kernels.cuh"
+#include "qsb_stream.cuh"
 
 struct qsb_ctx {
   int device;
@@ -1014,6 +1016,314 @@ int qsb_apply_dense(qsb_ctx* ctx, int32_t n, qsb_buffer* in, int64_t first, int6
   rc = after_launch(ctx, "apply_dense");
   cudaFreeAsync(scratch, ctx->stream);
   return rc;
+}
+
+}  // extern "C"
+
+// ---- streamed passes (TMA tile pipeline, qsb_stream.cuh) ---------------------------------------------------------
+struct qsb_stream {
+  qsb_ctx* ctx;
+  qsb_stream_kargs ka;
+  int32_t ebit[3];              // positions of the box's extra dimensions, load side
+  int32_t ebit_out[3];          // ... and store side
+  bool in_place;
+  qsb_blk* d_sweeps;            // block list with group orders for 256 workers per group ...
+  qsb_blk* d_sweeps128;         // ... and for 128
+  c128* d_mats;                 // dense 2- / 3-qubit matrices of the pass
+};
+
+typedef CUresult (*qsb_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (libcuda is not linked)
+static qsb_encode_fn tensor_map_encoder() {
+  static qsb_encode_fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (qsb_encode_fn)p;
+    cudaGetLastError();
+  }
+  return fn;
+}
+
+// rank-5 map of a 2^n-amplitude complex128 shard: [16 doubles = 128 B][2^(n-3) chunks][2][2][2]; the box holds one row
+// of 2^l amplitudes times the e extra bit dimensions, swizzled like the executor's tile (SWIZZLE_128B)
+static int stream_map(qsb_ctx* ctx, CUtensorMap* map, void* base, const qsb_stream* s, const int32_t* ebit) {
+  qsb_encode_fn enc = tensor_map_encoder();
+  if (!enc) return fail(ctx, QSB_E_UNSUPPORTED, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t gdim[5] = {16, (cuuint64_t)1 << (s->ka.n - 3), 1, 1, 1};
+  cuuint64_t gstride[4] = {128, 128, 128, 128};
+  cuuint32_t box[5] = {16, (cuuint32_t)1 << (s->ka.l - 3), 1, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  for (int j = 0; j < s->ka.e; ++j) {
+    gdim[2 + j] = 2;
+    gstride[1 + j] = (cuuint64_t)16 << ebit[j];
+    box[2 + j] = 2;
+  }
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ctx, QSB_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return QSB_OK;
+}
+
+extern "C" {
+
+int qsb_stream_create(qsb_ctx* ctx, int32_t n, int32_t m, int32_t l, int32_t e, const int32_t* positions,
+                      const int32_t* positions_out, const qsb_stream_block* blocks, int32_t n_blocks, const double* cdata,
+                      int64_t n_cdata, qsb_stream** out) {
+  if (!ctx || !out || !positions) return fail(ctx, QSB_E_INVAL, "qsb_stream_create: NULL argument");
+  *out = nullptr;
+  if (ctx->amp_bytes != 16) return fail(ctx, QSB_E_UNSUPPORTED, "streamed passes are complex128 only");
+  if (n < 6 || n > 30) return fail(ctx, QSB_E_INVAL, "streamed pass: n = %d outside [6, 30]", n);
+  if (m < 6 || m > QSB_ST_MAX_TILE_BITS || m > n || l < 3 || e < 0 || e > 3 || l + e > m || m - l - e > 5)
+    return fail(ctx, QSB_E_INVAL, "streamed pass: bad tile geometry n=%d m=%d l=%d e=%d", n, m, l, e);
+  if (n_blocks < 0 || n_blocks > QSB_ST_MAX_SWEEPS || (n_blocks > 0 && !blocks))
+    return fail(ctx, QSB_E_INVAL, "streamed pass: %d block sweeps (at most %d per pass)", n_blocks, QSB_ST_MAX_SWEEPS);
+  if (!is_perm(positions, n)) return fail(ctx, QSB_E_INVAL, "streamed pass: positions is not a permutation of 0..n-1");
+  if (!positions_out) positions_out = positions;
+  if (!is_perm(positions_out, n)) return fail(ctx, QSB_E_INVAL, "streamed pass: positions_out is not a permutation of 0..n-1");
+  for (int j = 0; j < l; ++j)
+    if (positions[j] != j || positions_out[j] != j)
+      return fail(ctx, QSB_E_INVAL, "streamed pass: the low %d slots must be the low index bits", l);
+  // dense matrices of the pass, packed behind one another (device copy below)
+  std::vector<c128> mats;
+  std::vector<qsb_blk> descs((size_t)(n_blocks > 0 ? n_blocks : 1));
+  std::vector<int64_t> mat_at((size_t)(n_blocks > 0 ? n_blocks : 1), -1);
+  memset((void*)descs.data(), 0, descs.size() * sizeof(qsb_blk));
+  for (int i = 0; i < n_blocks; ++i) {
+    const qsb_stream_block& bk = blocks[i];
+    qsb_blk& d = descs[i];
+    if (bk.n_ops < 0 || bk.n_ops > QSB_ST_BLOCK_OPS) return fail(ctx, QSB_E_INVAL, "block %d: %d ops", i, bk.n_ops);
+    uint32_t used = 0;
+    for (int j = 0; j < 4; ++j) {
+      if (bk.b[j] < 0 || bk.b[j] >= m || ((used >> bk.b[j]) & 1u)) return fail(ctx, QSB_E_INVAL, "block %d: bad slot bit", i);
+      used |= 1u << bk.b[j];
+      d.b[j] = bk.b[j];
+    }
+    // The op list must be CANONICAL: a 2x2 on a local bit comes before every gate on that bit (at most one per bit), a
+    // dense gate comes after the 2x2s and before everything else.  Then the 2x2s run in bit order and every
+    // permutation-type gate (CX, SWAP, Toffoli, Fredkin) and sign gate (CZ) is composed here into "register r is stored
+    // to the place of x[r], negated when sign[r] < 0".
+    int x[16], sign[16];
+    for (int r = 0; r < 16; ++r) { x[r] = r; sign[r] = 1; }
+    uint32_t gate_bits = 0, mat_bits = 0;
+    bool after_dense = false;
+    for (int t = 0; t < 4; ++t) {
+      d.cls[t] = QSB_CLS_NONE;
+      d.U[t][0] = d.U[t][3] = qsb_c(1.0, 0.0);
+      d.U[t][1] = d.U[t][2] = qsb_c(0.0, 0.0);
+    }
+    for (int q = 0; q < bk.n_ops; ++q) {
+      const qsb_stream_op& o = bk.ops[q];
+      const int t0 = o.t[0], t1 = o.t[1], t2 = o.t[2];
+      const bool in0 = t0 >= 0 && t0 < 4, in1 = t1 >= 0 && t1 < 4, in2 = t2 >= 0 && t2 < 4;
+      bool ok = false;
+      switch (o.kind) {
+        case QSB_B_MAT1:
+          ok = in0 && o.cls >= QSB_CLS_RDIAG && o.cls <= QSB_CLS_DENSE && !((gate_bits | mat_bits) >> t0 & 1u) && !after_dense;
+          if (ok) {
+            mat_bits |= 1u << t0;
+            d.cls[t0] = o.cls;
+            for (int z = 0; z < 4; ++z) d.U[t0][z] = qsb_c(o.U[2 * z], o.U[2 * z + 1]);
+          }
+          break;
+        case QSB_B_CZ:
+          ok = in0 && in1 && t0 != t1;
+          if (ok) for (int r = 0; r < 16; ++r) if (((x[r] >> t0) & 1) && ((x[r] >> t1) & 1)) sign[r] = -sign[r];
+          if (ok) gate_bits |= (1u << t0) | (1u << t1);
+          break;
+        case QSB_B_CX:
+          ok = in0 && in1 && t0 != t1;
+          if (ok) for (int r = 0; r < 16; ++r) x[r] ^= ((x[r] >> t0) & 1) << t1;
+          if (ok) gate_bits |= (1u << t0) | (1u << t1);
+          break;
+        case QSB_B_SWAP:
+          ok = in0 && in1 && t0 != t1;
+          if (ok) for (int r = 0; r < 16; ++r) {
+            const int ba = (x[r] >> t0) & 1, bb = (x[r] >> t1) & 1;
+            x[r] = (x[r] & ~((1 << t0) | (1 << t1))) | (bb << t0) | (ba << t1);
+          }
+          if (ok) gate_bits |= (1u << t0) | (1u << t1);
+          break;
+        case QSB_B_CCX:
+          ok = in0 && in1 && in2 && t0 < t1 && t2 != t0 && t2 != t1;
+          if (ok) for (int r = 0; r < 16; ++r) x[r] ^= (((x[r] >> t0) & (x[r] >> t1)) & 1) << t2;
+          if (ok) gate_bits |= (1u << t0) | (1u << t1) | (1u << t2);
+          break;
+        case QSB_B_CSWAP:
+          ok = in0 && in1 && in2 && t1 < t2 && t0 != t1 && t0 != t2;
+          if (ok) for (int r = 0; r < 16; ++r) if ((x[r] >> t0) & 1) {
+            const int ba = (x[r] >> t1) & 1, bb = (x[r] >> t2) & 1;
+            x[r] = (x[r] & ~((1 << t1) | (1 << t2))) | (bb << t1) | (ba << t2);
+          }
+          if (ok) gate_bits |= (1u << t0) | (1u << t1) | (1u << t2);
+          break;
+        case QSB_B_DENSE2: case QSB_B_DENSE3: {
+          const int cnt = o.kind == QSB_B_DENSE2 ? 16 : 64;
+          ok = !after_dense && gate_bits == 0;
+          if (ok && (!cdata || bk.mat < 0 || (bk.mat & 1) || bk.mat + 2 * cnt > n_cdata))
+            return fail(ctx, QSB_E_INVAL, "block %d: dense matrix outside cdata", i);
+          if (ok) {
+            after_dense = true;
+            d.dense = o.kind == QSB_B_DENSE2 ? 2 : 3;
+            gate_bits |= o.kind == QSB_B_DENSE2 ? 0xcu : 0xeu;
+            mat_at[i] = (int64_t)mats.size();
+            for (int z = 0; z < cnt; ++z) mats.push_back(qsb_c(cdata[bk.mat + 2 * z], cdata[bk.mat + 2 * z + 1]));
+          }
+          break;
+        }
+        default: break;
+      }
+      if (!ok)
+        return fail(ctx, QSB_E_INVAL, "block %d op %d: kind %d with bits (%d, %d, %d) is invalid or not in canonical order", i, q,
+                    o.kind, t0, t1, t2);
+    }
+    auto tile_off = [&](int v) {
+      int idx = 0;
+      for (int j = 0; j < 4; ++j) idx |= ((v >> j) & 1) << bk.b[j];
+      return (uint32_t)qsb_slot(idx) << 4;
+    };
+    d.neg_mask = 0;
+    for (int r = 0; r < 16; ++r) {
+      d.ld_off[r] = tile_off(r);
+      d.st_off[r] = tile_off(x[r]);
+      if (sign[r] < 0) d.neg_mask |= 1u << r;
+    }
+  }
+  CU(ctx, cudaSetDevice(ctx->device));
+  qsb_stream* s = new qsb_stream();
+  memset(&s->ka, 0, sizeof s->ka);
+  s->ctx = ctx;
+  s->ka.n = n; s->ka.m = m; s->ka.l = l; s->ka.e = e;
+  s->ka.n_sweeps = n_blocks;
+  s->ka.n_ops = 1 << (m - l - e);
+  s->in_place = true;
+  for (int j = 0; j < n; ++j) s->in_place = s->in_place && positions[j] == positions_out[j];
+  for (int j = 0; j < 3; ++j) { s->ebit[j] = j < e ? positions[l + j] : 0; s->ebit_out[j] = j < e ? positions_out[l + j] : 0; }
+  for (int j = 0; j < m - l - e; ++j) { s->ka.op_pos[j] = positions[l + e + j]; s->ka.op_pos_out[j] = positions_out[l + e + j]; }
+  for (int j = 0; j < n - m; ++j) { s->ka.tile_pos[j] = positions[m + j]; s->ka.tile_pos_out[j] = positions_out[m + j]; }
+  s->d_sweeps = s->d_sweeps128 = nullptr;
+  s->d_mats = nullptr;
+  // device copies: dense matrices, then the block list twice (group orders for 256 and for 128 workers per group)
+  const size_t nb = descs.size();
+  cudaError_t er = cudaMalloc(&s->d_sweeps, 2 * nb * sizeof(qsb_blk));
+  if (er == cudaSuccess && !mats.empty()) er = cudaMalloc(&s->d_mats, mats.size() * sizeof(c128));
+  if (er == cudaSuccess && !mats.empty())
+    er = cudaMemcpyAsync(s->d_mats, mats.data(), mats.size() * sizeof(c128), cudaMemcpyHostToDevice, ctx->stream);
+  for (int pass = 0; pass < 2 && er == cudaSuccess; ++pass) {
+    for (int i = 0; i < n_blocks; ++i) {
+      uint32_t used = 0;
+      for (int j = 0; j < 4; ++j) used |= 1u << descs[i].b[j];
+      int hm = 0;
+      descs[i].pos = qsb_group_order(m, used, pass == 0 ? 8 : 7, m - 4, 3, &hm);
+      descs[i].hmask = hm;
+      descs[i].mat = mat_at[i] >= 0 ? s->d_mats + mat_at[i] : nullptr;
+    }
+    er = cudaMemcpyAsync(s->d_sweeps + pass * nb, descs.data(), nb * sizeof(qsb_blk), cudaMemcpyHostToDevice, ctx->stream);
+    if (er == cudaSuccess) er = cudaStreamSynchronize(ctx->stream);        // `descs` is re-used for the second copy
+  }
+  s->d_sweeps128 = s->d_sweeps + nb;
+  if (er != cudaSuccess) {
+    cudaFree(s->d_sweeps);
+    cudaFree(s->d_mats);
+    delete s;
+    cudaGetLastError();
+    return fail(ctx, er == cudaErrorMemoryAllocation ? QSB_E_OOM : QSB_E_CUDA, "streamed pass upload: %s", cudaGetErrorString(er));
+  }
+  s->ka.sweeps = s->d_sweeps;
+  *out = s;
+  return QSB_OK;
+}
+
+static int stream_launch(qsb_stream* s, qsb_stream_maps& maps, int32_t flags) {
+  qsb_ctx* ctx = s->ctx;
+  const size_t smem = qsb_stream_smem_bytes(s->ka.m);
+  static int variant = -1;                 // developer knob: QSB_STREAM_VARIANT=1 -> no dedicated TMA warp
+  if (variant < 0) {
+    const char* v = getenv("QSB_STREAM_VARIANT");
+    variant = (v && atoi(v) == 1) ? 1 : 0;
+    const int full = (int)qsb_stream_smem_bytes(QSB_ST_MAX_TILE_BITS);
+    CU(ctx, cudaFuncSetAttribute(qsb_stream_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, full));
+    CU(ctx, cudaFuncSetAttribute(qsb_stream_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, full));
+  }
+  const int64_t ntiles = (int64_t)1 << (s->ka.n - s->ka.m);
+  const int grid = (int)(ntiles < ctx->sm_count ? ntiles : ctx->sm_count);
+  qsb_stream_kargs ka = s->ka;
+  ka.sweeps = s->d_sweeps128;
+  if (variant == 0) qsb_stream_kernel<128, true><<<grid, 2 * 128 + 32, smem, ctx->stream>>>(maps, ka);
+  else qsb_stream_kernel<128, false><<<grid, 2 * 128, smem, ctx->stream>>>(maps, ka);
+  cudaError_t er = cudaGetLastError();
+  if (er != cudaSuccess) return fail(ctx, QSB_E_CUDA, "streamed pass launch: %s", cudaGetErrorString(er));
+  ctx->launches += 1;
+  if (!(flags & QSB_RUN_ASYNC)) CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return QSB_OK;
+}
+
+int qsb_stream_run(qsb_stream* s, qsb_buffer* in, int64_t in_offset, qsb_buffer* out, int64_t out_offset, int32_t flags) {
+  if (!s || !in) return fail(nullptr, QSB_E_INVAL, "qsb_stream_run: NULL argument");
+  qsb_ctx* ctx = s->ctx;
+  if (!out) { out = in; out_offset = in_offset; }
+  const int64_t dim = (int64_t)1 << s->ka.n;
+  int rc;
+  if (!s->in_place && (char*)in->ptr + in_offset * 16 == (char*)out->ptr + out_offset * 16)
+    return fail(ctx, QSB_E_INVAL, "qsb_stream_run: a pass that stores to other positions than it loads from cannot run in place");
+  if (in_offset < 0 || out_offset < 0 || (in_offset & 7) || (out_offset & 7))
+    return fail(ctx, QSB_E_INVAL, "qsb_stream_run: offsets must be non-negative multiples of 8 amplitudes");
+  if ((rc = need(ctx, in, (in_offset + dim) * 16, "input shard"))) return rc;
+  if ((rc = need(ctx, out, (out_offset + dim) * 16, "output shard"))) return rc;
+  CU(ctx, cudaSetDevice(ctx->device));
+  qsb_stream_maps maps;
+  memset(&maps, 0, sizeof maps);
+  if ((rc = stream_map(ctx, &maps.in[0], (char*)in->ptr + in_offset * 16, s, s->ebit))) return rc;
+  if ((rc = stream_map(ctx, &maps.out, (char*)out->ptr + out_offset * 16, s, s->ebit_out))) return rc;
+  s->ka.peer_shift = 32;
+  s->ka.peer_or = 0;
+  return stream_launch(s, maps, flags);
+}
+
+int qsb_stream_run_peers(qsb_stream* s, const void* const* peers, int32_t n_peers, int32_t peer_shift, int64_t peer_rank_or,
+                         qsb_buffer* out, int64_t out_offset, int32_t flags) {
+  if (!s || !peers || !out) return fail(nullptr, QSB_E_INVAL, "qsb_stream_run_peers: NULL argument");
+  qsb_ctx* ctx = s->ctx;
+  const int n = s->ka.n;
+  const int64_t dim = (int64_t)1 << n;
+  int rc;
+  if (n_peers < 2 || n_peers > QSB_ST_MAX_PEERS || peer_shift < s->ka.l || peer_shift >= n || (1 << (n - peer_shift)) != n_peers)
+    return fail(ctx, QSB_E_INVAL, "qsb_stream_run_peers: %d peers do not match peer_shift %d of %d bits", n_peers, peer_shift, n);
+  if (peer_rank_or < 0 || peer_rank_or >= dim || (peer_rank_or & (((int64_t)1 << s->ka.l) - 1)))
+    return fail(ctx, QSB_E_INVAL, "qsb_stream_run_peers: bad peer_rank_or");
+  for (int j = 0; j < s->ka.e; ++j)
+    if (s->ebit[j] >= peer_shift)
+      return fail(ctx, QSB_E_UNSUPPORTED, "qsb_stream_run_peers: a TMA box dimension lies on a peer-selecting bit");
+  if (out_offset < 0 || (out_offset & 7)) return fail(ctx, QSB_E_INVAL, "qsb_stream_run_peers: bad out_offset");
+  if ((rc = need(ctx, out, (out_offset + dim) * 16, "output shard"))) return rc;
+  CU(ctx, cudaSetDevice(ctx->device));
+  qsb_stream_maps maps;
+  memset(&maps, 0, sizeof maps);
+  for (int p = 0; p < n_peers; ++p) {
+    if (!peers[p]) return fail(ctx, QSB_E_INVAL, "qsb_stream_run_peers: peer %d is NULL", p);
+    if ((rc = stream_map(ctx, &maps.in[p], const_cast<void*>(peers[p]), s, s->ebit))) return rc;
+  }
+  if ((rc = stream_map(ctx, &maps.out, (char*)out->ptr + out_offset * 16, s, s->ebit_out))) return rc;
+  s->ka.peer_shift = peer_shift;
+  s->ka.peer_or = (uint32_t)peer_rank_or;
+  return stream_launch(s, maps, flags);
+}
+
+int qsb_stream_free(qsb_stream* s) {
+  if (!s) return QSB_OK;
+  cudaSetDevice(s->ctx->device);
+  cudaStreamSynchronize(s->ctx->stream);
+  cudaFree(s->d_sweeps);
+  cudaFree(s->d_mats);
+  delete s;
+  return QSB_OK;
 }
 
 }  // extern "C"

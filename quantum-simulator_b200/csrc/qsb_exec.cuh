@@ -119,10 +119,8 @@ struct qsb_exec_args {
 
 // ---- descriptors: control warp -> workers ---------------------------------------------
 enum { QSB_D_EXIT = 0, QSB_D_INIT, QSB_D_SWEEP, QSB_D_REMAP, QSB_D_GFLUSH, QSB_D_RDM1, QSB_D_STORE };
-// structure class of a pending 2x2: none | diag(1, real s) | diag(d0, d1) | dense
-enum { QSB_CLS_NONE = 0, QSB_CLS_RDIAG = 1, QSB_CLS_DIAG = 2, QSB_CLS_DENSE = 3 };
-// gate applied inside a sweep after the pending matrices of its bits
-enum { QSB_G_NONE = 0, QSB_G_CX, QSB_G_CZ, QSB_G_SWAP, QSB_G_CCX, QSB_G_CSWAP, QSB_G_DENSE };
+// QSB_CLS_* (structure class of a pending 2x2) and QSB_G_* (gate applied inside a sweep after the pending matrices of
+// its bits) are part of the C ABI since the streamed passes take host-fused sweeps: see include/qsb.h
 
 struct alignas(16) qsb_desc {
   int32_t kind, gate, k, flags;
@@ -355,13 +353,13 @@ QSB_HD uint32_t qsb_permute(const uint32_t* tab, uint32_t x) {
 // (CTA-uniform) class branches are taken once per step instead of once per group.
 // amplitudes a worker keeps in registers per step: 16 (all loads in flight before the arithmetic); 8 for K = 3,
 // where 16 amplitudes plus three dense pending matrices would spill (measured: profiles/README.md)
-template <int K, bool DG, class Env>
+template <int K, bool DG, class Env, int AMPS = QSB_AMPS>
 QSB_PASS void qsb_sweep(Env& env, int m, const qsb_desc* d) {
   typedef typename Env::amp A;
   A* tile = env.tile();             // re-derived here so device code keeps the shared address space (LDS/STS)
   const unsigned long long sq0 = env.prof_on() ? env.clock() : 0;
   constexpr int D = 1 << K;
-  constexpr int NG = DG ? (K == 2 && QSB_AMPS >= 16 ? 2 : 1) : (K == 3 ? 1 : (QSB_AMPS / D > 0 ? QSB_AMPS / D : 1));
+  constexpr int NG = DG ? (K == 2 && AMPS >= 16 ? 2 : 1) : (K == 3 ? 1 : (AMPS / D > 0 ? AMPS / D : 1));
   const int G = d->gate;
   int bits[K], cls[K];
 #pragma unroll

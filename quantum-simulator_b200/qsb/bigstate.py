@@ -24,6 +24,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import capi
+from . import stream
 from .compiler import Lowering, Program, OP_DTYPE, MAX_LOCAL_BITS, SNAPSHOT, KRAUS_AD, KRAUS_GEN
 
 
@@ -146,8 +147,11 @@ class BigState:
     """One n-qubit complex128 state on this rank's GPU (a 2^(n-g) shard when the process group has 2^g ranks)."""
 
     def __init__(self, n, *, group=None, device=None, layout="reference", local_bits=None, distributed=True,
-                 fuse_exchange=True):
-        """distributed=False keeps the whole state on this device even when a process group is initialised.
+                 fuse_exchange=True, engine="tma"):
+        """engine: "tma" = the TMA tile pipeline with host-fused sweeps (csrc/qsb_stream.cuh, qsb/stream.py);
+        "executor" = round 1's path, one tile per CTA of the resident executor in its streaming mode (kept for A/B
+        and as a second implementation the tests compare against).
+        distributed=False keeps the whole state on this device even when a process group is initialised.
         fuse_exchange: fold every qubit exchange into the pass that follows it -- that pass LOADs its tiles straight
         from the peers' shards over NVLink peer mappings (torch symmetric memory) instead of waiting for an NCCL
         all-to-all into a second buffer; falls back to the all-to-all when the mappings cannot be set up."""
@@ -166,6 +170,10 @@ class BigState:
         if self.n > 30 + self.g or self.L < 1:
             raise ValueError(f"num_qubits {n} not supported on {self.world} device(s)")
         self.local_bits = local_bits
+        if engine not in ("tma", "executor"):
+            raise ValueError("engine must be 'tma' or 'executor'")
+        self.engine = engine
+        self.fused_exchanges = 0
         dev = capi.default_device() if device is None else device
         self.ctx = capi.get_context(dev)
         self.tdev = torch.device("cuda", dev)
@@ -204,6 +212,7 @@ class BigState:
             ptrs = np.array([int(p) for p in h.buffer_ptrs], dtype=np.int64)
             assert len(ptrs) == self.world and int(ptrs[self.rank]) == t.data_ptr()
             tables.append(self.ctx.to_device(ptrs))
+            self._peer_ptrs = getattr(self, "_peer_ptrs", []) + [ptrs.tolist()]
         torch.cuda.synchronize()
         dist.barrier(group=self.group)
         self._peer_tables = tables
@@ -230,8 +239,67 @@ class BigState:
         lw.bit_of_axis = list(self.bit_of_axis)
         return lw
 
+    # -- the TMA tile pipeline ------------------------------------------------------------------------------------
+    def compile(self, lw: Lowering, *, params=None, uniforms=None, seed=0):
+        """Plan `lw` against the state's CURRENT layout and upload every pass: (steps, moved, bit_of_axis).  The result
+        can be executed any number of times while the layout is the one it was compiled for (always true on one
+        device in the textbook layout; after an exchange the same steps still run, on relabelled qubits)."""
+        rel = _Relabel(lw, self.pos_of)
+        cdata = lw.pool.array()
+        steps, moved, _ = stream.plan(rel.items, cdata, self.n, self.g, list(range(self.n)), local_bits=self.local_bits,
+                                      params=params, uniforms=uniforms, seed=seed)
+        for st in steps:
+            if st.spass is not None:
+                st.handle = self.ctx.stream_pass(st.spass, cdata)
+        return steps, moved, list(lw.bit_of_axis)
+
+    def execute(self, compiled, sync=True):
+        """Run compiled steps: launches are asynchronous on the context's stream, one host sync at the end."""
+        steps, moved, bit_of_axis = compiled
+        pending_exchange = False
+        for st in steps:
+            if st.kind == "exchange":
+                if self._peer_tables is not None and not pending_exchange:
+                    pending_exchange = True          # folded into the LOAD of the next pass
+                else:
+                    self._exchange()
+                continue
+            if pending_exchange:
+                pending_exchange = False
+                shift = self.L - self.g
+                if all(p < shift for p in st.spass.positions[st.spass.l:st.spass.l + st.spass.e]):
+                    # every rank has finished writing its shard (fence), this pass then reads its tiles straight from
+                    # the peers' shards -- element s of my post-exchange shard = peer s >> shift, offset
+                    # (s & mask) | rank << shift -- and stores into my other buffer; the second fence keeps anyone
+                    # from overwriting a shard a peer is still reading
+                    o = self._other()
+                    self._rank_fence()
+                    st.handle.run_peers(self._peer_ptrs[self.cur], shift, self.rank << shift, self._wrapped[o])
+                    self._rank_fence()
+                    self.cur = o
+                    self.launches += 1
+                    self.fused_exchanges += 1
+                    continue
+                self._exchange()                     # a TMA box dimension sits on a peer-selecting bit: plain all-to-all
+            if st.spass.in_place:
+                st.handle.run(self._wrapped[self.cur])
+            else:
+                o = self._other()
+                st.handle.run(self._wrapped[self.cur], self._wrapped[o])
+                self.cur = o
+            self.launches += 1
+        if pending_exchange:                         # an exchange with no pass after it
+            self._exchange()
+        self.pos_of = [moved[p] for p in self.pos_of]
+        self.bit_of_axis = list(bit_of_axis)
+        if sync:
+            self.ctx.sync()
+
     def run(self, lw: Lowering, *, params=None, uniforms=None, seed=0):
         """Apply everything recorded in `lw` (created by self.lowering())."""
+        if self.engine == "tma":
+            self.execute(self.compile(lw, params=params, uniforms=uniforms, seed=seed))
+            return
         steps, moved = plan_distributed(_Relabel(lw, self.pos_of), self.g, self.local_bits)
         kw = {}
         if params is not None:
@@ -262,7 +330,7 @@ class BigState:
                 self._rank_fence()
                 self.cur = o
                 self.launches += 1
-                self.fused_exchanges = getattr(self, "fused_exchanges", 0) + 1
+                self.fused_exchanges += 1
                 self.ctx.sync()
                 continue
             if st.out_of_place:

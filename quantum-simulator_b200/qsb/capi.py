@@ -30,6 +30,7 @@ SYMBOLS = [
     "qsb_debug_profile",
     "qsb_probabilities", "qsb_probabilities_sum", "qsb_sample_index", "qsb_overlap",
     "qsb_masked_parity", "qsb_rdm_all", "qsb_rdm_general", "qsb_mi_all_pairs", "qsb_rho_accumulate", "qsb_readout_transform",
+    "qsb_stream_create", "qsb_stream_run", "qsb_stream_run_peers", "qsb_stream_free",
 ]
 
 
@@ -110,6 +111,10 @@ def load_library():
             "qsb_mi_all_pairs": (C.c_int, [vp, i32, vp, i64, i64, vp, vp]),
             "qsb_rho_accumulate": (C.c_int, [vp, i32, vp, i64, i64, dbl, vp]),
             "qsb_readout_transform": (C.c_int, [vp, i32, vp, i64, dbl, dbl]),
+            "qsb_stream_create": (C.c_int, [vp, i32, i32, i32, i32, P(i32), P(i32), vp, i32, vp, i64, P(vp)]),
+            "qsb_stream_run": (C.c_int, [vp, vp, i64, vp, i64, i32]),
+            "qsb_stream_run_peers": (C.c_int, [vp, P(vp), i32, i32, i64, vp, i64, i32]),
+            "qsb_stream_free": (C.c_int, [vp]),
         }
         for name, (res, args) in proto.items():
             fn = getattr(lib, name)
@@ -256,6 +261,46 @@ class DeviceProgram:
             pass
 
 
+class DevicePass:
+    """One streamed pass on the device (qsb_stream_*): a `stream.StreamPass` with its sweeps uploaded."""
+
+    def __init__(self, ctx, spass, cdata):
+        from .stream import pack_blocks
+        self.ctx, self.spass = ctx, spass
+        arr = pack_blocks(spass)
+        cd = np.ascontiguousarray(cdata, dtype=np.float64)
+        n = spass.n
+        pos = (C.c_int32 * n)(*[int(x) for x in spass.positions])
+        pos_out = (C.c_int32 * n)(*[int(x) for x in spass.positions_out])
+        h = C.c_void_p()
+        _check(ctx.lib.qsb_stream_create(ctx.handle, n, spass.m, spass.l, spass.e, pos, pos_out,
+                                         C.cast(arr, C.c_void_p), len(spass.blocks), _hostptr(cd), len(cd), C.byref(h)),
+               ctx.handle)
+        self.handle = h
+
+    def run(self, src, dst=None, *, src_offset=0, dst_offset=0, async_=True):
+        _check(self.ctx.lib.qsb_stream_run(self.handle, src.handle, src_offset, dst.handle if dst is not None else None,
+                                           dst_offset, RUN_ASYNC if async_ else 0), self.ctx.handle)
+
+    def run_peers(self, peer_ptrs, peer_shift, peer_rank_or, dst, *, dst_offset=0, async_=True):
+        """Load the tiles from the peers' shards (device pointers, rank order): the qubit exchange folded into the pass."""
+        arr = (C.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+        _check(self.ctx.lib.qsb_stream_run_peers(self.handle, arr, len(peer_ptrs), int(peer_shift), int(peer_rank_or),
+                                                 dst.handle, dst_offset, RUN_ASYNC if async_ else 0), self.ctx.handle)
+
+    def free(self):
+        if self.handle is not None:
+            if self.ctx.handle is not None:
+                self.ctx.lib.qsb_stream_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 class Context:
     """One CUDA device + stream + memory pool.  The C object is single-threaded by contract; every call made
     through this wrapper takes `self.lock`, so one Context can be shared by all threads of the process
@@ -345,6 +390,9 @@ class Context:
     # -- execution ------------------------------------------------------------------------
     def program(self, prog: Program):
         return DeviceProgram(self, prog)
+
+    def stream_pass(self, spass, cdata):
+        return DevicePass(self, spass, cdata)
 
     def run(self, dprog, count, *, states=None, first=0, load=False, store=True, params=None, params_stride=0,
             uniforms=None, uniforms_stride=0, seed=0, traj_offset=0, init_basis=None, default_basis=0,
