@@ -188,6 +188,9 @@ __device__ __forceinline__ void qsb_block_sweep(StreamEnv& env, int m, const qsb
   const int c0 = d->cls[0], c1 = d->cls[1], c2 = d->cls[2], c3 = d->cls[3];
   const int dense = d->dense;
   const uint32_t neg = d->neg_mask;
+  // the offset tables are re-read from shared memory in every step (broadcast LDS.128): holding them in registers for
+  // the whole sweep was measured 27 % slower (15.5 ms against 12.2 ms on the 26-qubit circuit; registers, not the two
+  // extra shared-memory round trips, are what this loop is short of)
   const uint4* ldo = reinterpret_cast<const uint4*>(d->ld_off);
   const uint4* sto = reinterpret_cast<const uint4*>(d->st_off);
   int hi = 0;

@@ -168,7 +168,7 @@ def test_pauli_draws_parameters_and_dense_gates_in_a_stream_plan():
 
 
 def test_geometry_defaults():
-    assert S.choose_geometry(26) == (12, 4, 3)           # 64 KiB tiles, 256-byte rows, 2 KiB per TMA op, 32 ops per tile
-    assert S.choose_geometry(27, low_bits=5) == (12, 5, 3)
+    assert S.choose_geometry(26) == (12, 5, 3)           # 64 KiB tiles, 512-byte rows, 4 KiB per TMA op, 16 ops per tile
+    assert S.choose_geometry(27, low_bits=4) == (12, 4, 3)
     m, l, e = S.choose_geometry(20, local_bits=10)
-    assert (m, l) == (10, 4) and m - l - e <= 5
+    assert (m, l) == (10, 5) and m - l - e <= 5
