@@ -1244,20 +1244,17 @@ int qsb_stream_create(qsb_ctx* ctx, int32_t n, int32_t m, int32_t l, int32_t e, 
 static int stream_launch(qsb_stream* s, qsb_stream_maps& maps, int32_t flags) {
   qsb_ctx* ctx = s->ctx;
   const size_t smem = qsb_stream_smem_bytes(s->ka.m);
-  static int variant = -1;                 // developer knob: QSB_STREAM_VARIANT=1 -> no dedicated TMA warp
-  if (variant < 0) {
-    const char* v = getenv("QSB_STREAM_VARIANT");
-    variant = (v && atoi(v) == 1) ? 1 : 0;
-    const int full = (int)qsb_stream_smem_bytes(QSB_ST_MAX_TILE_BITS);
-    CU(ctx, cudaFuncSetAttribute(qsb_stream_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, full));
-    CU(ctx, cudaFuncSetAttribute(qsb_stream_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, full));
+  static bool attr_set[64] = {false};
+  if (!attr_set[ctx->device & 63]) {          // the opt-in to > 48 KiB of dynamic shared memory is per device
+    CU(ctx, cudaFuncSetAttribute(qsb_stream_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)qsb_stream_smem_bytes(QSB_ST_MAX_TILE_BITS)));
+    attr_set[ctx->device & 63] = true;
   }
   const int64_t ntiles = (int64_t)1 << (s->ka.n - s->ka.m);
   const int grid = (int)(ntiles < ctx->sm_count ? ntiles : ctx->sm_count);
   qsb_stream_kargs ka = s->ka;
   ka.sweeps = s->d_sweeps128;
-  if (variant == 0) qsb_stream_kernel<128, true><<<grid, 2 * 128 + 32, smem, ctx->stream>>>(maps, ka);
-  else qsb_stream_kernel<128, false><<<grid, 2 * 128, smem, ctx->stream>>>(maps, ka);
+  qsb_stream_kernel<128><<<grid, QSB_ST_GROUPS * 128 + 32, smem, ctx->stream>>>(maps, ka);
   cudaError_t er = cudaGetLastError();
   if (er != cudaSuccess) return fail(ctx, QSB_E_CUDA, "streamed pass launch: %s", cudaGetErrorString(er));
   ctx->launches += 1;

@@ -32,8 +32,6 @@
 
 #define QSB_ST_BUFS 3
 #define QSB_ST_GROUPS 2
-// Builds of the kernel (A/B on the device, QSB_STREAM_VARIANT picks one): GT worker threads per group, with or without a
-// dedicated TMA warp.
 #define QSB_ST_MAX_SWEEPS 16           // block sweeps per pass
 #define QSB_ST_BLOCK_OPS 12            // ops per block of the C ABI (qsb_stream_block)
 #define QSB_ST_MAX_TILE_BITS 12          // 3 x 64 KiB tiles + the sweep list fit 227 KiB
@@ -228,12 +226,10 @@ __device__ __forceinline__ void qsb_block_sweep(StreamEnv& env, int m, const qsb
   }
 }
 
-// DEDICATED = true: a 17th / 9th warp does nothing but TMA (loads, stores, buffer turnover).
-// DEDICATED = false: no extra warp (the register file is allocated in units of 4 warps, so 16 worker warps keep 128
-// registers each): warp 0 of a group stores the tile its group has just swept and, one sweep into the group's next tile
-// (the store has long read the buffer by then), re-loads that buffer with the tile three places on.
-template <int GT, bool DEDICATED>
-__global__ void __launch_bounds__(QSB_ST_GROUPS * GT + (DEDICATED ? 32 : 0), 1)
+// GT worker threads per group (two groups) + one TMA warp.  (A build without the dedicated TMA warp -- warp 0 of each group
+// issuing its group's stores and refills between sweeps -- was measured 18 % slower and is gone.)
+template <int GT>
+__global__ void __launch_bounds__(QSB_ST_GROUPS * GT + 32, 1)
 qsb_stream_kernel(const __grid_constant__ qsb_stream_maps maps, const __grid_constant__ qsb_stream_kargs a) {
   const int tile_bytes = 16 << a.m;
   const int op_bytes = 16 << (a.l + a.e);
@@ -265,45 +261,41 @@ qsb_stream_kernel(const __grid_constant__ qsb_stream_maps maps, const __grid_con
   __syncthreads();
   const int64_t ntiles = (int64_t)1 << (a.n - a.m);
   const int64_t mine = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;   // tiles of this CTA
-  const int lane = tid & 31;
   auto tile_base = [&](int64_t j, const int32_t* pos) {
     const uint32_t t = (uint32_t)(blockIdx.x + j * gridDim.x);
     uint32_t off = 0;
     for (int q = 0; q < a.n - a.m; ++q) off |= ((t >> q) & 1u) << pos[q];
     return off;
   };
-  // one warp: gather tile j into buffer j % 3 (completes on full[j % 3])
-  auto issue_load = [&](int64_t j) {
-    const int b = (int)(j % QSB_ST_BUFS);
-    const uint32_t full = qsb_st_smem_u32(&bars[b]);
-    const uint32_t tb = tile_base(j, a.tile_pos);
-    if (lane == 0) qsb_st_mbar_expect(full, (uint32_t)tile_bytes);
-    __syncwarp();
-    const uint32_t pmask = a.peer_shift >= 32 ? 0xffffffffu : ((1u << a.peer_shift) - 1u);
-    for (int r = lane; r < a.n_ops; r += 32) {
-      const uint32_t x = tb | row_off[r];
-      const uint32_t src = a.peer_shift >= 32 ? 0u : (x >> a.peer_shift);
-      qsb_st_tma_load(qsb_st_smem_u32(base + (size_t)b * tile_bytes + (size_t)r * op_bytes), &maps.in[src],
-                      (int)(((x & pmask) | a.peer_or) >> 3), full);
-    }
-  };
-  // one warp: scatter buffer j % 3 to the positions of tile j (one bulk group per lane)
-  auto issue_store = [&](int64_t j) {
-    const int b = (int)(j % QSB_ST_BUFS);
-    const uint32_t tb = tile_base(j, a.tile_pos_out);
-    for (int r = lane; r < a.n_ops; r += 32)
-      qsb_st_tma_store(&maps.out, (int)((tb | row_off[32 + r]) >> 3),
-                       qsb_st_smem_u32(base + (size_t)b * tile_bytes + (size_t)r * op_bytes));
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-  };
 
-  if (DEDICATED && tid >= QSB_ST_GROUPS * GT) {
+  if (tid >= QSB_ST_GROUPS * GT) {
     // ================= producer warp: TMA loads and stores, buffer turnover =================
+    const int lane = tid & 31;
+    // gather tile j into buffer j % 3 (completes on full[j % 3])
+    auto issue_load = [&](int64_t j) {
+      const int b = (int)(j % QSB_ST_BUFS);
+      const uint32_t full = qsb_st_smem_u32(&bars[b]);
+      const uint32_t tb = tile_base(j, a.tile_pos);
+      if (lane == 0) qsb_st_mbar_expect(full, (uint32_t)tile_bytes);
+      __syncwarp();
+      const uint32_t pmask = a.peer_shift >= 32 ? 0xffffffffu : ((1u << a.peer_shift) - 1u);
+      for (int r = lane; r < a.n_ops; r += 32) {
+        const uint32_t x = tb | row_off[r];
+        const uint32_t src = a.peer_shift >= 32 ? 0u : (x >> a.peer_shift);
+        qsb_st_tma_load(qsb_st_smem_u32(base + (size_t)b * tile_bytes + (size_t)r * op_bytes), &maps.in[src],
+                        (int)(((x & pmask) | a.peer_or) >> 3), full);
+      }
+    };
     for (int64_t j = 0; j < mine && j < QSB_ST_BUFS; ++j) issue_load(j);
     for (int64_t j = 0; j < mine; ++j) {
       const int b = (int)(j % QSB_ST_BUFS);
       qsb_st_mbar_wait(qsb_st_smem_u32(&bars[QSB_ST_BUFS + b]), (uint32_t)((j / QSB_ST_BUFS) & 1));   // tile j is swept
-      issue_store(j);
+      // scatter buffer b to the (store-side) positions of tile j: one bulk group per lane
+      const uint32_t tb = tile_base(j, a.tile_pos_out);
+      for (int r = lane; r < a.n_ops; r += 32)
+        qsb_st_tma_store(&maps.out, (int)((tb | row_off[32 + r]) >> 3),
+                         qsb_st_smem_u32(base + (size_t)b * tile_bytes + (size_t)r * op_bytes));
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       if (j + QSB_ST_BUFS < mine) {
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");    // the store has read the buffer: refill it
         __syncwarp();
@@ -322,45 +314,23 @@ qsb_stream_kernel(const __grid_constant__ qsb_stream_maps maps, const __grid_con
   env.wbits = GT == 256 ? 8 : 7;
   env.tile_bytes = tile_bytes;
   const int bar_id = 1 + g;
-  const bool tma_warp = !DEDICATED && env.wid < 32;       // this group's TMA issuer
-  if (!DEDICATED && tid < 32)
-    for (int64_t j = 0; j < mine && j < QSB_ST_BUFS; ++j) issue_load(j);
-  int64_t refill = -1;                                    // tile to load once the store of its buffer's last tile has read it
   for (int64_t j = g; j < mine; j += QSB_ST_GROUPS) {
     const int b = (int)(j % QSB_ST_BUFS);
     env.cur = b;
+    // A parity wait only tells "the phase before the current one is complete".  Tile j - 3 used this buffer and was
+    // swept by the OTHER group: unless that is known to be over, full[b] may still be in the phase of tile j - 3 (its
+    // load not even landed) and the wait for tile j's phase would fall straight through.  With no sweeps in a pass
+    // (a reorder) a group does get three tiles ahead of a slow load, so: first "tile j - 3 is swept", then "tile j is in".
+    if (j >= QSB_ST_BUFS)
+      qsb_st_mbar_wait(qsb_st_smem_u32(&bars[QSB_ST_BUFS + b]), (uint32_t)(((j - QSB_ST_BUFS) / QSB_ST_BUFS) & 1));
     qsb_st_mbar_wait(qsb_st_smem_u32(&bars[b]), (uint32_t)((j / QSB_ST_BUFS) & 1));                 // tile j has landed
     for (int s = 0; s < a.n_sweeps; ++s) {
       qsb_block_sweep(env, a.m, &descs[s]);
-      if (tma_warp && s == 0 && refill >= 0) {
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        __syncwarp();
-        issue_load(refill);
-        refill = -1;
-      }
       if (s + 1 < a.n_sweeps) asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(GT) : "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy writes -> visible to the TMA store
     asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(GT) : "memory");
-    if (DEDICATED) {
-      if (env.wid == 0) qsb_st_mbar_arrive(qsb_st_smem_u32(&bars[QSB_ST_BUFS + b]));
-    } else if (tma_warp) {
-      if (refill >= 0) {                                  // a pass without sweeps: the refill could not ride behind one
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        __syncwarp();
-        issue_load(refill);
-      }
-      issue_store(j);
-      refill = j + QSB_ST_BUFS < mine ? j + QSB_ST_BUFS : -1;
-    }
-  }
-  if (tma_warp) {
-    if (refill >= 0) {                                    // the other group still waits for this tile
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      __syncwarp();
-      issue_load(refill);
-    }
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (env.wid == 0) qsb_st_mbar_arrive(qsb_st_smem_u32(&bars[QSB_ST_BUFS + b]));
   }
 }
 

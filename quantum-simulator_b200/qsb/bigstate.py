@@ -21,6 +21,9 @@ currently lives.  Three kinds of step:
 
 from __future__ import annotations
 
+import os
+import sys
+
 import numpy as np
 
 from . import capi
@@ -257,7 +260,11 @@ class BigState:
         """Run compiled steps: launches are asynchronous on the context's stream, one host sync at the end."""
         steps, moved, bit_of_axis = compiled
         pending_exchange = False
-        for st in steps:
+        trace = os.environ.get("QSB_TRACE")
+        for k, st in enumerate(steps):
+            if trace:                                # developer aid: which step a rank is in when something goes wrong
+                self.ctx.sync()
+                print(f"[rank {self.rank}] step {k}/{len(steps)} {st.kind} cur={self.cur}", file=sys.stderr, flush=True)
             if st.kind == "exchange":
                 if self._peer_tables is not None and not pending_exchange:
                     pending_exchange = True          # folded into the LOAD of the next pass

@@ -147,6 +147,64 @@ def test_world2_gloo_sharded_state_with_qubit_exchanges():
     assert err < 1e-12
 
 
+def _stream_exchange_worker(rank, world, port, n, out_q):
+    """The TMA pipeline's plan (qsb/stream.py: host-fused block sweeps, reorder passes, exchanges) executed per rank with
+    the NumPy model of a pass and a real gloo all_to_all_single for the exchange steps."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from qsb import stream as S
+    from qsb.bigstate import exchange_rank_bits
+    from qsb.workloads import layered_circuit
+    from test_bigstate import ordered, lower
+    from test_stream_plan import replay
+    g = world.bit_length() - 1
+    L = n - g
+    gl = ordered(n, layered_circuit(n, 6, 78))
+    lw = lower(n, gl)
+    steps, pos_of, _ = S.plan(lw.items, lw.pool.array(), n, g, list(range(n)), local_bits=5, low_bits=2, box_bits=1)
+    rng = np.random.default_rng(4)
+    psi = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+    psi /= np.linalg.norm(psi)
+    shard = psi[rank << L:(rank + 1) << L].copy()
+    kinds = [st.kind for st in steps]
+    for st in steps:
+        if st.kind == "exchange":
+            src = torch.from_numpy(shard.view(np.float64).copy())
+            dst = torch.empty_like(src)
+            exchange_rank_bits(src, dst)
+            shard = dst.numpy().view(np.complex128).copy()
+        else:
+            shard = replay([st], L, 0, shard, lw.pool.array())
+    parts = [torch.zeros(2 * (1 << L), dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(parts, torch.from_numpy(shard.view(np.float64).copy()))
+    if rank == 0:
+        full = np.concatenate([p.numpy().view(np.complex128) for p in parts])
+        pos = [pos_of[lw.bit_of_axis[j]] for j in range(n)]
+        got = np.ascontiguousarray(full.reshape([2] * n).transpose([n - 1 - pos[j] for j in range(n)])).reshape(-1)
+        ref = psi
+        for name, targets, params in gl:
+            ref = O.apply_gate(ref, n, O.gate_matrix(name, params), targets)
+        out_q.put((float(np.max(np.abs(got - ref))), kinds.count("exchange"), kinds.count("reorder")))
+    dist.destroy_process_group()
+
+
+def test_world2_gloo_stream_plan_with_qubit_exchanges():
+    """Config 5 on the TMA pipeline's planner, N = 2 on CPU: passes of block sweeps, reorder passes and exchanges."""
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_stream_exchange_worker, args=(r, 2, port, 10, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    err, n_ex, n_re = q.get()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert n_ex >= 1
+    assert err < 1e-12
+
+
 def _qec_worker(rank, world, port, out_q):
     """threshold_sweep_sharded with the device stood in for by the oracle's cycle (the sharding, the seed chain and
     the gather are what is under test)."""
