@@ -44,9 +44,6 @@ def algorithmic_bytes_per_trajectory(n, gates, k_pauli, k_ad):
 # DRAM bytes one trajectory really moves (ncu dram__bytes_read.sum + dram__bytes_write.sum of the trajectory
 # kernel divided by its trajectories: profiles/r01g_traj_kernel_ncu_full_traj480.csv, 468.3 MB / 480)
 MEASURED_DRAM_BYTES_PER_TRAJECTORY = (11614464 + 456644096) / 480
-# shared-memory wavefronts (128 B each) one trajectory costs, same capture
-# (l1tex__data_pipe_lsu_wavefronts_mem_shared.sum = 3 367 032 907 per 480 trajectories)
-MEASURED_SMEM_WAVEFRONTS_PER_TRAJECTORY = 3367032907 / 480
 
 
 def measured_peak():
@@ -256,14 +253,55 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------ GPU arm
+TILE_BYTES = 128 << 10          # one CTA's share of a 16-qubit complex128 state (2^13 amplitudes)
+
+
+def onchip_bytes_per_trajectory(ctx, dp, D, units=120):
+    """Shared-memory bytes one trajectory moves, from the executor's own counters (qsb_debug_profile, the profiling
+    build of the kernel, run once on `units` trajectories outside every timed region): descriptors executed per kind
+    x the tile bytes each kind reads + writes in every CTA of the cluster."""
+    u = ctx.to_device(np.random.default_rng(5).random((units, D)))
+    st = ctx.alloc(units * (16 << N_QUBITS))
+    ctx.profile(True)
+    try:
+        ctx.run(dp, units, states=st, uniforms=u, uniforms_stride=D)
+        p = ctx.profile(True, read=True).astype(np.float64)
+    finally:
+        ctx.profile(False)
+    ctas = len(p)
+    per_cta_units = units / (ctas / 8)                       # trajectories each cluster of 8 ran
+    c = p[:, 9:17].mean(axis=0) / per_cta_units              # descriptors per trajectory per CTA, by kind
+    pairs = p[:, 125:128].mean(axis=0) / per_cta_units       # exchange rounds moving 1 / 2 / 3 (rank bit, local bit) pairs
+    n_init, n_sweep, n_remap, n_gflush, n_rdm1, n_store = c[1], c[2], c[3], c[4], c[5], c[6]
+    remap_bytes = sum(pairs[k] * 2 * (1 - 0.5 ** (k + 1)) * TILE_BYTES for k in range(3)) if pairs.sum() > 0 else n_remap * TILE_BYTES
+    per_cta = (n_sweep * 2 * TILE_BYTES + remap_bytes + n_gflush * 2 * TILE_BYTES + n_rdm1 * TILE_BYTES
+               + n_store * 2 * TILE_BYTES + n_init * TILE_BYTES)
+    return {"bytes_per_trajectory": float(per_cta * 8), "sweeps": float(n_sweep), "exchanges": float(n_remap),
+            "rank_bit_flushes": float(n_gflush), "marginals": float(n_rdm1), "profiled_trajectories": units}
+
+
+def fp64_gemm_peak(torch):
+    """FP64 tensor-core (DMMA) peak of this device, measured here: cuBLAS DGEMM 8192^3, best of 5."""
+    a = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
+    b = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
+    torch.matmul(a, b)
+    best = 1e9
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return 2 * 8192.0 ** 3 / (best * 1e-3) / 1e12
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from qsb import capi
-    from qsb.lowering import lower_circuit
-    from qsb.workloads import layered_circuit, config3_noise, to_gate_instances
+    from qsb.workloads import layered_circuit, to_gate_instances
     from quantum_sim.engine.circuit import QuantumCircuit, GateInstance
-    from quantum_sim.engine.gate_registry import GateRegistry
     from quantum_sim.engine.noise import NoiseModel, DepolarizingNoise, AmplitudeDampingNoise
     from quantum_sim.engine.simulator import Simulator
 
@@ -302,109 +340,143 @@ def run_ours(args):
     t_uniforms = torch.from_numpy(np.random.default_rng(777 + rank).random((T, D))).cuda()
     t_sample_u = torch.from_numpy(np.random.default_rng(888 + rank).random(T)).cuda()
     t_idx = torch.empty(T, dtype=torch.int64, device="cuda")
-    t_hist = torch.zeros(dim, dtype=torch.float64, device="cuda")
+    t_hist = [torch.zeros(dim, dtype=torch.float64, device="cuda") for _ in range(2)]
     t_flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     b_states = ctx.wrap(t_states.data_ptr(), T * dim * 16)
     b_uniforms = ctx.wrap(t_uniforms.data_ptr(), T * D * 8)
     b_sample_u = ctx.wrap(t_sample_u.data_ptr(), T * 8)
     b_idx = ctx.wrap(t_idx.data_ptr(), T * 8)
-    b_hist = ctx.wrap(t_hist.data_ptr(), dim * 8)
+    b_hist = [ctx.wrap(t.data_ptr(), dim * 8) for t in t_hist]
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
+    pending = [None, None]                       # the all-reduce still reading histogram buffer k
 
-    def step(timers=None):
-        t_flush.zero_()                          # evict L2 between steps (256 MiB > 126 MB), not timed
-        t_hist.zero_()
-        e0, e1, e2 = ev(), ev(), ev()
+    def step(s, timers=None):
+        """One pass of the hot path over one batch.  The histogram of step s is summed over the ranks by ONE NCCL
+        all-reduce that runs on NCCL's stream under the trajectories of step s + 1 (double-buffered), so rank skew is
+        absorbed instead of being paid at every step; the last one is waited for inside the timed region."""
+        k = s & 1
+        if pending[k] is not None:
+            pending[k].wait()
+            pending[k] = None
+        t_flush.zero_()                          # evict L2 between steps (256 MiB > 126 MB)
+        t_hist[k].zero_()
+        e0, e1 = ev(), ev()
         e0.record(stream)
         ctx.run(dp, T, states=b_states, uniforms=b_uniforms, uniforms_stride=D, traj_offset=rank * T, async_=True)
         e1.record(stream)
         ctx.lib.qsb_sample_index(ctx.handle, n, b_states.handle, 0, T, b_sample_u.handle, b_idx.handle)
-        ctx.lib.qsb_probabilities_sum(ctx.handle, n, b_states.handle, 0, T, b_hist.handle)
+        ctx.lib.qsb_probabilities_sum(ctx.handle, n, b_states.handle, 0, T, b_hist[k].handle)
         if world > 1:
-            dist.all_reduce(t_hist)
-        e2.record(stream)
+            pending[k] = dist.all_reduce(t_hist[k], async_op=True)
         if timers is not None:
-            timers.append((e0, e1, e2))
+            timers.append((e0, e1))
+        return k
+
+    def drain():
+        for k in range(2):
+            if pending[k] is not None:
+                pending[k].wait()
+                pending[k] = None
 
     def fence():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
+    for s in range(args.warmup):
+        step(s)
+    drain()
     fence()
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = ctx.launches
     timers = []
     fence()
-    for _ in range(args.steps):
-        step(timers)
+    t_begin, t_end = ev(), ev()
+    t_begin.record(stream)
+    last = 0
+    for s in range(args.steps):
+        last = step(s, timers)
+    drain()
+    t_end.record(stream)
     fence()
     launches = ctx.launches - launches0
     clocks = sampler.stop()
-    step_ms = [e0.elapsed_time(e2) for e0, e1, e2 in timers]
-    kern_ms = [e0.elapsed_time(e1) for e0, e1, e2 in timers]
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device="cuda")
+    kern_ms = [e0.elapsed_time(e1) for e0, e1 in timers]
+    total_ms = torch.tensor([t_begin.elapsed_time(t_end)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms.item())
     value = world * T * args.steps / (total_ms * 1e-3)
-    hist_total = float(t_hist.sum().item())
+    hist_total = float(t_hist[last].sum().item())
 
-    # ---- end to end through the engine API with host buffers: Simulator.run_with_noise(circuit, shots)
+    # ---- end to end through the engine API with host buffers: Simulator.run_with_noise(circuit, shots); with N > 1
+    # the product's sharded entry point (shots split over the ranks, counts merged in shot order)
     e2e_T = args.e2e_traj
-    sim.run_with_noise(qc, shots=e2e_T, seed=1)      # warm-up: program cached, staging pinned, pool blocks mapped
+    nm.set_seed(4242)                            # one noise stream for the whole job: every rank positions itself in it
+    run_e2e = (lambda seed: sim.run_with_noise_sharded(qc, shots=world * e2e_T, seed=seed)) if world > 1 else \
+              (lambda seed: sim.run_with_noise(qc, shots=e2e_T, seed=seed))
+    run_e2e(1)                                   # warm-up: program cached, staging pinned, pool blocks mapped
     fence()
     t0 = time.perf_counter()
     for s in range(args.e2e_steps):
-        res = sim.run_with_noise(qc, shots=e2e_T, seed=100 + s)
+        res = run_e2e(100 + s)
     torch.cuda.synchronize()
     e2e_dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
     e2e_value = world * e2e_T * args.e2e_steps / float(e2e_dt.item())
-    assert sum(res.measurement_counts.values()) == e2e_T
+    assert sum(res.measurement_counts.values()) == world * e2e_T
 
+    # ---- the other half of the metric and the sharded state: measured on ALL ranks (max over ranks)
+    gate_apps = measure_gate_apps(ctx, qc, rank, world, torch, dist)
+    big = None if args.no_extras else measure_sharded_state(rank, world, torch, dist, args.big_qubits)
     extras = None
-    if rank == 0 and not args.no_extras:
+    if rank == 0 and world == 1 and not args.no_extras:
         extras = measure_other_paths(ctx, sim, qc)
     if rank == 0:
         peak, peak_src = measured_peak()
         kms = float(np.mean(kern_ms))
         achieved = alg_bytes * T / (kms * 1e-3) / 1e9
+        clk_hz = float(clocks.get("sm_mhz") or 1965.0) * 1e6
+        try:
+            oc = onchip_bytes_per_trajectory(ctx, dp, D)
+            oc_rate = oc["bytes_per_trajectory"] * T / (kms * 1e-3 * clk_hz * ctx.sm_count)
+            onchip = {"bound": "shared memory", "unit": "B/clk/SM", "peak": 128.0, "achieved": oc_rate, "frac": oc_rate / 128.0,
+                      "sms": ctx.sm_count, "sm_mhz": clk_hz / 1e6, **oc,
+                      "source": "descriptor counts of the executor's profiling build on this program (qsb_debug_profile, "
+                                "outside the timed region) x tile bytes read + written per descriptor kind, over kernel time "
+                                "x SM clock x all SMs (clusters of 8 fit on 120 of the 148)"}
+        except Exception as e:                   # never let a diagnostic break the headline line
+            onchip = {"error": repr(e)}
         line = {
             "metric": METRIC, "value": value, "unit": "trajectories/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
             "config": bench_config(T, world),
             "check": {"histogram_total": hist_total, "gates": prog.n_gate_ops, "kraus_draws": D},
-            "roofline": {"bound": "hbm", "kernel": f"qsb_traj_kernel<{1 << (prog.n - prog.m)}>",
+            "roofline": {"bound": "onchip_shared_memory",
+                         "kernel": f"qsb_traj_kernel<{1 << (prog.n - prog.m)}>", "kernel_ms": kms,
+                         # what the contract asks for: ALGORITHMIC bytes (SURVEY 8d) against the measured HBM copy rate
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "algorithmic_bytes_per_launch": alg_bytes * T, "peak_source": peak_src,
                          "traffic": MEASURED_DRAM_BYTES_PER_TRAJECTORY * T,
-                         "traffic_source": "ncu dram bytes per trajectory (profiles/r01g_traj_kernel_ncu_full_traj480.csv) x trajectories per launch",
-                         "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes * T, "kernel_ms": kms,
-                         "note": "trajectories are resident in cluster shared memory; algorithmic bytes count "
-                                 "every gate/Kraus sweep (SURVEY 8d), real DRAM traffic is ~1 MiB/trajectory "
-                                 "(see profiles/), so frac > 1 is expected; `onchip` is the physical bound",
-                         # where the kernel really stands: shared-memory bytes per SM-clock against 128 B/clk/SM
-                         "onchip": (lambda clk_hz, sms: {
-                             "bound": "shared memory", "unit": "B/clk/SM", "peak": 128.0,
-                             "achieved": MEASURED_SMEM_WAVEFRONTS_PER_TRAJECTORY * 128.0 * T / (kms * 1e-3 * clk_hz * sms),
-                             "frac": MEASURED_SMEM_WAVEFRONTS_PER_TRAJECTORY * T / (kms * 1e-3 * clk_hz * sms),
-                             "sms_holding_clusters": sms, "sm_mhz": clk_hz / 1e6,
-                             "source": "ncu shared-memory wavefronts per trajectory (profiles/r01g_*) x trajectories / "
-                                       "(kernel time x SM clock x SMs that can hold clusters of 8)"})(
-                             float(clocks.get("sm_mhz") or 1965.0) * 1e6, 120)},
+                         "traffic_source": "ncu dram bytes per trajectory (profiles/r01g_traj_kernel_ncu_full_traj480.csv) x "
+                                           "trajectories per launch",
+                         "note": "every trajectory lives in the shared memory of an 8-CTA cluster from |0> to its final "
+                                 "store: HBM sees ~1 MiB per trajectory, so the HBM fraction of the algorithmic bytes is far "
+                                 "above 1 and is NOT the bound; `onchip` is the kernel's distance from its physical limit",
+                         "onchip": onchip},
             "e2e": {"value": e2e_value, "unit": "trajectories/s",
                     "h2d_bytes_per_step": e2e_T * (D + 1) * 8, "d2h_bytes_per_step": e2e_T * 8,
-                    "api": "quantum_sim.engine.simulator.Simulator.run_with_noise", "shots": e2e_T,
-                    "steps": args.e2e_steps},
+                    "api": "quantum_sim.engine.simulator.Simulator." + ("run_with_noise_sharded" if world > 1 else "run_with_noise"),
+                    "shots_per_gpu": e2e_T, "steps": args.e2e_steps},
             "gpu_launches": launches, "clocks": clocks,
+            "gate_apps": gate_apps,
         }
+        if big is not None:
+            line["config5_sharded_state"] = big
         if extras is not None:
             line["other_paths"] = extras
         if world == 1 and not args.no_cpu_baseline:
@@ -414,10 +486,107 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def measure_gate_apps(ctx, qc16, rank, world, torch, dist, sets=4096):
+    """BASELINE config 2, the other half of the metric: the 16-qubit layered circuit noiseless for `sets` parameter
+    sets PER GPU (rows of the (world * sets) x 473 matrix sharded by contiguous ranges, like batch_costs_sharded),
+    one launch per rank, parameters resident, device-timed; gate-apps/s = all ranks' gates / max-over-ranks time."""
+    from quantum_sim.engine.optimizer import ParameterizedCircuitConfig
+    cfg = ParameterizedCircuitConfig.auto_detect(qc16)
+    dp, row_cols = cfg._device_program()
+    P = cfg.num_params
+    vals = np.random.default_rng(2027).uniform(-np.pi, np.pi, (world * sets, P))[rank * sets:(rank + 1) * sets]
+    rows = ctx.to_device(np.ascontiguousarray(vals[:, row_cols]))
+    states = ctx.alloc(sets * (16 << N_QUBITS))
+    ctx.run(dp, sets, states=states, params=rows, params_stride=len(row_cols))          # warm-up
+    best = 1e9
+    for _ in range(3):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.timer_start()
+        ctx.run(dp, sets, states=states, params=rows, params_stride=len(row_cols), async_=True)
+        best = min(best, ctx.timer_stop())
+    ms = torch.tensor([best], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    G = len(qc16.gates)
+    peak, _ = measured_peak()
+    alg = world * sets * G * 2.0 * 16 * 2 ** N_QUBITS          # SURVEY 8d: one read + one write of the state per gate
+    return {"value": world * sets * G / (ms * 1e-3), "unit": "gate-apps/s", "config": "configs[1]: layered_circuit(16,64,2026) "
+            "noiseless, 4096 parameter sets per GPU", "param_sets_per_gpu": sets, "gates": G, "ms": ms, "n_gpus": world,
+            "roofline": {"bound": "onchip_shared_memory", "achieved": alg / (ms * 1e-3) / 1e9 / world, "peak": peak, "unit": "GB/s per GPU",
+                         "frac": alg / (ms * 1e-3) / 1e9 / world / peak,
+                         "note": "algorithmic bytes (2 x 1 MiB per gate-app) against the measured HBM copy rate; states are "
+                                 "cluster-resident, real DRAM traffic is the 1 MiB final store per parameter set"}}
+
+
+def measure_sharded_state(rank, world, torch, dist, n):
+    """BASELINE config 5: layered_circuit(n, 20, 2026) on ONE state sharded over all ranks (global qubits = rank bits),
+    streamed passes on the TMA tile pipeline, qubit exchanges folded into the next pass's peer loads (NCCL all-to-all
+    when peer mappings are unavailable).  Plan + upload outside the timed region; best of 3, max over ranks."""
+    try:
+        from qsb.bigstate import BigState
+        from qsb.workloads import layered_circuit
+        from quantum_sim.engine.circuit import QuantumCircuit, GateInstance
+        from quantum_sim.engine.gate_registry import GateRegistry
+        qc = QuantumCircuit(16)
+        qc.num_qubits = n                                   # the reference's cap lives in its constructors only
+        for name, targets, params, col in layered_circuit(n, 20, CIRCUIT_SEED):
+            qc.add_gate(GateInstance(name, list(targets), list(params), col))
+        gl = [(g.gate_name, list(g.target_qubits), list(g.params)) for col in qc.get_ordered_gates() for g in col]
+        st = BigState(n, layout="textbook")
+        lw = st.lowering()
+        reg = GateRegistry.instance()
+        for name, targets, params in gl:
+            lw.gate(name, targets, params, reg.get(name).matrix_func)
+        comp = st.compile(lw)
+        kinds = [s.kind for s in comp[0]]
+        blocks = sum(len(s.spass.blocks) for s in comp[0] if s.spass is not None)
+        st.execute(comp)
+        times = []
+        for _ in range(3):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            st.execute(comp, sync=False)
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        ms = torch.tensor([min(times)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms = float(ms.item())
+        nrm = st.norm2()
+        passes = kinds.count("pass") + kinds.count("reorder")
+        shard = 16.0 * 2 ** n / world
+        g = world.bit_length() - 1
+        peak, _ = measured_peak()
+        real = passes * 2 * shard / (ms * 1e-3) / 1e9
+        out = {"qubits": n, "gates": len(gl), "n_gpus": world, "ms": ms, "gate_apps_per_s": len(gl) / (ms * 1e-3),
+               "passes": kinds.count("pass"), "reorder_passes": kinds.count("reorder"), "block_sweeps": blocks,
+               "exchanges": kinds.count("exchange"), "fused_exchanges": st.fused_exchanges // 4,
+               "exchange": "peer loads folded into the next pass (TMA over NVLink)" if st.fused_exchanges else
+                           ("NCCL all_to_all_single" if kinds.count("exchange") else "none"),
+               "nvlink_bytes_per_gpu_per_direction": kinds.count("exchange") * (1 - 2.0 ** -g) * shard,
+               "norm2": nrm,
+               "roofline": {"bound": "hbm", "achieved": real, "peak": peak, "unit": "GB/s per GPU", "frac": real / peak,
+                            "note": "REAL bytes: (passes + reorder passes) x 2 x shard bytes / time, exchanges included in the time",
+                            "algorithmic_GBps_per_gpu": len(gl) * 2 * shard / (ms * 1e-3) / 1e9}}
+        del st, comp
+        torch.cuda.empty_cache()
+        return out
+    except Exception as e:                       # never let a secondary measurement break the headline line
+        return {"error": repr(e)}
+
+
 def measure_other_paths(ctx, sim, qc16):
-    """Short, separately timed runs of the other BASELINE configs (not part of the headline timing):
-    device time by CUDA events on the ctx stream, inputs resident."""
+    """Short, separately timed runs of the other BASELINE configs on one GPU (not part of the headline timing):
+    device time by CUDA events on the ctx stream where stated, inputs resident."""
     import torch
+    from qsb import capi
     from qsb.workloads import layered_circuit, to_gate_instances
     from quantum_sim.engine.circuit import QuantumCircuit, GateInstance
     from quantum_sim.engine.noise import NoiseModel, DepolarizingNoise, AmplitudeDampingNoise
@@ -425,19 +594,17 @@ def measure_other_paths(ctx, sim, qc16):
     from quantum_sim.engine.qec import QECSimulator, SteaneCode
     from quantum_sim.engine.simulator import Simulator
     out = {}
-    # config 2: 16-qubit layered circuit, 4096 parameter sets in one launch (noiseless) -> gate-apps/s
+    # config 2 through the engine API (h2d of the 4096 x 473 parameter matrix included; the device-timed figure is `gate_apps`)
     cfg = ParameterizedCircuitConfig.auto_detect(qc16)
     vals = np.random.default_rng(2027).uniform(-np.pi, np.pi, (4096, cfg.num_params))
-    cfg.run_batch(vals)                      # warm-up at the measured batch size (program cached, pool blocks mapped)
+    cfg.run_batch(vals)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     cfg.run_batch(vals)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    gates = len(qc16.gates)
-    out["config2_param_batch"] = {"param_sets": 4096, "gates": gates, "seconds": dt, "gate_apps_per_s": 4096 * gates / dt,
-                                  "algorithmic_GBps": 4096 * gates * 2 * 16 * 2 ** 16 / dt / 1e9,
-                                  "includes": "h2d of the 4096x473 parameter matrix"}
+    out["config2_param_batch_api"] = {"param_sets": 4096, "gates": len(qc16.gates), "seconds": dt,
+                                      "gate_apps_per_s": 4096 * len(qc16.gates) / dt, "api": "ParameterizedCircuitConfig.run_batch"}
     # config 3: 12 qubits, depolarizing + amplitude damping, 500 trajectories -> rho (DMMA) + all-pairs MI per layer
     n = 12
     qc = QuantumCircuit(n)
@@ -456,8 +623,9 @@ def measure_other_paths(ctx, sim, qc16):
     out["config3_ensemble_rho"] = {"qubits": n, "trials": 500, "seconds": dt, "trace": float(np.real(np.trace(rho))),
                                    "purity": float(np.real(np.sum(rho * rho.T))),
                                    "includes": "host draws, 500 trajectories, DMMA rho, 256 MiB d2h"}
-    # the rho accumulation alone (FP64 tensor pipe): rho += (1/N) sum_t psi_t psi_t^dagger over N resident states
+    # the rho accumulation alone against the FP64 tensor-core peak measured in this run (cuBLAS DGEMM)
     try:
+        peak64 = fp64_gemm_peak(torch)
         N3 = 2048
         st3 = ctx.to_device((np.random.default_rng(9).normal(size=(N3, 2 ** n, 2)).view(np.complex128).reshape(N3, 2 ** n)
                              / np.sqrt(2.0 ** (n + 1))))
@@ -469,9 +637,10 @@ def measure_other_paths(ctx, sim, qc16):
         ms3 = ctx.timer_stop()
         full = 8.0 * 4.0 ** n * N3 / (ms3 * 1e-3) / 1e12
         out["config3_rho_kernel"] = {"qubits": n, "states": N3, "ms": ms3, "tflops_full_matrix_convention": full,
-                                     "tflops_executed": full / 2, "fp64_spec_tflops": 37.0, "frac_of_spec": full / 2 / 37.0,
-                                     "note": "Hermitian half computed on DMMA (mma.sync m8n8k4 f64); ncu: DMMA sub-pipe 88 % "
-                                             "active (profiles/r01d_rho_kernel_ncu_full.csv)"}
+                                     "roofline": {"bound": "tensor", "achieved": full / 2, "peak": peak64, "unit": "TFLOP/s",
+                                                  "frac": full / 2 / peak64,
+                                                  "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (best of 5)",
+                                                  "note": "executed flops: the Hermitian half of rho on DMMA (mma.sync m8n8k4 f64)"}}
         del st3, rho3
     except Exception as e:
         out["config3_rho_kernel"] = {"error": repr(e)}
@@ -482,14 +651,19 @@ def measure_other_paths(ctx, sim, qc16):
     u3 = ctx.to_device(np.random.default_rng(3).random((T3, dp.prog.n_draws)))
     snaps = ctx.alloc(T3 * ns * dim3 * 16)
     ctx.run(dp, 8, uniforms=u3, uniforms_stride=dp.prog.n_draws, snapshots=snaps, store=False)
+    mi = all_pairs_mutual_information_device(n, snaps, 0, 8)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     ctx.run(dp, T3, uniforms=u3, uniforms_stride=dp.prog.n_draws, snapshots=snaps, store=False)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
     mi = all_pairs_mutual_information_device(n, snaps, 0, T3 * ns)
     torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    out["config3_layer_mi"] = {"qubits": n, "trials": T3, "layers": ns, "pairs": int(mi.shape[1]), "seconds": dt,
-                               "state_layers_per_s": T3 * ns / dt, "mean_mi_bits": float(mi.mean()),
+    t2 = time.perf_counter()
+    out["config3_layer_mi"] = {"qubits": n, "trials": T3, "layers": ns, "pairs": int(mi.shape[1]), "seconds": t2 - t0,
+                               "state_layers_per_s": T3 * ns / (t2 - t0), "mi_pass_seconds": t2 - t1,
+                               "mi_pass_state_layers_per_s": T3 * ns / (t2 - t1),
+                               "mi_pass_GBps": T3 * ns * dim3 * 16 / (t2 - t1) / 1e9, "mean_mi_bits": float(mi.mean()),
                                "includes": "trajectories with per-column snapshots, RDMs, Jacobi entropies, d2h of MI"}
     del snaps
     # config 4: Steane [[7,1,3]] cycles (13 qubits), batched
@@ -503,7 +677,6 @@ def measure_other_paths(ctx, sim, qc16):
     dt = time.perf_counter() - t0
     out["config4_steane_cycles"] = {"cycles": 2048, "seconds": dt, "cycles_per_s": 2048 / dt,
                                     "includes": "reference streams (one default_rng per trial), decode table, d2h of syndromes"}
-    # throughput mode of config 4: one vectorised generator per sweep point instead of one default_rng per trial
     Tq = 16384
     uq = np.random.default_rng(77).random((Tq, 7))
     qs.run_cycles([t % 2 for t in range(Tq)], "depolarizing", 0.05, None, uniforms=uq)    # warm-up at this batch size
@@ -513,59 +686,39 @@ def measure_other_paths(ctx, sim, qc16):
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     out["config4_steane_cycles_bulk_draws"] = {"cycles": Tq, "seconds": dt, "cycles_per_s": Tq / dt}
-    # complex64 mode of the headline workload (BASELINE: reported separately, tolerance 1e-5): same circuit, noise
-    # and draws; 2^14 complex64 amplitudes per CTA -> clusters of 4 and all 148 SMs busy
+    # complex64 mode of the headline workload (BASELINE: reported separately, tolerance 1e-5): same circuit, noise and
+    # draws on the complex64 context; 2^14 complex64 amplitudes per CTA -> clusters of 4 and all 148 SMs busy
     try:
         from qsb.lowering import lower_circuit
         nm16 = sim._noise_model
         T64, n16 = 2048, qc16.num_qubits
-        u64 = ctx.to_device(np.random.default_rng(777).random((T64, 1)))     # placeholder, resized below
+        c64 = capi.get_context(ctx.device, precision="c64")
         res64 = {}
         for m64 in (14, 13):
             prog64, _ = lower_circuit(n16, qc16.get_ordered_gates(), sim._gate_registry,
                                       lambda name: nm16._channel_specs(name), local_bits=m64, max_local_bits=14)
             D64 = prog64.n_draws
             draws = np.random.default_rng(777).random((T64, D64))
-            ctx.set_precision("c64")
-            try:
-                dp64 = ctx.program(prog64)
-                u64 = ctx.to_device(draws)
-                st64 = ctx.alloc(T64 * (8 << n16))
-                ctx.run(dp64, 256, states=st64, uniforms=u64, uniforms_stride=D64)
-                torch.cuda.synchronize()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                ctx.run(dp64, T64, states=st64, uniforms=u64, uniforms_stride=D64, async_=True)
-                e1.record()
-                torch.cuda.synchronize()
-                ms = e0.elapsed_time(e1)
-                nrm = ctx.alloc(T64 * 16)
-                ctx.overlap(n16, st64, 0, st64, 0, 1, T64, nrm)
-                worst = float(np.max(np.abs(nrm.download(np.complex128, (T64,)) - 1.0)))
-            finally:
-                ctx.set_precision("c128")
+            dp64 = c64.program(prog64)
+            u64 = c64.to_device(draws)
+            st64 = c64.alloc(T64 * (8 << n16))
+            c64.run(dp64, 256, states=st64, uniforms=u64, uniforms_stride=D64)
+            c64.timer_start()
+            c64.run(dp64, T64, states=st64, uniforms=u64, uniforms_stride=D64, async_=True)
+            ms = c64.timer_stop()
+            nrm = c64.alloc(T64 * 16)
+            c64.overlap(n16, st64, 0, st64, 0, 1, T64, nrm)
+            worst = float(np.max(np.abs(nrm.download(np.complex128, (T64,)) - 1.0)))
             res64[f"local_bits_{m64}"] = {"cluster": 1 << (n16 - m64), "trajectories": T64, "ms": ms,
                                           "trajectories_per_s": T64 / (ms * 1e-3), "max_norm_error": worst}
         out["headline_complex64"] = res64
     except Exception as e:
         out["headline_complex64"] = {"error": repr(e)}
-    # config 5 (single-GPU leg): 26-qubit layered circuit streamed through shared memory
+    # config 5 on one GPU at 26 qubits (the 1 GiB state of VERDICT r01's 37 ms figure): plan + upload outside the timing
     try:
-        from qsb.bigstate import BigState
-        nb = 26
-        gl = [(g.gate_name, list(g.target_qubits), list(g.params)) for g in
-              to_gate_instances(layered_circuit(nb, 20, 2026), GateInstance)]
-        st = BigState(nb, layout="textbook", distributed=False)   # rank 0 alone: no collectives here
-        st.apply_gates(gl[:8])
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        st.apply_gates(gl)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        out["config5_streamed_26q"] = {"qubits": nb, "gates": len(gl), "seconds": dt, "gate_apps_per_s": len(gl) / dt,
-                                       "algorithmic_GBps": len(gl) * 2 * 16 * 2 ** nb / dt / 1e9, "norm2": st.norm2()}
-        del st
-    except Exception as e:           # never let a secondary measurement break the headline line
+        import torch.distributed as dist
+        out["config5_streamed_26q"] = measure_sharded_state(0, 1, torch, dist, 26)
+    except Exception as e:
         out["config5_streamed_26q"] = {"error": repr(e)}
     return out
 
@@ -581,7 +734,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", action="store_true", help="(internal) print the cpu_baseline object and exit")
-    ap.add_argument("--no-extras", action="store_true", help="skip the short secondary measurements (configs 2-5)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the short secondary measurements (configs 3-5)")
+    ap.add_argument("--big-qubits", type=int, default=30, help="config 5: qubits of the state sharded over all ranks")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
