@@ -431,10 +431,12 @@ def run_ours(args):
 
     # ---- the other half of the metric and the sharded state: measured on ALL ranks (max over ranks)
     gate_apps = measure_gate_apps(ctx, qc, rank, world, torch, dist)
-    big = None if args.no_extras else measure_sharded_state(rank, world, torch, dist, args.big_qubits)
     extras = None
     if rank == 0 and world == 1 and not args.no_extras:
         extras = measure_other_paths(ctx, sim, qc)
+    # last: the 16 GiB state goes through torch's allocator, and the pool-backed legs above were measured 10x slower
+    # (block re-mapping) when they ran after its release
+    big = None if args.no_extras else measure_sharded_state(rank, world, torch, dist, args.big_qubits)
     if rank == 0:
         peak, peak_src = measured_peak()
         kms = float(np.mean(kern_ms))
