@@ -868,13 +868,31 @@ int qsb_rdm_all(qsb_ctx* ctx, int32_t n, qsb_buffer* states, int64_t first, int6
   if ((rc = need(ctx, states, (first + count) * dim * ctx->amp_bytes, "states"))) return rc;
   CU(ctx, cudaSetDevice(ctx->device));
   const char* s = (const char*)states->ptr + first * dim * ctx->amp_bytes;
+  if (rdm1 && (rc = need(ctx, rdm1, count * n * 4 * 16, "rdm1"))) return rc;
+  if (rdm2 && npairs > 0 && (rc = need(ctx, rdm2, count * npairs * 16 * 16, "rdm2"))) return rc;
+  if (n >= 4 && n <= 13 && !getenv("QSB_RDM_SCALAR")) {
+    // one read of every state: all pairs as 8x8 real Grams on the FP64 tensor cores (qsb_rdm_gram_kernel)
+    const size_t smem = (size_t)16 << n;
+    static bool attr[2][64] = {{false}};
+    const int which = ctx->amp_bytes == 8 ? 1 : 0;
+    if (!attr[which][ctx->device & 63]) {
+      if (which) CU(ctx, cudaFuncSetAttribute(qsb_rdm_gram_kernel<c64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 << 13));
+      else CU(ctx, cudaFuncSetAttribute(qsb_rdm_gram_kernel<c128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 << 13));
+      attr[which][ctx->device & 63] = true;
+    }
+    const int per_sm = (int)((200u << 10) / (smem + 1024)) < 1 ? 1 : (int)((200u << 10) / (smem + 1024));
+    int64_t grid = (int64_t)ctx->sm_count * (per_sm > 4 ? 4 : per_sm);
+    if (grid > count) grid = count;
+    QSB_BY_AMP(ctx, (qsb_rdm_gram_kernel<A><<<(unsigned)grid, 256, smem, ctx->stream>>>(
+                        (const A*)s, n, npairs, count, rdm1 ? (c128*)rdm1->ptr : nullptr,
+                        (rdm2 && npairs > 0) ? (c128*)rdm2->ptr : nullptr)));
+    return after_launch(ctx, "rdm_gram");
+  }
   if (rdm1) {
-    if ((rc = need(ctx, rdm1, count * n * 4 * 16, "rdm1"))) return rc;
     QSB_BY_AMP(ctx, (qsb_rdm1_kernel<A><<<(unsigned)(count * n), 256, 0, ctx->stream>>>((const A*)s, n, (c128*)rdm1->ptr)));
     if ((rc = after_launch(ctx, "rdm1"))) return rc;
   }
   if (rdm2 && npairs > 0) {
-    if ((rc = need(ctx, rdm2, count * npairs * 16 * 16, "rdm2"))) return rc;
     QSB_BY_AMP(ctx, (qsb_rdm2_kernel<A><<<(unsigned)(count * npairs), 256, 0, ctx->stream>>>((const A*)s, n, npairs,
                                                                                           (c128*)rdm2->ptr)));
     if ((rc = after_launch(ctx, "rdm2"))) return rc;
@@ -964,6 +982,16 @@ int qsb_readout_transform(qsb_ctx* ctx, int32_t n, qsb_buffer* probs, int64_t co
     return fail(ctx, QSB_E_INVAL, "Readout error probabilities must be in [0, 1]");
   if ((rc = need(ctx, probs, count * dim * 8, "probabilities"))) return rc;
   CU(ctx, cudaSetDevice(ctx->device));
+  if (n <= 14 && !getenv("QSB_READOUT_AXIS")) {        // the whole transform in shared memory, one launch
+    static bool attr[64] = {false};
+    if (!attr[ctx->device & 63]) {
+      CU(ctx, cudaFuncSetAttribute(qsb_readout_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 << 14));
+      attr[ctx->device & 63] = true;
+    }
+    qsb_readout_fused_kernel<<<(unsigned)count, 512, (size_t)8 << n, ctx->stream>>>((double*)probs->ptr, n, 1.0 - p01, p10,
+                                                                                    p01, 1.0 - p10);
+    return after_launch(ctx, "readout_transform");
+  }
   // axis q of the reference's [2]*n tensor is bit n-1-q; axes are transformed in order q = 0..n-1 (noise.py:163)
   for (int q = 0; q < n; ++q) {
     qsb_readout_axis_kernel<<<grid_for(ctx, count * dim / 2, 256), 256, 0, ctx->stream>>>(

@@ -425,6 +425,124 @@ __global__ void qsb_rdm2_kernel(const A* __restrict__ psi, int n, int npairs, c1
   }
 }
 
+__device__ __forceinline__ void qsb_dmma(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// ---- all 1- and 2-qubit RDMs of a state from ONE read, on the FP64 tensor cores -------------------------------------
+// (analysis.py:120-166 builds the 2^n x 2^n outer product per call; state_vector.py:121-140; the event detector asks
+// for all n(n-1)/2 pairs of every state, analysis.py:315-333.)
+// rho_ij[r][c] = sum_env M[r][env] conj(M[c][env]) is the Gram matrix of the 4 x 2^(n-2) complex matrix M of the state
+// viewed with bits (i, j) as the row index.  Stacked as the real 8 x 2^(n-2) matrix X = [Re M; Im M] it is one real 8 x 8
+// Gram X X^T -- exactly the shape of mma.sync.m8n8k4.f64 with B = A^T, so ONE register per lane feeds both operands:
+// lane (g, t) holds X[g][k0 + t].  rho = (G_rr + G_ii) + i (G_ir - G_ri) over the four 4 x 4 blocks of G.
+// One CTA keeps one state in shared memory (n <= 13; XOR-folded so that the four rows of a lane group hit different
+// banks) and its eight warps share the pairs; 1-qubit RDMs fall out of the pair (q, q+1) [(n-2, n-1) for the last
+// qubit] by a partial trace.  HBM sees the state once instead of n(n-1)/2 + n times.
+__device__ __forceinline__ int qsb_rdm_swz(int i) { return i ^ (((i >> 3) ^ (i >> 6) ^ (i >> 9) ^ (i >> 12)) & 7); }
+
+template <class A>
+__global__ void __launch_bounds__(256) qsb_rdm_gram_kernel(const A* __restrict__ psi, int n, int npairs, int64_t count,
+                                                            c128* __restrict__ rdm1, c128* __restrict__ rdm2) {
+  extern __shared__ __align__(16) unsigned char qsb_rdm_smem[];
+  c128* st = reinterpret_cast<c128*>(qsb_rdm_smem);
+  const int dim = 1 << n;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int r = g & 3, part = g >> 2;                  // row of M, 0 = real part / 1 = imaginary part
+  for (int64_t s = blockIdx.x; s < count; s += gridDim.x) {
+    __syncthreads();                                   // the previous state's readers are done
+    const A* src = psi + s * dim;
+    for (int i = threadIdx.x; i < dim; i += 256) st[qsb_rdm_swz(i)] = qsb_wide(src[i]);
+    __syncthreads();
+    for (int p = warp; p < npairs; p += 8) {
+      int qi = 0, rem = p;
+      while (rem >= n - 1 - qi) { rem -= n - 1 - qi; ++qi; }
+      const int qj = qi + 1 + rem;
+      if (!rdm2 && rem != 0 && p != npairs - 1) continue;    // 1-qubit RDMs only: n - 1 pairs carry them all
+      const int bh = n - 1 - qi, bl = n - 1 - qj;      // index bits of qubits i (row MSB) and j; bh > bl
+      // the two lowest index bits outside {bh, bl} carry t (the k index inside one DMMA); the other n - 4 free bits are
+      // walked by a masked increment
+      int p0 = 0;
+      while (p0 == bl || p0 == bh) ++p0;
+      int p1 = p0 + 1;
+      while (p1 == bl || p1 == bh) ++p1;
+      const int fixed = (1 << bh) | (1 << bl) | (1 << p0) | (1 << p1);
+      const int freemask = (dim - 1) & ~fixed;
+      const int lane_off = ((r >> 1) << bh) | ((r & 1) << bl) | ((t & 1) << p0) | ((t >> 1) << p1);
+      const int lane_swz = qsb_rdm_swz(lane_off);      // the fold is linear over XOR and the bit sets are disjoint
+      double d0 = 0.0, d1 = 0.0;
+      int base = 0;
+      const int steps = dim >> 4;
+#pragma unroll 4
+      for (int k = 0; k < steps; ++k) {
+        const int slot = qsb_rdm_swz(base) ^ lane_swz;
+        const double v = reinterpret_cast<const double*>(st + slot)[part];
+        qsb_dmma(d0, d1, v, v);
+        base = ((base | fixed) + 1) & freemask;
+      }
+      // G[g][2t], G[g][2t+1] -> rho[r][c], c = 2t, 2t+1 for the lanes with g < 4, t < 2
+      const double rr0 = d0, rr1 = d1;
+      const double ii0 = __shfl_sync(0xffffffffu, d0, ((g + 4) & 7) * 4 + ((t + 2) & 3));
+      const double ii1 = __shfl_sync(0xffffffffu, d1, ((g + 4) & 7) * 4 + ((t + 2) & 3));
+      const double ir0 = __shfl_sync(0xffffffffu, d0, ((g + 4) & 7) * 4 + t);       // G[r + 4][c]  = Im_r . Re_c
+      const double ir1 = __shfl_sync(0xffffffffu, d1, ((g + 4) & 7) * 4 + t);
+      const double ri0 = __shfl_sync(0xffffffffu, d0, g * 4 + ((t + 2) & 3));       // G[r][c + 4]  = Re_r . Im_c
+      const double ri1 = __shfl_sync(0xffffffffu, d1, g * 4 + ((t + 2) & 3));
+      c128 e0 = make_double2(rr0 + ii0, ir0 - ri0), e1 = make_double2(rr1 + ii1, ir1 - ri1);
+      if (g < 4 && t < 2) {
+        if (2 * t == g) e0.y = 0.0;                    // the diagonal of a Gram matrix is real
+        if (2 * t + 1 == g) e1.y = 0.0;
+        if (rdm2) {
+          c128* o = rdm2 + (s * npairs + p) * 16 + g * 4 + 2 * t;
+          o[0] = e0;
+          o[1] = e1;
+        }
+      }
+      if (rdm1) {
+        // partial traces: rho_i[a][b] = sum_c rho_ij[(a, c)][(b, c)] from pair (qi, qi + 1); the last qubit takes
+        // rho_j[a][b] = sum_c rho_ij[(c, a)][(c, b)] from pair (n - 2, n - 1)
+        const bool first_of_qi = rem == 0;
+        const bool last_pair = p == npairs - 1;
+        if (first_of_qi || last_pair) {
+          // gather the 16 entries: entry (row, col) sits in lane (row, col >> 1), register col & 1
+          c128 m[4][4];
+#pragma unroll
+          for (int row = 0; row < 4; ++row)
+#pragma unroll
+            for (int col = 0; col < 4; ++col) {
+              const int srcl = row * 4 + (col >> 1);
+              const double x = __shfl_sync(0xffffffffu, (col & 1) ? e1.x : e0.x, srcl);
+              const double y = __shfl_sync(0xffffffffu, (col & 1) ? e1.y : e0.y, srcl);
+              m[row][col] = make_double2(x, y);
+            }
+          if (lane == 0) {
+            if (first_of_qi) {
+              c128* o = rdm1 + (s * n + qi) * 4;
+#pragma unroll
+              for (int a2 = 0; a2 < 2; ++a2)
+#pragma unroll
+                for (int b2 = 0; b2 < 2; ++b2)
+                  o[a2 * 2 + b2] = make_double2(m[2 * a2][2 * b2].x + m[2 * a2 + 1][2 * b2 + 1].x,
+                                                a2 == b2 ? 0.0 : m[2 * a2][2 * b2].y + m[2 * a2 + 1][2 * b2 + 1].y);
+            }
+            if (last_pair) {
+              c128* o = rdm1 + (s * n + qj) * 4;
+#pragma unroll
+              for (int a2 = 0; a2 < 2; ++a2)
+#pragma unroll
+                for (int b2 = 0; b2 < 2; ++b2)
+                  o[a2 * 2 + b2] = make_double2(m[a2][b2].x + m[2 + a2][2 + b2].x,
+                                                a2 == b2 ? 0.0 : m[a2][b2].y + m[2 + a2][2 + b2].y);
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
 // Reduced density matrix of an arbitrary set of k <= 6 kept qubits (analysis.py:120-166):
 // rho[r][c] = sum_env psi[r, env] conj(psi[c, env]); kept_bits[0] = index bit of the first kept qubit (the MSB of
 // r), env_bits = the other n - k index bits.  One CTA per state; a thread owns whole (r, c) entries, so every
@@ -556,10 +674,6 @@ __global__ void qsb_mi_kernel(const c128* __restrict__ rdm1, const c128* __restr
 #define QSB_RHO_KC 16
 #define QSB_RHO_PAD 2          // doubles of row padding: the 4 k-rows a fragment load touches hit different banks
 
-__device__ __forceinline__ void qsb_dmma(double& d0, double& d1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-               : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
-}
 
 template <class A>
 __global__ void __launch_bounds__(256) qsb_rho_kernel(const A* __restrict__ psi, int64_t dim, int64_t count,
@@ -650,6 +764,35 @@ __global__ void qsb_readout_axis_kernel(double* __restrict__ p, int64_t dim, int
     q[i0] = c00 * p0 + c01 * p1;
     q[i0 | ((int64_t)1 << b)] = c10 * p0 + c11 * p1;
   }
+}
+
+// ReadoutError.apply_to_distribution (noise.py:141-175) for n <= 14 in ONE launch: a CTA keeps one distribution
+// (8 * 2^n bytes <= 128 KiB) in shared memory, applies the 2x2 confusion butterfly of every axis in the reference's
+// order (axis q = index bit n-1-q, q ascending), sums, renormalises (total > 1e-15) and writes it back -- one read
+// and one write of HBM instead of n + 1 of each.
+__global__ void __launch_bounds__(512) qsb_readout_fused_kernel(double* __restrict__ p, int n, double c00, double c01,
+                                                                 double c10, double c11) {
+  extern __shared__ __align__(16) unsigned char qsb_ro_smem[];
+  double* sp = reinterpret_cast<double*>(qsb_ro_smem);
+  __shared__ double scratch[32];
+  const int dim = 1 << n, half = dim >> 1;
+  double* q = p + (int64_t)blockIdx.x * dim;
+  for (int i = threadIdx.x; i < dim; i += blockDim.x) sp[i] = q[i];
+  __syncthreads();
+  for (int b = n - 1; b >= 0; --b) {
+    for (int g = threadIdx.x; g < half; g += blockDim.x) {
+      const int i0 = ((g >> b) << (b + 1)) | (g & ((1 << b) - 1));
+      const double p0 = sp[i0], p1 = sp[i0 | (1 << b)];
+      sp[i0] = c00 * p0 + c01 * p1;
+      sp[i0 | (1 << b)] = c10 * p0 + c11 * p1;
+    }
+    __syncthreads();
+  }
+  double v[1] = {0.0};
+  for (int i = threadIdx.x; i < dim; i += blockDim.x) v[0] += sp[i];
+  qsb_block_sum<1>(v, scratch);
+  const bool norm = v[0] > 1e-15;
+  for (int i = threadIdx.x; i < dim; i += blockDim.x) q[i] = norm ? sp[i] / v[0] : sp[i];
 }
 
 // divide each distribution by its total if total > 1e-15 (noise.py:172-174); one CTA per distribution

@@ -83,8 +83,9 @@ def test_masked_parity_steane_checks(ctx):
             assert abs(got[t, k, 0] - e) < 1e-13 and abs(got[t, k, 1] - o) < 1e-13
 
 
-@pytest.mark.parametrize("n", [2, 5, 12])
+@pytest.mark.parametrize("n", [2, 4, 5, 8, 12, 13, 14])
 def test_rdm_all_pairs(ctx, n):
+    """n = 4..13: one read of the state, all pairs as 8x8 real Grams on DMMA (qsb_rdm_gram_kernel); else the per-pair kernels."""
     rng = np.random.default_rng(400 + n)
     psi = rand_states(rng, 2, n)
     npairs = n * (n - 1) // 2
@@ -103,6 +104,51 @@ def test_rdm_all_pairs(ctx, n):
                 k += 1
 
 
+def test_rdm_gram_kernel_batches_and_single_outputs(ctx):
+    """More states than CTAs (grid-stride), 1-qubit RDMs alone (n - 1 pairs carry them), 2-qubit RDMs alone, the scalar
+    per-pair kernels as a second implementation, and complex64 input."""
+    import os
+    from qsb import capi
+    n, count = 9, 700
+    npairs = n * (n - 1) // 2
+    rng = np.random.default_rng(77)
+    psi = rand_states(rng, count, n)
+    s = ctx.to_device(psi)
+    r1, r2 = ctx.alloc(count * n * 4 * 16), ctx.alloc(count * npairs * 16 * 16)
+    ctx.rdm_all(n, s, 0, count, r1, r2)
+    g1, g2 = r1.download(np.complex128, (count, n, 2, 2)), r2.download(np.complex128, (count, npairs, 4, 4))
+    for t in (0, 1, 147, 148, 443, 699):
+        for q in range(n):
+            assert np.max(np.abs(g1[t, q] - O.reduced_density_matrix_1q(psi[t], n, q))) < 1e-13
+        k = 0
+        for i in range(n):
+            for jj in range(i + 1, n):
+                assert np.max(np.abs(g2[t, k] - O.partial_trace(psi[t], n, [i, jj]))) < 1e-13
+                k += 1
+    assert np.max(np.abs(g2 - np.conj(np.swapaxes(g2, -1, -2)))) < 1e-15          # Hermitian to rounding
+    only1 = ctx.alloc(count * n * 4 * 16).zero()
+    ctx.rdm_all(n, s, 0, count, only1, None)
+    assert np.array_equal(only1.download(np.complex128, (count, n, 2, 2)), g1)
+    only2 = ctx.alloc(count * npairs * 16 * 16).zero()
+    ctx.rdm_all(n, s, 0, count, None, only2)
+    assert np.array_equal(only2.download(np.complex128, (count, npairs, 4, 4)), g2)
+    os.environ["QSB_RDM_SCALAR"] = "1"                    # round 1's kernels: one CTA per (state, pair)
+    try:
+        a1, a2 = ctx.alloc(count * n * 4 * 16), ctx.alloc(count * npairs * 16 * 16)
+        ctx.rdm_all(n, s, 0, count, a1, a2)
+    finally:
+        del os.environ["QSB_RDM_SCALAR"]
+    assert np.max(np.abs(a1.download(np.complex128, (count, n, 2, 2)) - g1)) < 1e-14
+    assert np.max(np.abs(a2.download(np.complex128, (count, npairs, 4, 4)) - g2)) < 1e-14
+    c64 = capi.get_context(precision="c64")
+    p64 = psi[:5].astype(np.complex64)
+    b1, b2 = c64.alloc(5 * n * 4 * 16), c64.alloc(5 * npairs * 16 * 16)
+    c64.rdm_all(n, c64.to_device(p64), 0, 5, b1, b2)
+    w = p64.astype(np.complex128)
+    got2 = b2.download(np.complex128, (5, npairs, 4, 4))
+    assert np.max(np.abs(got2[3, 0] - O.partial_trace(w[3], n, [0, 1]))) < 1e-13
+
+
 @pytest.mark.parametrize("n,count", [(3, 7), (6, 33), (8, 100)])
 def test_rho_accumulate(ctx, n, count):
     rng = np.random.default_rng(500 + n)
@@ -115,8 +161,9 @@ def test_rho_accumulate(ctx, n, count):
     assert np.max(np.abs(got - want)) < 1e-14
 
 
-@pytest.mark.parametrize("n", [1, 3, 8, 16])
+@pytest.mark.parametrize("n", [1, 3, 8, 12, 14, 15, 16])
 def test_readout_transform(ctx, n):
+    """n <= 14: all axes + renormalisation in one shared-memory kernel; above: one launch per axis."""
     rng = np.random.default_rng(600 + n)
     p = rng.random((2, 2 ** n))
     p /= p.sum(1, keepdims=True)
