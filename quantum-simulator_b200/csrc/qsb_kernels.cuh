@@ -440,7 +440,10 @@ __device__ __forceinline__ void qsb_dmma(double& d0, double& d1, double a, doubl
 // One CTA keeps one state in shared memory (n <= 13; XOR-folded so that the four rows of a lane group hit different
 // banks) and its eight warps share the pairs; 1-qubit RDMs fall out of the pair (q, q+1) [(n-2, n-1) for the last
 // qubit] by a partial trace.  HBM sees the state once instead of n(n-1)/2 + n times.
-__device__ __forceinline__ int qsb_rdm_swz(int i) { return i ^ (((i >> 3) ^ (i >> 6) ^ (i >> 9) ^ (i >> 12)) & 7); }
+// Shared-memory slot of amplitude i: the parity of the index bits above bit 2 is XORed into bit 2.  The eight amplitudes a
+// half-warp reads differ in three index bits -- the row bit of the pair and the two lowest other bits -- so whichever bit
+// the pair uses, they land in eight different 16-byte bank groups.  (Linear over XOR: swz(a ^ b) = swz(a) ^ swz(b).)
+__device__ __forceinline__ int qsb_rdm_swz(int i) { return i ^ ((__popc(i >> 3) & 1) << 2); }
 
 template <class A>
 __global__ void __launch_bounds__(256) qsb_rdm_gram_kernel(const A* __restrict__ psi, int n, int npairs, int64_t count,
@@ -450,7 +453,10 @@ __global__ void __launch_bounds__(256) qsb_rdm_gram_kernel(const A* __restrict__
   const int dim = 1 << n;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int r = g & 3, part = g >> 2;                  // row of M, 0 = real part / 1 = imaginary part
+  // rows of X interleave the parts: row 2r = Re M[r], row 2r + 1 = Im M[r].  A half-warp (g = 0..3) then reads BOTH
+  // 8-byte halves of eight amplitudes -- 128 contiguous-per-amplitude bytes, all 32 banks -- instead of the real halves of
+  // sixteen (which can use only half of the banks: ncu showed 58 % of the wavefronts as conflict replays)
+  const int r = g >> 1, part = g & 1;
   for (int64_t s = blockIdx.x; s < count; s += gridDim.x) {
     __syncthreads();                                   // the previous state's readers are done
     const A* src = psi + s * dim;
@@ -472,33 +478,38 @@ __global__ void __launch_bounds__(256) qsb_rdm_gram_kernel(const A* __restrict__
       const int freemask = (dim - 1) & ~fixed;
       const int lane_off = ((r >> 1) << bh) | ((r & 1) << bl) | ((t & 1) << p0) | ((t >> 1) << p1);
       const int lane_swz = qsb_rdm_swz(lane_off);      // the fold is linear over XOR and the bit sets are disjoint
-      double d0 = 0.0, d1 = 0.0;
+      // two independent accumulator pairs (even / odd k steps): one dependent DMMA chain per warp left the tensor pipe
+      // half idle (ncu: dmma sub-pipe 50 % active, math_pipe_throttle the top stall)
+      double d0 = 0.0, d1 = 0.0, f0 = 0.0, f1 = 0.0;
       int base = 0;
-      const int steps = dim >> 4;
+      const unsigned char* lane_ptr = qsb_rdm_smem + 8 * part;
+      const int steps = dim >> 4;                       // >= 1; even for n >= 5
+      int k = 0;
 #pragma unroll 4
-      for (int k = 0; k < steps; ++k) {
-        const int slot = qsb_rdm_swz(base) ^ lane_swz;
-        const double v = reinterpret_cast<const double*>(st + slot)[part];
-        qsb_dmma(d0, d1, v, v);
+      for (; k + 1 < steps; k += 2) {
+        const int slot_a = qsb_rdm_swz(base) ^ lane_swz;
         base = ((base | fixed) + 1) & freemask;
+        const int slot_b = qsb_rdm_swz(base) ^ lane_swz;
+        base = ((base | fixed) + 1) & freemask;
+        const double va = *reinterpret_cast<const double*>(lane_ptr + (slot_a << 4));
+        const double vb = *reinterpret_cast<const double*>(lane_ptr + (slot_b << 4));
+        qsb_dmma(d0, d1, va, va);
+        qsb_dmma(f0, f1, vb, vb);
       }
-      // G[g][2t], G[g][2t+1] -> rho[r][c], c = 2t, 2t+1 for the lanes with g < 4, t < 2
-      const double rr0 = d0, rr1 = d1;
-      const double ii0 = __shfl_sync(0xffffffffu, d0, ((g + 4) & 7) * 4 + ((t + 2) & 3));
-      const double ii1 = __shfl_sync(0xffffffffu, d1, ((g + 4) & 7) * 4 + ((t + 2) & 3));
-      const double ir0 = __shfl_sync(0xffffffffu, d0, ((g + 4) & 7) * 4 + t);       // G[r + 4][c]  = Im_r . Re_c
-      const double ir1 = __shfl_sync(0xffffffffu, d1, ((g + 4) & 7) * 4 + t);
-      const double ri0 = __shfl_sync(0xffffffffu, d0, g * 4 + ((t + 2) & 3));       // G[r][c + 4]  = Re_r . Im_c
-      const double ri1 = __shfl_sync(0xffffffffu, d1, g * 4 + ((t + 2) & 3));
-      c128 e0 = make_double2(rr0 + ii0, ir0 - ri0), e1 = make_double2(rr1 + ii1, ir1 - ri1);
-      if (g < 4 && t < 2) {
-        if (2 * t == g) e0.y = 0.0;                    // the diagonal of a Gram matrix is real
-        if (2 * t + 1 == g) e1.y = 0.0;
-        if (rdm2) {
-          c128* o = rdm2 + (s * npairs + p) * 16 + g * 4 + 2 * t;
-          o[0] = e0;
-          o[1] = e1;
-        }
+      if (k < steps) {
+        const double va = *reinterpret_cast<const double*>(lane_ptr + ((qsb_rdm_swz(base) ^ lane_swz) << 4));
+        qsb_dmma(d0, d1, va, va);
+      }
+      d0 += f0;
+      d1 += f1;
+      // lane (g, t): d0 = G[g][2t], d1 = G[g][2t + 1].  With g = 2r: d0 = Re_r.Re_c, d1 = Re_r.Im_c (c = t); the lane
+      // four places on (g + 1) holds Im_r.Re_c, Im_r.Im_c:  rho[r][c] = (ReRe + ImIm) + i (ImRe - ReIm)
+      const double o0 = __shfl_down_sync(0xffffffffu, d0, 4);
+      const double o1 = __shfl_down_sync(0xffffffffu, d1, 4);
+      c128 e = make_double2(d0 + o1, o0 - d1);
+      if (!(g & 1)) {
+        if (r == t) e.y = 0.0;                         // the diagonal of a Gram matrix is real
+        if (rdm2) rdm2[(s * npairs + p) * 16 + r * 4 + t] = e;
       }
       if (rdm1) {
         // partial traces: rho_i[a][b] = sum_c rho_ij[(a, c)][(b, c)] from pair (qi, qi + 1); the last qubit takes
@@ -506,17 +517,13 @@ __global__ void __launch_bounds__(256) qsb_rdm_gram_kernel(const A* __restrict__
         const bool first_of_qi = rem == 0;
         const bool last_pair = p == npairs - 1;
         if (first_of_qi || last_pair) {
-          // gather the 16 entries: entry (row, col) sits in lane (row, col >> 1), register col & 1
+          // gather the 16 entries: entry (row, col) sits in lane (g = 2 row, t = col)
           c128 m[4][4];
 #pragma unroll
           for (int row = 0; row < 4; ++row)
 #pragma unroll
-            for (int col = 0; col < 4; ++col) {
-              const int srcl = row * 4 + (col >> 1);
-              const double x = __shfl_sync(0xffffffffu, (col & 1) ? e1.x : e0.x, srcl);
-              const double y = __shfl_sync(0xffffffffu, (col & 1) ? e1.y : e0.y, srcl);
-              m[row][col] = make_double2(x, y);
-            }
+            for (int col = 0; col < 4; ++col)
+              m[row][col] = make_double2(__shfl_sync(0xffffffffu, e.x, 8 * row + col), __shfl_sync(0xffffffffu, e.y, 8 * row + col));
           if (lane == 0) {
             if (first_of_qi) {
               c128* o = rdm1 + (s * n + qi) * 4;

@@ -45,11 +45,52 @@ def _circuit_key(circuit):
 
 
 class Simulator:
-    """Executes a QuantumCircuit; optional NoiseModel applied after every gate."""
+    """Executes a QuantumCircuit; optional NoiseModel applied after every gate.
 
-    def __init__(self, noise_model=None):
+    Two backend switches beyond the reference's signature ("config / flags"):
+      precision = "c128" (default: the reference's complex128, amplitudes to 1e-12) | "c64" (complex64 states on the
+                  device, 2^14-amplitude tiles, tolerance 1e-5; results come back as complex128 arrays)
+      rng_mode  = "reference" (default: Kraus draws are taken from NoiseModel._rng exactly like the reference's
+                  `choice` calls, so seeded counts are bit-identical) | "philox" (counter-based Philox4x32-10 in the
+                  kernel: draw d of trajectory t = f(philox_seed, t, d); no host generator, no upload -- the
+                  throughput mode; trajectories are numbered consecutively over the calls of this Simulator)."""
+
+    def __init__(self, noise_model=None, precision="c128", rng_mode="reference", philox_seed=0):
+        if precision not in ("c128", "c64"):
+            raise ValueError("precision must be 'c128' or 'c64'")
+        if rng_mode not in ("reference", "philox"):
+            raise ValueError("rng_mode must be 'reference' or 'philox'")
         self._gate_registry = GateRegistry.instance()
         self._noise_model = noise_model
+        self._precision = precision
+        self._rng_mode = rng_mode
+        self._philox_seed = int(philox_seed)
+        self._philox_next = 0            # global index of the next trajectory (Philox counter)
+
+    # ---- backend plumbing ------------------------------------------------------------------
+    def _ctx(self):
+        return runtime.ctx(self._precision)
+
+    def _amp(self):
+        return (8, np.complex64) if self._precision == "c64" else (16, np.complex128)
+
+    def _draw_kwargs(self, c, dp, count, uniforms=None):
+        """Kraus draws of `count` trajectories: the reference's stream (uploaded) or the in-kernel Philox stream."""
+        d = dp.prog.n_draws
+        if not d:
+            return {}
+        if self._rng_mode == "philox":
+            kw = dict(seed=self._philox_seed, traj_offset=self._philox_next)
+            self._philox_next += count
+            return kw
+        if uniforms is None:
+            uniforms = self._noise_model._rng.random(count * d).reshape(count, d)
+        return dict(uniforms=c.to_device(uniforms), uniforms_stride=d)
+
+    def _host_states(self, buf, shape):
+        ab, dt = self._amp()
+        arr = buf.download(dt, shape)
+        return arr if dt is np.complex128 else arr.astype(np.complex128)
 
     # ---- lowering ------------------------------------------------------------------------
     def _program(self, circuit, record_steps=False, with_noise=True):
@@ -59,15 +100,16 @@ class Simulator:
         key = ("circuit", layout, _circuit_key(circuit), record_steps,
                nm._signature() if nm is not None and hasattr(nm, "_signature") else None)
         has_meas = [False]
+        max_bits = 14 if self._precision == "c64" else 13       # complex64 tiles hold twice the amplitudes
 
         def build():
             channels = (lambda name: nm._channel_specs(name)) if nm is not None else None
             prog, hm = lower_circuit(n, circuit.get_ordered_gates(), self._gate_registry, channels,
-                                     record_steps=record_steps, layout=layout)
+                                     record_steps=record_steps, layout=layout, max_local_bits=max_bits)
             prog.meta["has_measurement"] = hm
             return prog
 
-        dp = runtime.cached_program(key, build)
+        dp = runtime.cached_program(key, build, self._precision)
         return dp, dp.prog.meta["has_measurement"]
 
     @staticmethod
@@ -84,24 +126,23 @@ class Simulator:
         if n != len(circuit.initial_states):
             n = len(circuit.initial_states)       # from_initial_states sizes the register (simulator.py:53)
         dp, has_meas = self._program(circuit, record_steps)
-        c = runtime.ctx()
+        c = self._ctx()
+        ab, _ = self._amp()
         dim = 2 ** n
-        state_buf = c.alloc(16 * dim)
-        kw = {}
-        if dp.prog.n_draws:
-            draws = self._noise_model._rng.random(dp.prog.n_draws)
-            kw.update(uniforms=c.to_device(draws), uniforms_stride=dp.prog.n_draws)
+        state_buf = c.alloc(ab * dim)
+        kw = self._draw_kwargs(c, dp, 1)
         snaps = None
         if dp.prog.n_snapshots:
-            snaps = c.alloc(dp.prog.n_snapshots * dim * 16)
+            snaps = c.alloc(dp.prog.n_snapshots * dim * ab)
             kw.update(snapshots=snaps)
         c.run(dp, 1, states=state_buf, default_basis=self._basis(circuit), **kw)
-        state = StateVector._from_device(n, state_buf)
+        state = (StateVector._from_device(n, state_buf) if self._precision == "c128"
+                 else StateVector._from_host(n, self._host_states(state_buf, (dim,))))
         step_states = None
         if record_steps:
             step_states = []
             if snaps is not None:
-                host = snaps.download(np.complex128, (dp.prog.n_snapshots, dim))
+                host = self._host_states(snaps, (dp.prog.n_snapshots, dim))
                 step_states = [StateVector._from_host(n, host[i].copy()) for i in range(dp.prog.n_snapshots)]
 
         if has_meas or shots > 0:
@@ -127,15 +168,13 @@ class Simulator:
         dp, _ = self._program(circuit, record_steps=True)
         if dp.prog.n_snapshots == 0:
             return
-        c = runtime.ctx()
+        c = self._ctx()
+        ab, _ = self._amp()
         dim = 2 ** n
-        kw = {}
-        if dp.prog.n_draws:
-            kw.update(uniforms=c.to_device(self._noise_model._rng.random(dp.prog.n_draws)),
-                      uniforms_stride=dp.prog.n_draws)
-        snaps = c.alloc(dp.prog.n_snapshots * dim * 16)
+        kw = self._draw_kwargs(c, dp, 1)
+        snaps = c.alloc(dp.prog.n_snapshots * dim * ab)
         c.run(dp, 1, default_basis=self._basis(circuit), snapshots=snaps, **kw)
-        host = snaps.download(np.complex128, (dp.prog.n_snapshots, dim))
+        host = self._host_states(snaps, (dp.prog.n_snapshots, dim))
         for i in range(dp.prog.n_snapshots):
             yield StateVector._from_host(n, host[i].copy()), i
 
@@ -146,12 +185,11 @@ class Simulator:
     def _trajectory_batch(self, circuit, uniforms, count):
         """Run `count` trajectories of `circuit` (+ noise) and return (ctx, device states buffer)."""
         dp, _ = self._program(circuit)
-        c = runtime.ctx()
+        c = self._ctx()
+        ab, _ = self._amp()
         dim = 2 ** circuit.num_qubits
-        states = c.alloc(count * dim * 16)
-        kw = {}
-        if dp.prog.n_draws:
-            kw.update(uniforms=c.to_device(uniforms), uniforms_stride=dp.prog.n_draws)
+        states = c.alloc(count * dim * ab)
+        kw = self._draw_kwargs(c, dp, count, uniforms) if (uniforms is not None or self._rng_mode == "philox") else {}
         c.run(dp, count, states=states, default_basis=self._basis(circuit), **kw)
         return c, states
 
@@ -167,17 +205,19 @@ class Simulator:
         dp, _ = self._program(circuit)
         d = dp.prog.n_draws
         counts: dict = {}
-        chunk = max(1, min(shots, _CHUNK_BYTES // (16 * dim)))
-        c = runtime.ctx()
+        ab, _ = self._amp()
+        chunk = max(1, min(shots, _CHUNK_BYTES // (ab * dim)))
+        c = self._ctx()
+        philox = self._rng_mode == "philox"
         # Draws are generated straight into pinned staging memory in slices of _PIPE_SHOTS trajectories and
         # uploaded without a host wait, so the generator works on slice k+1 while the GPU runs slice k.  The
         # noise generator still hands out d doubles per shot in shot order, never reseeded (noise.py:253-259).
         # Slice sizes grow 8x (draws are ~20x cheaper than trajectories), so few launches pay a ragged last wave.
         sub = max(1, min(chunk, _PIPE_SHOTS[1]))
-        stage = [c.staging(("run_with_noise", k), (sub, max(d, 1))) for k in range(2)]
-        dev_u = [c.alloc(sub * max(d, 1) * 8) for _ in range(2)]
+        stage = [c.staging(("run_with_noise", k), (sub, max(d, 1))) for k in range(2)] if not philox else None
+        dev_u = [c.alloc(sub * max(d, 1) * 8) for _ in range(2)] if not philox else None
         done = [None, None]
-        states = c.alloc(chunk * dim * 16)
+        states = c.alloc(chunk * dim * ab)
         basis = self._basis(circuit)
         for lo in range(0, shots, chunk):
             cnt = min(chunk, shots - lo)
@@ -185,7 +225,10 @@ class Simulator:
             while s0 < cnt:
                 k, m = j & 1, min(m, cnt - s0)
                 kw = {}
-                if d:
+                if d and philox:
+                    kw.update(seed=self._philox_seed, traj_offset=self._philox_next)
+                    self._philox_next += m
+                elif d:
                     if done[k] is not None:
                         done[k].wait()                       # slice j-2 has left this staging buffer
                     self._noise_model._rng.random(out=stage[k][:m].reshape(-1))
@@ -208,7 +251,7 @@ class Simulator:
         """Device leg of a shard of shots: trajectories for the rows of `uniforms`, one sampled basis index each."""
         cnt = len(measure_u)
         n = circuit.num_qubits
-        c = runtime.ctx()
+        c = self._ctx()
         _, states = self._trajectory_batch(circuit, uniforms, cnt)
         out = c.alloc(max(cnt, 1) * 8)
         c.sample_index(n, states, 0, cnt, c.to_device(np.ascontiguousarray(measure_u)), out)
@@ -256,7 +299,7 @@ class Simulator:
         dim = 2 ** n
         dp, _ = self._program(circuit)
         d = dp.prog.n_draws
-        c = runtime.ctx()
+        c = self._ctx()
         seeds = [int(rng.integers(0, 2 ** 63)) for _ in range(n_trials)]
         t_rho = torch.zeros(2 * dim * dim, dtype=torch.float64, device=torch.device("cuda", c.device))
         torch.cuda.current_stream(t_rho.device).synchronize()
@@ -288,20 +331,20 @@ class Simulator:
         dim = 2 ** n
         dp, _ = self._program(circuit)
         d = dp.prog.n_draws
-        c = runtime.ctx()
+        c = self._ctx()
         rho = c.alloc(16 * dim * dim).zero()
         seeds = [int(rng.integers(0, 2 ** 63)) for _ in range(n_trials)]     # drawn even without noise
-        chunk = max(1, min(n_trials, _CHUNK_BYTES // (16 * dim)))
+        chunk = max(1, min(n_trials, _CHUNK_BYTES // (self._amp()[0] * dim)))
         for lo in range(0, n_trials, chunk):
             cnt = min(chunk, n_trials - lo)
             uniforms = None
-            if d:
+            if d and self._rng_mode == "reference":
                 uniforms = np.empty((cnt, d), dtype=np.float64)
                 for i in range(cnt):
                     uniforms[i] = np.random.default_rng(seeds[lo + i]).random(d)
             _, states = self._trajectory_batch(circuit, uniforms, cnt)
             c.rho_accumulate(n, states, 0, cnt, 1.0 / n_trials, rho)
-        if self._noise_model is not None and n_trials > 0:
+        if self._noise_model is not None and n_trials > 0 and self._rng_mode == "reference":
             self._noise_model.set_seed(seeds[-1])      # the reference leaves the model seeded with the last child seed
             if d:
                 self._noise_model._rng.random(d)

@@ -69,7 +69,7 @@ def test_random_programs_in_complex64_on_the_gpu(case):
     """complex64 mode (tolerance 1e-5; a Kraus branch may differ from the complex128 oracle only when a uniform lands
     within float rounding of a threshold -- such a trajectory is skipped, not compared)."""
     from gpu_util import gpu_run
-    _check(case, lambda *a, **k: gpu_run(*a, precision="c64", **k), tol=2e-5, strict_branches=False)
+    _check(case, lambda *a, **k: gpu_run(*a, precision="c64", **k), tol=1e-5, strict_branches=False)
 
 
 def _check(case, gpu_run, tol=1e-12, strict_branches=True):

@@ -217,3 +217,74 @@ def test_reference_validation_suite_shapes(E):
         assert abs(np.sum(np.abs(d) ** 2) - 1.0) < 1e-8
         if gamma == 1.0:
             assert abs(abs(d[0]) - 1.0) < 1e-8
+
+
+def _noisy_circuit(n=10, depth=6):
+    from qsb.workloads import layered_circuit
+    from quantum_sim.engine.circuit import QuantumCircuit, GateInstance
+    from quantum_sim.engine.noise import NoiseModel, DepolarizingNoise, AmplitudeDampingNoise
+    qc = QuantumCircuit(n)
+    for name, targets, params, col in layered_circuit(n, depth, 31):
+        qc.add_gate(GateInstance(name, list(targets), list(params), col))
+    nm = NoiseModel()
+    nm.add_global_noise(DepolarizingNoise(0.02))
+    nm.add_global_noise(AmplitudeDampingNoise(0.05))
+    return qc, nm
+
+
+def test_simulator_complex64_precision_through_the_engine_api():
+    """Simulator(..., precision="c64") (SURVEY section 5's precision switch): complex64 states on the device, results
+    as complex128 arrays, within BASELINE's 1e-5 of the complex128 run on the same draws."""
+    from quantum_sim.engine.simulator import Simulator
+    qc, nm = _noisy_circuit()
+    nm.set_seed(5)
+    a = Simulator(nm).run(qc, shots=0, record_steps=True)
+    nm.set_seed(5)
+    b = Simulator(nm, precision="c64").run(qc, shots=0, record_steps=True)
+    assert b.final_state.data.dtype == np.complex128
+    assert np.max(np.abs(a.final_state.data - b.final_state.data)) < 1e-5
+    assert np.max(np.abs(a.final_state.data - b.final_state.data)) > 0          # it really ran in another precision
+    for x, y in zip(a.step_states, b.step_states):
+        assert np.max(np.abs(x.data - y.data)) < 1e-5
+    nm.set_seed(6)
+    ca = Simulator(nm).run_with_noise(qc, shots=300, seed=9).measurement_counts
+    nm.set_seed(6)
+    cb = Simulator(nm, precision="c64").run_with_noise(qc, shots=300, seed=9).measurement_counts
+    assert sum(cb.values()) == 300
+    same = sum(min(ca.get(k, 0), cb.get(k, 0)) for k in set(ca) | set(cb))
+    assert same >= 297                                   # a shot may flip only when a uniform sits within float rounding of a threshold
+    ra = Simulator(nm).ensemble_density_matrix(qc, 40, seed=3)
+    rb = Simulator(nm, precision="c64").ensemble_density_matrix(qc, 40, seed=3)
+    assert np.max(np.abs(ra - rb)) < 1e-5 and abs(np.trace(rb).real - 1.0) < 1e-5
+    with pytest.raises(ValueError):
+        Simulator(nm, precision="fp16")
+
+
+def test_simulator_philox_mode_through_the_engine_api():
+    """Simulator(..., rng_mode="philox"): the in-kernel counter-based stream.  Trajectory t, draw d uses
+    philox_uniform(seed, t, d) -- feeding exactly those numbers through the reference-draw path gives bit-identical
+    states, trajectories are numbered consecutively over calls, and a different seed gives other trajectories."""
+    from qsb.stream import philox_uniform
+    from quantum_sim.engine.simulator import Simulator
+    qc, nm = _noisy_circuit(8, 5)
+    seed, count = 1234567, 12
+    ph = Simulator(nm, rng_mode="philox", philox_seed=seed)
+    ref = Simulator(nm)
+    d = ref._program(qc)[0].prog.n_draws
+    n = qc.num_qubits
+    U = np.array([[philox_uniform(seed, t, k) for k in range(d)] for t in range(2 * count)])
+    for call in range(2):                                 # the second call continues at trajectory `count`
+        _, sp = ph._trajectory_batch(qc, None, count)
+        _, sr = ref._trajectory_batch(qc, U[call * count:(call + 1) * count], count)
+        assert np.array_equal(sp.download(np.complex128, (count, 2 ** n)), sr.download(np.complex128, (count, 2 ** n)))
+    other = Simulator(nm, rng_mode="philox", philox_seed=seed + 1)
+    _, so = other._trajectory_batch(qc, None, count)
+    _, s0 = Simulator(nm, rng_mode="philox", philox_seed=seed)._trajectory_batch(qc, None, count)
+    assert not np.array_equal(so.download(np.complex128, (count, 2 ** n)), s0.download(np.complex128, (count, 2 ** n)))
+    # the public entry points run in this mode without touching the noise model's generator
+    state = nm._rng.bit_generator.state
+    res = Simulator(nm, rng_mode="philox", philox_seed=7).run_with_noise(qc, shots=500, seed=1)
+    assert sum(res.measurement_counts.values()) == 500
+    rho = Simulator(nm, rng_mode="philox", philox_seed=7).ensemble_density_matrix(qc, 64, seed=1)
+    assert abs(np.trace(rho).real - 1.0) < 1e-12 and np.max(np.abs(rho - rho.conj().T)) < 1e-15
+    assert nm._rng.bit_generator.state == state

@@ -87,3 +87,43 @@ def test_noisy_16q_trajectories_unit_norm_and_branch_parity():
     got = states.download(np.complex128, (T, 2 ** n))[0]
     assert br.download(np.int32, (T, prog.n_draws))[0].tolist() == branches
     assert np.max(np.abs(got - psi)) < 1e-12
+
+
+def test_config3_per_layer_mutual_information_matches_reference():
+    """BASELINE config 3: per-trajectory, per-layer mutual information of all 66 pairs on the 12-qubit noisy
+    circuit -- trajectories with per-column snapshots, the single-read DMMA RDM kernel and device entropies -- against
+    the REAL reference's StateAnalysis.mutual_information (tests/golden/make_golden_cfg3_mi.py: 2 noise seeds x 2
+    layers x 66 pairs)."""
+    import json
+    import os
+    from qsb import capi
+    from qsb.workloads import layered_circuit
+    from quantum_sim.engine.analysis import all_pairs_mutual_information_device, StateAnalysis
+    from quantum_sim.engine.circuit import QuantumCircuit, GateInstance
+    from quantum_sim.engine.noise import NoiseModel, DepolarizingNoise, AmplitudeDampingNoise
+    from quantum_sim.engine.simulator import Simulator
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_cfg3_mi.json")) as f:
+        gold = json.load(f)
+    n = gold["n"]
+    qc = QuantumCircuit(n)
+    for name, targets, params, col in layered_circuit(n, gold["depth"], gold["circuit_seed"]):
+        qc.add_gate(GateInstance(name, list(targets), list(params), col))
+    ctx = capi.get_context()
+    for s in gold["noise_seeds"]:
+        nm = NoiseModel()
+        nm.add_global_noise(DepolarizingNoise(0.01))
+        nm.add_global_noise(AmplitudeDampingNoise(0.02))
+        nm.set_seed(s)
+        res = Simulator(nm).run(qc, shots=0, record_steps=True, seed=s)
+        states = np.stack([st.data for st in res.step_states])
+        mi = all_pairs_mutual_information_device(n, ctx.to_device(states), 0, len(states))
+        for layer in gold["layers"]:
+            want = np.array(gold["mi"][f"{s}:{layer}"])
+            assert np.max(np.abs(mi[layer] - want)) < 1e-9, (s, layer)
+            # and through the per-pair API of the reference
+            k = 0
+            for i in range(n):
+                for j in range(i + 1, n):
+                    if k % 13 == 0:
+                        assert abs(StateAnalysis.mutual_information(res.step_states[layer], i, j) - want[k]) < 1e-9
+                    k += 1
