@@ -434,6 +434,7 @@ def run_ours(args):
     extras = None
     if rank == 0 and world == 1 and not args.no_extras:
         extras = measure_other_paths(ctx, sim, qc)
+    qec = None if args.no_extras else measure_qec_sweep(rank, world, torch, dist)
     # last: the 16 GiB state goes through torch's allocator, and the pool-backed legs above were measured 10x slower
     # (block re-mapping) when they ran after its release
     big = None if args.no_extras else measure_sharded_state(rank, world, torch, dist, args.big_qubits)
@@ -477,6 +478,8 @@ def run_ours(args):
             "gpu_launches": launches, "clocks": clocks,
             "gate_apps": gate_apps,
         }
+        if qec is not None:
+            line["config4_qec_sweep"] = qec
         if big is not None:
             line["config5_sharded_state"] = big
         if extras is not None:
@@ -521,6 +524,34 @@ def measure_gate_apps(ctx, qc16, rank, world, torch, dist, sets=4096):
                          "frac": alg / (ms * 1e-3) / 1e9 / world / peak,
                          "note": "algorithmic bytes (2 x 1 MiB per gate-app) against the measured HBM copy rate; states are "
                                  "cluster-resident, real DRAM traffic is the 1 MiB final store per parameter set"}}
+
+
+def measure_qec_sweep(rank, world, torch, dist, per_gpu=16384):
+    """BASELINE config 4 in its throughput mode: the 15-point Steane threshold sweep of scripts/qec_threshold.py with
+    counter-based (Philox) error draws, `per_gpu` trials per point per GPU, trials sharded over all ranks, ONE
+    all-reduce of the per-point sums at the end.  Wall clock (host draws and per-trial program generation included)."""
+    try:
+        from quantum_sim.engine.qec import QECSimulator, SteaneCode
+        qs = QECSimulator(SteaneCode())
+        probs = np.linspace(0.001, 0.3, 15).tolist()
+        qs.threshold_sweep_philox(probs[:2], n_trials=world * per_gpu, noise_type="depolarizing", seed=1, batch=per_gpu)   # warm-up
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        pts = qs.threshold_sweep_philox(probs, n_trials=world * per_gpu, noise_type="depolarizing", seed=42, batch=per_gpu)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dt = float(dt.item())
+        cycles = 15 * world * per_gpu
+        return {"code": "Steane [[7,1,3]]", "points": 15, "trials_per_point": world * per_gpu, "n_gpus": world, "seconds": dt,
+                "cycles_per_s": cycles / dt, "logical_rate_first_last": [pts[0].logical_rate, pts[-1].logical_rate],
+                "api": "QECSimulator.threshold_sweep_philox", "includes": "host Philox draws, per-trial Pauli programs, "
+                "syndrome / fidelity reductions, one all-reduce of the sums"}
+    except Exception as e:
+        return {"error": repr(e)}
 
 
 def measure_sharded_state(rank, world, torch, dist, n):

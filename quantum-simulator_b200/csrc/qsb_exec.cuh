@@ -377,13 +377,15 @@ QSB_PASS void qsb_sweep(Env& env, int m, const qsb_desc* d) {
   for (int k = 0; k < K; ++k) sb[k] = bits[k];
   qsb_sort_bits<K>(sb);
 #endif
+  // off[r] = SWIZZLED slot offset of local index r: the swizzle is linear over XOR and a group's base has none of
+  // the target bits, so slot(base | o) = slot(base) ^ slot(o) -- one XOR per access instead of a shift / mask / XOR chain
   int off[D];
 #pragma unroll
   for (int r = 0; r < D; ++r) {
     int o = 0;
 #pragma unroll
     for (int k = 0; k < K; ++k) if ((r >> (K - 1 - k)) & 1) o |= 1 << bits[k];
-    off[r] = o;
+    off[r] = QSB_SLOT(o);
   }
   A P[K][4];                        // always a valid matrix (identity where nothing is pending)
 #pragma unroll
@@ -407,9 +409,9 @@ QSB_PASS void qsb_sweep(Env& env, int m, const qsb_desc* d) {
 #pragma unroll
       for (int k = 0; k < K; ++k) bs = qsb_ins0(bs, sb[k]);
 #endif
-      base[j] = bs;
+      base[j] = QSB_SLOT(bs);
 #pragma unroll
-      for (int r = 0; r < D; ++r) a[j][r] = tile[QSB_SLOT(bs | off[r])];
+      for (int r = 0; r < D; ++r) a[j][r] = tile[base[j] ^ off[r]];
     }
 #pragma unroll
     for (int k = 0; k < K; ++k) {
@@ -446,7 +448,7 @@ QSB_PASS void qsb_sweep(Env& env, int m, const qsb_desc* d) {
         }
 #pragma unroll
         for (int j = 0; j < NG; ++j)
-          if (g0 + j * env.W < cnt) tile[QSB_SLOT(base[j] | off[r])] = acc[j];
+          if (g0 + j * env.W < cnt) tile[base[j] ^ off[r]] = acc[j];
       }
       continue;
     }
@@ -464,7 +466,7 @@ QSB_PASS void qsb_sweep(Env& env, int m, const qsb_desc* d) {
       }
       if (g0 + j * env.W < cnt) {
 #pragma unroll
-        for (int r = 0; r < D; ++r) tile[QSB_SLOT(base[j] | off[r])] = x[r];
+        for (int r = 0; r < D; ++r) tile[base[j] ^ off[r]] = x[r];
       }
     }
   }

@@ -55,6 +55,22 @@ def allreduce_sum_(tensor):
     return tensor
 
 
+def allreduce_sum_numpy(array: np.ndarray, device=None) -> np.ndarray:
+    """Sum of a small float64 array over the ranks (ONE collective); the array itself for one rank."""
+    import torch
+    import torch.distributed as dist
+    world, _ = world_info()
+    if world == 1:
+        return array
+    t = torch.from_numpy(np.ascontiguousarray(array, dtype=np.float64).copy())
+    if device is None and dist.get_backend() == "nccl":
+        device = torch.device("cuda", torch.cuda.current_device())
+    if device is not None:
+        t = t.to(device)
+    dist.all_reduce(t)
+    return t.cpu().numpy()
+
+
 def gather_concat(array: np.ndarray, device=None):
     """Concatenate equal-dtype 1-D arrays of all ranks in rank order (lengths may differ by one)."""
     import torch

@@ -569,6 +569,41 @@ class QECSimulator:
             results.append(self._point(p, merged, n_trials))
         return results
 
+    def threshold_sweep_philox(self, noise_probs: list, n_trials: int = 100000, noise_type: str = "depolarizing",
+                               seed: int = 0, batch: int = 16384, _run_cycles=None) -> list:
+        """Throughput mode of the sweep (BASELINE config 4 with 10^5 trials per point): the per-qubit error draws come
+        from a COUNTER-BASED generator -- NumPy's Philox keyed by (seed, point, batch) -- instead of one
+        `default_rng(trial_seed)` per trial (qec.py:585-586), so no host generator is created
+        per trial and any rank can produce exactly its own slice.  The trials of every point are split over the ranks
+        of the default process group; the only collective is ONE all-reduce of the per-point sums at the very end.
+        Same estimators as `threshold_sweep` (qec.py:607-620), statistically equivalent, not stream-compatible."""
+        from qsb import distributed as D
+        world, rank = D.world_info()
+        run = _run_cycles or self.run_cycles
+        nd = self._code.data_qubits
+        sums = np.zeros((len(noise_probs), 4))                      # successes, fidelity, |<Z_L>|, no-logical-error
+        n_batches = (n_trials + batch - 1) // batch
+        for k, p in enumerate(noise_probs):
+            # batch j of point k has its own Philox key: any rank can produce exactly its batches, and the result
+            # does not depend on how many ranks share the work
+            lo, hi = D.shard_bounds(n_batches, world, rank)
+            for j in range(lo, hi):
+                b0, b1 = j * batch, min(n_trials, (j + 1) * batch)
+                gen = np.random.Generator(np.random.Philox(key=[int(seed) & (2 ** 64 - 1), (k << 32) | j]))
+                u = gen.random((b1 - b0, nd))
+                r = run([t % 2 for t in range(b0, b1)], noise_type, p, None, uniforms=u)
+                fa = np.asarray(r["fidelity_after"], dtype=np.float64)
+                sums[k] += (np.count_nonzero(fa > 0.5), fa.sum(), np.abs(np.asarray(r["z_exp"], dtype=np.float64)).sum(),
+                            np.count_nonzero(~np.asarray(r["logical_error"], dtype=bool)))
+        sums = D.allreduce_sum_numpy(sums)
+        out = []
+        for k, p in enumerate(noise_probs):
+            succ, fid, zf, zok = sums[k]
+            out.append(ThresholdPoint(physical_rate=p, logical_rate=1.0 - succ / n_trials, success_rate=succ / n_trials,
+                                      avg_fidelity=fid / n_trials, logical_z_fidelity=zf / n_trials,
+                                      decoder_success_rate=zok / n_trials, projection_logical_rate=1.0 - fid / n_trials))
+        return out
+
     @staticmethod
     def _point(p, r, n_trials):
         # the reference accumulates trial by trial in Python floats; do the same so the sums round identically

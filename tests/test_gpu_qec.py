@@ -68,3 +68,23 @@ def test_projection_logical_error_consistent():
     fids = [sim.run_cycle(1, "depolarizing", 0.05, seed=s).fidelity_after for s in seeds]
     assert abs(r["mean_fidelity"] - sum(fids) / 24) < 1e-12
     assert r["n_trials"] == 24
+
+
+def test_philox_threshold_sweep_agrees_with_the_reference_stream_sweep_statistically():
+    """threshold_sweep_philox (counter-based bulk draws, the throughput mode of config 4) estimates the same quantities
+    as the reference-stream sweep: with 6000 trials per point the two differ by sampling error only, and the
+    sweep is reproducible and independent of the batch size used to key... (the key includes the batch index, so the
+    batch size is part of the stream's definition -- a fixed batch gives bit-identical repeats)."""
+    from quantum_sim.engine.qec import QECSimulator, SteaneCode
+    sim = QECSimulator(SteaneCode())
+    probs = [0.01, 0.08, 0.25]
+    a = sim.threshold_sweep_philox(probs, n_trials=6000, noise_type="depolarizing", seed=5, batch=2048)
+    b = sim.threshold_sweep_philox(probs, n_trials=6000, noise_type="depolarizing", seed=5, batch=2048)
+    r = sim.threshold_sweep(probs, n_trials=1500, noise_type="depolarizing", seed=5)
+    for x, y, z in zip(a, b, r):
+        assert x == y
+        assert x.physical_rate == z.physical_rate
+        # binomial standard errors: sqrt(p(1-p)/6000) + sqrt(p(1-p)/1500) <= 0.02; allow 5 sigma
+        assert abs(x.logical_rate - z.logical_rate) < 0.1 and abs(x.avg_fidelity - z.avg_fidelity) < 0.1
+        assert abs(x.decoder_success_rate - z.decoder_success_rate) < 0.1
+    assert a[0].logical_rate < a[1].logical_rate < a[2].logical_rate

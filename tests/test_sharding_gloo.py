@@ -322,3 +322,46 @@ def test_world2_gloo_batch_costs_sharded():
         assert p.exitcode == 0
     vals = np.random.default_rng(5).uniform(-1, 1, (11, 3))
     assert np.array_equal(got, np.array([float(np.sum(np.cos(r))) for r in vals]))      # every rank holds all costs
+
+
+def _philox_sweep_worker(rank, world, port, out_q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from quantum_sim.engine.qec import QECSimulator, SteaneCode
+    out_q.put((rank, _philox_sweep(world)))
+    dist.destroy_process_group()
+
+
+def _philox_sweep(world):
+    """threshold_sweep_philox with the device stood in for by a cheap deterministic function of the uniforms."""
+    from quantum_sim.engine.qec import QECSimulator, SteaneCode
+
+    def run_cycles(logicals, noise_type, p, seeds, uniforms=None):
+        fired = (uniforms < p).sum(axis=1)
+        return {"fidelity_after": np.where(fired <= 1, 1.0, 0.25), "z_exp": np.where(fired % 2 == 0, 1.0, -0.5),
+                "logical_error": fired >= 2}
+
+    sim = QECSimulator.__new__(QECSimulator)
+    sim._code = SteaneCode.__new__(SteaneCode)
+    pts = sim.threshold_sweep_philox([0.02, 0.2], n_trials=1000, noise_type="depolarizing", seed=9, batch=128,
+                                     _run_cycles=run_cycles)
+    return [(pt.physical_rate, pt.logical_rate, pt.avg_fidelity, pt.logical_z_fidelity, pt.decoder_success_rate) for pt in pts]
+
+
+def test_world2_gloo_philox_threshold_sweep_is_independent_of_the_world_size():
+    """Counter-based draws keyed by (seed, point, batch): two ranks sharing the batches give the single-process sums."""
+    single = _philox_sweep(1)
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_philox_sweep_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get() for _ in range(2))
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    for r in range(2):
+        for a, b in zip(got[r], single):
+            assert a[0] == b[0] and all(abs(x - y) < 1e-12 for x, y in zip(a[1:], b[1:]))
+    assert 0.0 < single[1][1] < 1.0
