@@ -201,17 +201,28 @@ class Simulator:
         if rng is None:
             rng = np.random.default_rng(seed)
         n = circuit.num_qubits
+        idx = self._noisy_indices(circuit, shots, self._noise_model._rng, rng)
+        counts: dict = {}
+        for i in idx.tolist():
+            key = format(i, f"0{n}b")
+            counts[key] = counts.get(key, 0) + 1
+        final_state = StateVector.from_initial_states(circuit.initial_states)   # placeholder, as in the reference
+        return SimulationResult(final_state=final_state, measurement_counts=counts, num_shots=shots, seed=seed)
+
+    def _noisy_indices(self, circuit, shots, noise_rng, meas_rng) -> np.ndarray:
+        """Sampled basis index of `shots` noisy trajectories, in shot order (the device leg of run_with_noise and of a
+        rank's share of run_with_noise_sharded).  `noise_rng` hands out d doubles per shot in shot order, never
+        reseeded (noise.py:253-259); `meas_rng` one double per shot (state_vector.py:107-113)."""
+        n = circuit.num_qubits
         dim = 2 ** n
         dp, _ = self._program(circuit)
         d = dp.prog.n_draws
-        counts: dict = {}
         ab, _ = self._amp()
         chunk = max(1, min(shots, _CHUNK_BYTES // (ab * dim)))
         c = self._ctx()
         philox = self._rng_mode == "philox"
         # Draws are generated straight into pinned staging memory in slices of _PIPE_SHOTS trajectories and
-        # uploaded without a host wait, so the generator works on slice k+1 while the GPU runs slice k.  The
-        # noise generator still hands out d doubles per shot in shot order, never reseeded (noise.py:253-259).
+        # uploaded without a host wait, so the generator works on slice k+1 while the GPU runs slice k.
         # Slice sizes grow 8x (draws are ~20x cheaper than trajectories), so few launches pay a ragged last wave.
         sub = max(1, min(chunk, _PIPE_SHOTS[1]))
         stage = [c.staging(("run_with_noise", k), (sub, max(d, 1))) for k in range(2)] if not philox else None
@@ -219,6 +230,7 @@ class Simulator:
         done = [None, None]
         states = c.alloc(chunk * dim * ab)
         basis = self._basis(circuit)
+        out_idx = np.empty(shots, dtype=np.int64)
         for lo in range(0, shots, chunk):
             cnt = min(chunk, shots - lo)
             s0, m, j = 0, min(_PIPE_SHOTS[0], sub), 0
@@ -231,32 +243,19 @@ class Simulator:
                 elif d:
                     if done[k] is not None:
                         done[k].wait()                       # slice j-2 has left this staging buffer
-                    self._noise_model._rng.random(out=stage[k][:m].reshape(-1))
+                    noise_rng.random(out=stage[k][:m].reshape(-1))
                     dev_u[k].upload_async(stage[k][:m])
                     done[k] = (done[k] or c.event()).record()
                     kw.update(uniforms=dev_u[k], uniforms_stride=d)
                 c.run(dp, m, states=states, first=s0, default_basis=basis, async_=True, **kw)
                 s0, m, j = s0 + m, min(8 * m, sub), j + 1
-            u = c.to_device(rng.random(cnt))
+            u = c.to_device(meas_rng.random(cnt))
             out = c.alloc(cnt * 8)
             c.sample_index(n, states, 0, cnt, u, out)
-            for i in out.download(np.int64, (cnt,)).tolist():
-                key = format(i, f"0{n}b")
-                counts[key] = counts.get(key, 0) + 1
-        final_state = StateVector.from_initial_states(circuit.initial_states)   # placeholder, as in the reference
-        return SimulationResult(final_state=final_state, measurement_counts=counts, num_shots=shots, seed=seed)
+            out.download(np.int64, (cnt,), out=out_idx[lo:lo + cnt])
+        return out_idx
 
     # ---- sharded over the ranks of the default process group (one process per GPU, torchrun) ---------------------
-    def _shot_indices(self, circuit, uniforms, measure_u):
-        """Device leg of a shard of shots: trajectories for the rows of `uniforms`, one sampled basis index each."""
-        cnt = len(measure_u)
-        n = circuit.num_qubits
-        c = self._ctx()
-        _, states = self._trajectory_batch(circuit, uniforms, cnt)
-        out = c.alloc(max(cnt, 1) * 8)
-        c.sample_index(n, states, 0, cnt, c.to_device(np.ascontiguousarray(measure_u)), out)
-        return out.download(np.int64, (cnt,))
-
     def run_with_noise_sharded(self, circuit: QuantumCircuit, shots: int = 1024, seed: int | None = None,
                                rng: np.random.Generator | None = None, _indices_fn=None) -> SimulationResult:
         """`run_with_noise` with the shots split over the ranks.  Both generators are POSITIONED, not replayed: rank r
@@ -274,10 +273,12 @@ class Simulator:
         noise_rng = D.positioned_rng(self._noise_model._rng, lo * d)
         meas_rng = D.positioned_rng(rng if rng is not None else seed, lo)
         cnt = hi - lo
-        uniforms = noise_rng.random(cnt * d).reshape(cnt, d) if d else None
-        measure_u = meas_rng.random(cnt)
-        fn = _indices_fn or self._shot_indices
-        idx = np.asarray(fn(circuit, uniforms, measure_u), dtype=np.int64) if cnt else np.zeros(0, dtype=np.int64)
+        if _indices_fn is None:                    # same pipelined device leg as run_with_noise, on this rank's slice
+            idx = self._noisy_indices(circuit, cnt, noise_rng, meas_rng) if cnt else np.zeros(0, dtype=np.int64)
+        else:
+            uniforms = noise_rng.random(cnt * d).reshape(cnt, d) if d else None
+            measure_u = meas_rng.random(cnt)
+            idx = np.asarray(_indices_fn(circuit, uniforms, measure_u), dtype=np.int64) if cnt else np.zeros(0, dtype=np.int64)
         all_idx = D.gather_concat(idx)
         # leave both generators where the single loop would have left them
         if d:
