@@ -316,6 +316,14 @@ int qsb_stream_run(qsb_stream* pass, qsb_buffer* in, int64_t in_offset, qsb_buff
                    int32_t flags);
 int qsb_stream_run_peers(qsb_stream* pass, const void* const* peers, int32_t n_peers, int32_t peer_shift,
                          int64_t peer_rank_or, qsb_buffer* out, int64_t out_offset, int32_t flags);
+/* The exchange folded into the STORE of a pass (the compute + collective kernel of config 5): tiles are loaded from
+ * `in`, swept, and every TMA box is stored straight into the shard of the peer its destination index names -- element x
+ * of the pass's output goes to peers[x >> peer_shift] at offset (x & (2^peer_shift - 1)) | peer_rank_or -- posted
+ * writes over NVLink that overlap the sweeps of the following tiles.  With positions_out != positions the same pass
+ * also does the position reorder that brings the leaving qubits to the top.  peers = host array of the 2^(n -
+ * peer_shift) ranks' destination shard pointers (mine included); none may be the shard being read. */
+int qsb_stream_run_scatter(qsb_stream* pass, qsb_buffer* in, int64_t in_offset, const void* const* peers, int32_t n_peers,
+                           int32_t peer_shift, int64_t peer_rank_or, int32_t flags);
 int qsb_stream_free(qsb_stream* pass);
 
 #ifdef __cplusplus

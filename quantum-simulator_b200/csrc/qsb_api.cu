@@ -1306,9 +1306,44 @@ int qsb_stream_run(qsb_stream* s, qsb_buffer* in, int64_t in_offset, qsb_buffer*
   qsb_stream_maps maps;
   memset(&maps, 0, sizeof maps);
   if ((rc = stream_map(ctx, &maps.in[0], (char*)in->ptr + in_offset * 16, s, s->ebit))) return rc;
-  if ((rc = stream_map(ctx, &maps.out, (char*)out->ptr + out_offset * 16, s, s->ebit_out))) return rc;
+  if ((rc = stream_map(ctx, &maps.out[0], (char*)out->ptr + out_offset * 16, s, s->ebit_out))) return rc;
   s->ka.peer_shift = 32;
   s->ka.peer_or = 0;
+  s->ka.out_shift = 32;
+  s->ka.out_or = 0;
+  return stream_launch(s, maps, flags);
+}
+
+int qsb_stream_run_scatter(qsb_stream* s, qsb_buffer* in, int64_t in_offset, const void* const* peers, int32_t n_peers,
+                           int32_t peer_shift, int64_t peer_rank_or, int32_t flags) {
+  if (!s || !in || !peers) return fail(nullptr, QSB_E_INVAL, "qsb_stream_run_scatter: NULL argument");
+  qsb_ctx* ctx = s->ctx;
+  const int n = s->ka.n;
+  const int64_t dim = (int64_t)1 << n;
+  int rc;
+  if (n_peers < 2 || n_peers > QSB_ST_MAX_PEERS || peer_shift < s->ka.l || peer_shift >= n || (1 << (n - peer_shift)) != n_peers)
+    return fail(ctx, QSB_E_INVAL, "qsb_stream_run_scatter: %d peers do not match peer_shift %d of %d bits", n_peers, peer_shift, n);
+  if (peer_rank_or < 0 || peer_rank_or >= dim || (peer_rank_or & (((int64_t)1 << peer_shift) - 1)))
+    return fail(ctx, QSB_E_INVAL, "qsb_stream_run_scatter: bad peer_rank_or");
+  for (int j = 0; j < s->ka.e; ++j)
+    if (s->ebit_out[j] >= peer_shift)
+      return fail(ctx, QSB_E_UNSUPPORTED, "qsb_stream_run_scatter: a TMA box dimension of the store lies on a peer-selecting bit");
+  if (in_offset < 0 || (in_offset & 7)) return fail(ctx, QSB_E_INVAL, "qsb_stream_run_scatter: bad in_offset");
+  if ((rc = need(ctx, in, (in_offset + dim) * 16, "input shard"))) return rc;
+  CU(ctx, cudaSetDevice(ctx->device));
+  qsb_stream_maps maps;
+  memset(&maps, 0, sizeof maps);
+  if ((rc = stream_map(ctx, &maps.in[0], (char*)in->ptr + in_offset * 16, s, s->ebit))) return rc;
+  for (int p = 0; p < n_peers; ++p) {
+    if (!peers[p]) return fail(ctx, QSB_E_INVAL, "qsb_stream_run_scatter: peer %d is NULL", p);
+    if (peers[p] == (const void*)((char*)in->ptr + in_offset * 16))
+      return fail(ctx, QSB_E_INVAL, "qsb_stream_run_scatter: the pass would overwrite the shard it reads");
+    if ((rc = stream_map(ctx, &maps.out[p], const_cast<void*>(peers[p]), s, s->ebit_out))) return rc;
+  }
+  s->ka.peer_shift = 32;
+  s->ka.peer_or = 0;
+  s->ka.out_shift = peer_shift;
+  s->ka.out_or = (uint32_t)peer_rank_or;
   return stream_launch(s, maps, flags);
 }
 
@@ -1335,9 +1370,11 @@ int qsb_stream_run_peers(qsb_stream* s, const void* const* peers, int32_t n_peer
     if (!peers[p]) return fail(ctx, QSB_E_INVAL, "qsb_stream_run_peers: peer %d is NULL", p);
     if ((rc = stream_map(ctx, &maps.in[p], const_cast<void*>(peers[p]), s, s->ebit))) return rc;
   }
-  if ((rc = stream_map(ctx, &maps.out, (char*)out->ptr + out_offset * 16, s, s->ebit_out))) return rc;
+  if ((rc = stream_map(ctx, &maps.out[0], (char*)out->ptr + out_offset * 16, s, s->ebit_out))) return rc;
   s->ka.peer_shift = peer_shift;
   s->ka.peer_or = (uint32_t)peer_rank_or;
+  s->ka.out_shift = 32;
+  s->ka.out_or = 0;
   return stream_launch(s, maps, flags);
 }
 

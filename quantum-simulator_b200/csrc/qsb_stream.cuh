@@ -43,7 +43,7 @@ extern __shared__ __align__(1024) unsigned char qsb_stream_smem[];
 // the pass, else only in[0]) and the shard they are stored to
 struct qsb_stream_maps {
   CUtensorMap in[QSB_ST_MAX_PEERS];
-  CUtensorMap out;
+  CUtensorMap out[QSB_ST_MAX_PEERS];
 };
 
 struct qsb_blk;
@@ -51,6 +51,8 @@ struct qsb_stream_kargs {
   int32_t n, m, l, e;
   int32_t peer_shift, pad0;              // source element x comes from in[x >> peer_shift] (peer_shift = n: one source)
   uint32_t peer_or, pad1;                // ... at offset (x & (2^peer_shift - 1)) | peer_or
+  int32_t out_shift, pad2;               // destination element x goes to out[x >> out_shift] (out_shift = 32: one destination)
+  uint32_t out_or, pad3;                 // ... at offset (x & (2^out_shift - 1)) | out_or
   int32_t n_sweeps, n_ops;               // sweeps per tile; TMA ops per tile = 2^(m - l - e)
   int32_t op_pos[16];                    // slot l+e+j -> bit position in the (local) amplitude index, load side
   int32_t tile_pos[32];                  // slot m+j   -> bit position, load side
@@ -292,9 +294,15 @@ qsb_stream_kernel(const __grid_constant__ qsb_stream_maps maps, const __grid_con
       qsb_st_mbar_wait(qsb_st_smem_u32(&bars[QSB_ST_BUFS + b]), (uint32_t)((j / QSB_ST_BUFS) & 1));   // tile j is swept
       // scatter buffer b to the (store-side) positions of tile j: one bulk group per lane
       const uint32_t tb = tile_base(j, a.tile_pos_out);
-      for (int r = lane; r < a.n_ops; r += 32)
-        qsb_st_tma_store(&maps.out, (int)((tb | row_off[32 + r]) >> 3),
+      const uint32_t omask = a.out_shift >= 32 ? 0xffffffffu : ((1u << a.out_shift) - 1u);
+      for (int r = lane; r < a.n_ops; r += 32) {
+        // with out_shift < 32 the store IS the qubit exchange: the top index bits of the destination pick the peer
+        // whose shard receives the box (a posted write over NVLink), my rank fills the bits it vacates
+        const uint32_t x = tb | row_off[32 + r];
+        const uint32_t dst = a.out_shift >= 32 ? 0u : (x >> a.out_shift);
+        qsb_st_tma_store(&maps.out[dst], (int)(((x & omask) | a.out_or) >> 3),
                          qsb_st_smem_u32(base + (size_t)b * tile_bytes + (size_t)r * op_bytes));
+      }
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       if (j + QSB_ST_BUFS < mine) {
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");    // the store has read the buffer: refill it

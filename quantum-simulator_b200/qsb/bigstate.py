@@ -150,7 +150,7 @@ class BigState:
     """One n-qubit complex128 state on this rank's GPU (a 2^(n-g) shard when the process group has 2^g ranks)."""
 
     def __init__(self, n, *, group=None, device=None, layout="reference", local_bits=None, distributed=True,
-                 fuse_exchange=True, engine="tma"):
+                 fuse_exchange=True, engine="tma", fuse_where="store"):
         """engine: "tma" = the TMA tile pipeline with host-fused sweeps (csrc/qsb_stream.cuh, qsb/stream.py);
         "executor" = round 1's path, one tile per CTA of the resident executor in its streaming mode (kept for A/B
         and as a second implementation the tests compare against).
@@ -176,6 +176,13 @@ class BigState:
         if engine not in ("tma", "executor"):
             raise ValueError("engine must be 'tma' or 'executor'")
         self.engine = engine
+        # where a fused exchange happens (engine "tma"): "store" = in the store of the pass BEFORE it (peer-mapped TMA
+        # stores; the reorder rides along, so an exchange costs no pass of its own), "load" = in the load of the pass
+        # AFTER it (peer-mapped TMA loads behind a separate reorder pass)
+        if fuse_where not in ("store", "load"):
+            raise ValueError("fuse_where must be 'store' or 'load'")
+        self.fuse_where = fuse_where
+        self.fuse_store = fuse_exchange and fuse_where == "store"
         self.fused_exchanges = 0
         dev = capi.default_device() if device is None else device
         self.ctx = capi.get_context(dev)
@@ -250,7 +257,7 @@ class BigState:
         rel = _Relabel(lw, self.pos_of)
         cdata = lw.pool.array()
         steps, moved, _ = stream.plan(rel.items, cdata, self.n, self.g, list(range(self.n)), local_bits=self.local_bits,
-                                      params=params, uniforms=uniforms, seed=seed)
+                                      params=params, uniforms=uniforms, seed=seed, fuse_store=self.fuse_where != "load")
         for st in steps:
             if st.spass is not None:
                 st.handle = self.ctx.stream_pass(st.spass, cdata)
@@ -270,6 +277,24 @@ class BigState:
                     pending_exchange = True          # folded into the LOAD of the next pass
                 else:
                     self._exchange()
+                continue
+            if st.scatter:
+                # the exchange (and the reorder that precedes it) rides in this pass's STORE: every TMA box goes
+                # straight into the shard of the peer it belongs to, posted writes over NVLink under the sweeps of the
+                # following tiles.  Destination = everybody's idle buffer (the fence after the previous exchange made sure
+                # nobody still reads it); one fence afterwards: all boxes have landed before anyone sweeps them.
+                shift = self.L - self.g
+                o = self._other()
+                if self._peer_tables is not None and self.fuse_store:
+                    st.handle.run_scatter(self._wrapped[self.cur], self._peer_ptrs[o], shift, self.rank << shift)
+                    self._rank_fence()
+                    self.cur = o
+                    self.fused_exchanges += 1
+                else:                                # no peer mappings: the same pass out of place, then the all-to-all
+                    st.handle.run(self._wrapped[self.cur], self._wrapped[o])
+                    self.cur = o
+                    self._exchange()
+                self.launches += 1
                 continue
             if pending_exchange:
                 pending_exchange = False

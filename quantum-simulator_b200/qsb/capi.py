@@ -30,7 +30,7 @@ SYMBOLS = [
     "qsb_debug_profile",
     "qsb_probabilities", "qsb_probabilities_sum", "qsb_sample_index", "qsb_overlap",
     "qsb_masked_parity", "qsb_rdm_all", "qsb_rdm_general", "qsb_mi_all_pairs", "qsb_rho_accumulate", "qsb_readout_transform",
-    "qsb_stream_create", "qsb_stream_run", "qsb_stream_run_peers", "qsb_stream_free",
+    "qsb_stream_create", "qsb_stream_run", "qsb_stream_run_peers", "qsb_stream_run_scatter", "qsb_stream_free",
 ]
 
 
@@ -114,6 +114,7 @@ def load_library():
             "qsb_stream_create": (C.c_int, [vp, i32, i32, i32, i32, P(i32), P(i32), vp, i32, vp, i64, P(vp)]),
             "qsb_stream_run": (C.c_int, [vp, vp, i64, vp, i64, i32]),
             "qsb_stream_run_peers": (C.c_int, [vp, P(vp), i32, i32, i64, vp, i64, i32]),
+            "qsb_stream_run_scatter": (C.c_int, [vp, vp, i64, P(vp), i32, i32, i64, i32]),
             "qsb_stream_free": (C.c_int, [vp]),
         }
         for name, (res, args) in proto.items():
@@ -287,6 +288,13 @@ class DevicePass:
         arr = (C.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
         _check(self.ctx.lib.qsb_stream_run_peers(self.handle, arr, len(peer_ptrs), int(peer_shift), int(peer_rank_or),
                                                  dst.handle, dst_offset, RUN_ASYNC if async_ else 0), self.ctx.handle)
+
+    def run_scatter(self, src, peer_ptrs, peer_shift, peer_rank_or, *, src_offset=0, async_=True):
+        """Store every box into the shard of the peer its destination index names: the qubit exchange folded into the
+        store of this pass (peer_ptrs = the ranks' destination shard pointers, rank order)."""
+        arr = (C.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+        _check(self.ctx.lib.qsb_stream_run_scatter(self.handle, src.handle, src_offset, arr, len(peer_ptrs), int(peer_shift),
+                                                   int(peer_rank_or), RUN_ASYNC if async_ else 0), self.ctx.handle)
 
     def free(self):
         if self.handle is not None:

@@ -7,6 +7,9 @@ with the axis scramble of :66-73 already turned into bookkeeping).  Output: a li
               shared memory, takes the pass's sweeps, and is scattered back
     reorder   a pass without sweeps whose store permutes index positions (brings exchange victims to the top)
     exchange  rank positions <-> top local positions (NCCL all-to-all, or folded into the next pass's peer loads)
+A pass / reorder step with `scatter` set carries the exchange in its own store: its output positions already have the
+leaving qubits on top, and on the device every TMA box is written into the shard of the peer it belongs to
+(qsb_stream_run_scatter) -- the compute pass, the reorder and the all-to-all are ONE kernel.
 
 Gate fusion happens HERE, once per program, because in a streamed pass every tile sees the same ops:
   * a 1-qubit op (gate, Pauli Kraus branch) never costs a sweep: it is multiplied into the PENDING 2x2 of its
@@ -103,6 +106,8 @@ class Step:
     kind: str                     # "pass" | "reorder" | "exchange"
     spass: StreamPass = None
     handle: object = None         # device object, filled in by the runner
+    scatter: bool = False         # the qubit exchange follows this pass and is folded into its STORE (peer-mapped TMA stores)
+    meta: object = None           # planner bookkeeping: (resident positions, chosen ops) of a pass that may be re-closed
 
 
 def classify(P):
@@ -211,11 +216,13 @@ def choose_geometry(L, local_bits=None, low_bits=None, box_bits=None):
 
 
 def plan(items, cdata, n, g, pos_of, *, local_bits=None, low_bits=None, box_bits=None, params=None, uniforms=None,
-         seed=0, traj=0, flush=True):
+         seed=0, traj=0, flush=True, fuse_store=True):
     """Op list (bits = VIRTUAL bits) -> (steps, pos_of, pending).
 
     n = all index bits, g = rank positions n-g..n-1 (0: one device), pos_of[v] = position of virtual bit v now.
-    Positions 0..L-1 (L = n - g) address the local shard.  `flush` applies whatever is pending at the end."""
+    Positions 0..L-1 (L = n - g) address the local shard.  `flush` applies whatever is pending at the end.
+    fuse_store: fold every exchange (and the reorder that precedes it) into the store of the pass before it
+    (`Step.scatter`); otherwise emit separate "reorder" and "exchange" steps."""
     L = n - g
     m, l, e = choose_geometry(L, local_bits, low_bits, box_bits)
     if g > 0 and L - l < 2 * g:
@@ -228,10 +235,14 @@ def plan(items, cdata, n, g, pos_of, *, local_bits=None, low_bits=None, box_bits
         pending = {}
     steps = []
 
-    def close_pass(resident, chosen):
-        resident = sorted(resident)
+    def close_pass(resident, chosen, store_map=None, victims=()):
+        """Emit one pass.  store_map (position -> position) makes the store permute positions; `victims` are resident
+        positions that must not ride in the TMA box (they become peer-selecting bits on the store side)."""
+        low = list(range(l))
+        rest = sorted(p for p in resident if p >= l and p not in victims)
+        resident_order = low + rest + sorted(p for p in resident if p in victims)
         others = [p for p in range(L) if p not in resident]
-        positions = resident + others
+        positions = resident_order + others
         slot = {p: j for j, p in enumerate(positions)}
         sweeps, flushes = [], []
         for gate, bits, Ps, mat in chosen:
@@ -243,7 +254,9 @@ def plan(items, cdata, n, g, pos_of, *, local_bits=None, low_bits=None, box_bits
         for i in range(0, len(flushes), 3):
             grp = flushes[i:i + 3]
             sweeps.append(Sweep(G_NONE, [b for b, _ in grp], [P for _, P in grp]))
-        steps.append(Step("pass", StreamPass(L, m, l, e, positions, list(positions), sweeps)))
+        out = list(positions) if store_map is None else [store_map[p] for p in positions]
+        return Step("pass" if chosen else "reorder", StreamPass(L, m, l, e, positions, out, sweeps),
+                    scatter=store_map is not None and fuse_store, meta=(set(resident), list(chosen)))
 
     while todo:
         resident = set(range(l))
@@ -273,7 +286,7 @@ def plan(items, cdata, n, g, pos_of, *, local_bits=None, low_bits=None, box_bits
                 if len(resident) >= m:
                     break
                 resident.add(p)
-            close_pass(resident, chosen)
+            steps.append(close_pass(resident, chosen))
             todo = rest
             continue
         if g == 0:
@@ -288,19 +301,29 @@ def plan(items, cdata, n, g, pos_of, *, local_bits=None, low_bits=None, box_bits
         movable = [v for v in range(n) if l <= pos_of[v] < L]
         victims = sorted(movable, key=lambda v: (-next_use.get(v, 1 << 60), -pos_of[v]))[:g]
         vic_pos = sorted(pos_of[v] for v in victims)
-        if vic_pos != list(range(L - g, L)):
-            keep = [p for p in range(l, L) if p not in vic_pos]
-            new_of_old = {p: p for p in range(l)}
-            for j, p in enumerate(keep):
-                new_of_old[p] = l + j
-            for j, p in enumerate(vic_pos):
-                new_of_old[p] = L - g + j
-            positions = list(range(L))               # slot j = position j on the load side
-            steps.append(Step("reorder", StreamPass(L, m, l, e, positions, [new_of_old[p] for p in positions], [])))
-            for v in range(n):
-                if pos_of[v] < L:
-                    pos_of[v] = new_of_old[pos_of[v]]
-        steps.append(Step("exchange"))
+        keep = [p for p in range(l, L) if p not in vic_pos]
+        new_of_old = {p: p for p in range(l)}
+        for j, p in enumerate(keep):
+            new_of_old[p] = l + j
+        for j, p in enumerate(vic_pos):
+            new_of_old[p] = L - g + j
+        identity = vic_pos == list(range(L - g, L))
+        if fuse_store and steps and steps[-1].kind == "pass" and not steps[-1].scatter:
+            # the pass just before the exchange does the reorder AND the exchange in its store
+            resident, chosen = steps.pop().meta
+            steps.append(close_pass(resident, chosen, store_map=new_of_old, victims=vic_pos))
+        elif fuse_store:
+            # nothing to ride on: a pass without sweeps (its tile = the low positions, victims excluded from the box)
+            resident = set(range(l)) | set(keep[:m - l])
+            steps.append(close_pass(resident, [], store_map=new_of_old, victims=vic_pos))
+        else:
+            if not identity:
+                positions = list(range(L))           # slot j = position j on the load side
+                steps.append(Step("reorder", StreamPass(L, m, l, e, positions, [new_of_old[p] for p in positions], [])))
+            steps.append(Step("exchange"))
+        for v in range(n):
+            if pos_of[v] < L:
+                pos_of[v] = new_of_old[pos_of[v]]
         for v in range(n):
             p = pos_of[v]
             if p >= L:

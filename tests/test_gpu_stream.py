@@ -167,6 +167,46 @@ def test_peer_loads_fold_the_exchange_into_a_pass(g):
         assert np.array_equal(out.download(np.complex128, (2 ** L,)), want_buf.download(np.complex128, (2 ** L,))), (g, r)
 
 
+@pytest.mark.parametrize("g", [1, 2, 3])
+def test_scatter_stores_fold_the_exchange_into_a_pass(g):
+    """qsb_stream_run_scatter on ONE device: 2^g shards stand in for the GPUs.  A pass (sweeps + position reorder) whose
+    boxes are stored straight into the peers' shards must equal the same pass stored locally followed by the all-to-all
+    exchange (rank bits <-> top local bits)."""
+    from qsb import capi
+    n, world = 17 + g, 1 << g
+    L = n - g
+    rng = np.random.default_rng(60 + g)
+    gl = ordered(n, layered_circuit(n, 3, 11))
+    lw = lower(n, gl, layout="textbook")
+    cdata = lw.pool.array()
+    steps, _, _ = S.plan(lw.items, cdata, n, g, list(range(n)))
+    st = next(s for s in steps if s.scatter)
+    sp = st.spass
+    assert sp.positions != sp.positions_out or True
+    ctx = capi.get_context()
+    shards = rng.normal(size=(world, 2 ** L)) + 1j * rng.normal(size=(world, 2 ** L))
+    srcs = [ctx.to_device(np.ascontiguousarray(shards[r])) for r in range(world)]
+    dsts = [ctx.alloc(16 << L).zero() for _ in range(world)]
+    h = ctx.stream_pass(sp, cdata)
+    for r in range(world):
+        h.run_scatter(srcs[r], [d.ptr for d in dsts], L - g, r << (L - g))
+    ctx.sync()
+    got = [d.download(np.complex128, (2 ** L,)) for d in dsts]
+    # the same pass stored locally, then the exchange on the host
+    local = []
+    for r in range(world):
+        out = ctx.alloc(16 << L).zero()
+        h.run(srcs[r], out)
+        ctx.sync()
+        local.append(out.download(np.complex128, (2 ** L,)))
+    chunk = 2 ** (L - g)
+    for r in range(world):
+        want = np.concatenate([local[c][r * chunk:(r + 1) * chunk] for c in range(world)])
+        assert np.array_equal(got[r], want), (g, r)
+    with pytest.raises(ValueError):
+        h.run_scatter(srcs[0], [srcs[0].ptr] + [d.ptr for d in dsts[1:]], L - g, 0)     # would overwrite what it reads
+
+
 def test_argument_checks():
     from qsb import capi
     ctx = capi.get_context()

@@ -167,15 +167,22 @@ def _stream_exchange_worker(rank, world, port, n, out_q):
     psi = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
     psi /= np.linalg.norm(psi)
     shard = psi[rank << L:(rank + 1) << L].copy()
-    kinds = [st.kind for st in steps]
+    kinds = ["exchange" if st.scatter else st.kind for st in steps]
+
+    def a2a(shard):
+        src = torch.from_numpy(shard.view(np.float64).copy())
+        dst = torch.empty_like(src)
+        exchange_rank_bits(src, dst)
+        return dst.numpy().view(np.complex128).copy()
+
     for st in steps:
         if st.kind == "exchange":
-            src = torch.from_numpy(shard.view(np.float64).copy())
-            dst = torch.empty_like(src)
-            exchange_rank_bits(src, dst)
-            shard = dst.numpy().view(np.complex128).copy()
+            shard = a2a(shard)
         else:
-            shard = replay([st], L, 0, shard, lw.pool.array())
+            local = S.Step(st.kind, st.spass)                     # this rank's pass; the folded exchange is the all-to-all
+            shard = replay([local], L, 0, shard, lw.pool.array())
+            if st.scatter:
+                shard = a2a(shard)
     parts = [torch.zeros(2 * (1 << L), dtype=torch.float64) for _ in range(world)]
     dist.all_gather(parts, torch.from_numpy(shard.view(np.float64).copy()))
     if rank == 0:

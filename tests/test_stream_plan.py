@@ -29,10 +29,13 @@ def replay(steps, n, g, psi, cdata):
     """Execute a stream plan with NumPy on the full 2^n vector viewed as 2^g shards."""
     L = n - g
     shards = [psi[r << L:(r + 1) << L].copy() for r in range(1 << g)]
+    def exchange(shards):
+        chunks = [s.reshape(1 << g, -1) for s in shards]
+        return [np.concatenate([chunks[src][dst] for src in range(1 << g)]) for dst in range(1 << g)]
+
     for st in steps:
         if st.kind == "exchange":
-            chunks = [s.reshape(1 << g, -1) for s in shards]
-            shards = [np.concatenate([chunks[src][dst] for src in range(1 << g)]) for dst in range(1 << g)]
+            shards = exchange(shards)
             continue
         sp = st.spass
         assert sorted(sp.positions) == list(range(L)) and sorted(sp.positions_out) == list(range(L))
@@ -56,6 +59,9 @@ def replay(steps, n, g, psi, cdata):
                 perm[L - 1 - sp.positions_out[j]] = L - 1 - j
             new.append(np.ascontiguousarray(src.transpose(perm)).reshape(-1))
         shards = new
+        if st.scatter:                      # the exchange rides in this pass's store (qsb_stream_run_scatter)
+            assert g > 0 and all(p < L - g for p in sp.positions_out[sp.l:sp.l + sp.e])     # no box dimension on a peer bit
+            shards = exchange(shards)
     return np.concatenate(shards)
 
 
@@ -68,15 +74,17 @@ def reference_state(n, gl, psi):
 
 @pytest.mark.parametrize("n,g,m,layout", [(7, 0, 4, "reference"), (8, 1, 4, "reference"), (9, 2, 5, "textbook"),
                                           (11, 3, 5, "reference"), (11, 0, 6, "textbook"), (12, 2, 6, "reference")])
-def test_stream_plan_replay_matches_oracle(n, g, m, layout):
+@pytest.mark.parametrize("fuse_store", [True, False])
+def test_stream_plan_replay_matches_oracle(n, g, m, layout, fuse_store):
     rng = np.random.default_rng(n)
     gl = ordered(n, layered_circuit(n, 6, 40 + n))
     lw = lower(n, gl, layout=layout)
-    steps, pos_of, pending = S.plan(lw.items, lw.pool.array(), n, g, list(range(n)), local_bits=m, low_bits=2, box_bits=1)
+    steps, pos_of, pending = S.plan(lw.items, lw.pool.array(), n, g, list(range(n)), local_bits=m, low_bits=2, box_bits=1,
+                                    fuse_store=fuse_store)
     assert not pending
     kinds = [s.kind for s in steps]
     if g:
-        assert "exchange" in kinds
+        assert ("exchange" in kinds) != fuse_store and any(s.scatter for s in steps) == fuse_store
     psi = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
     psi /= np.linalg.norm(psi)
     got_mem = replay(steps, n, g, psi, lw.pool.array())
@@ -145,6 +153,7 @@ def test_pauli_draws_parameters_and_dense_gates_in_a_stream_plan():
     uni = rng.random(lw.n_draws)
     steps, pos_of, _ = S.plan(lw.items, lw.pool.array(), n, 1, list(range(n)), local_bits=5, low_bits=2, box_bits=1,
                               params=prm, uniforms=uni)
+    assert any(st.scatter for st in steps)
     psi = np.zeros(2 ** n, dtype=np.complex128)
     psi[0] = 1.0
     got_mem = replay(steps, n, 1, psi, lw.pool.array())
