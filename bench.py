@@ -574,7 +574,7 @@ def measure_sharded_state(rank, world, torch, dist, n):
         for name, targets, params in gl:
             lw.gate(name, targets, params, reg.get(name).matrix_func)
         comp = st.compile(lw)
-        kinds = [s.kind for s in comp[0]]
+        kinds = [s.kind for s in comp[0]] + ["exchange"] * sum(1 for s in comp[0] if s.scatter)
         blocks = sum(len(s.spass.blocks) for s in comp[0] if s.spass is not None)
         st.execute(comp)
         times = []
@@ -601,7 +601,7 @@ def measure_sharded_state(rank, world, torch, dist, n):
         out = {"qubits": n, "gates": len(gl), "n_gpus": world, "ms": ms, "gate_apps_per_s": len(gl) / (ms * 1e-3),
                "passes": kinds.count("pass"), "reorder_passes": kinds.count("reorder"), "block_sweeps": blocks,
                "exchanges": kinds.count("exchange"), "fused_exchanges": st.fused_exchanges // 4,
-               "exchange": "peer loads folded into the next pass (TMA over NVLink)" if st.fused_exchanges else
+               "exchange": "folded into the store of the preceding pass (peer-mapped TMA stores over NVLink)" if st.fused_exchanges else
                            ("NCCL all_to_all_single" if kinds.count("exchange") else "none"),
                "nvlink_bytes_per_gpu_per_direction": kinds.count("exchange") * (1 - 2.0 ** -g) * shard,
                "norm2": nrm,

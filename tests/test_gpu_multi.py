@@ -38,12 +38,15 @@ def _torchrun(n, args):
 
 
 @pytest.mark.skipif(_gpus() < 2, reason="needs at least 2 GPUs")
-@pytest.mark.parametrize("fuse", [True, False])
+@pytest.mark.parametrize("fuse", ["store", "load", "nccl"])
 def test_sharded_state_on_all_gpus_matches_the_oracle(fuse):
-    """Global qubits sharded over the GPUs of the box (all of them, a power of two), exchanges either folded into the
-    next pass's peer loads or done by the NCCL all-to-all: 24 qubits against the oracle, 28 qubits unit norm."""
+    """Global qubits sharded over the GPUs of the box (all of them, a power of two); exchanges folded into the store of
+    the preceding pass (peer-mapped TMA stores), into the load of the following pass (peer-mapped TMA loads), or done by
+    the NCCL all-to-all: 24 qubits against the oracle, 28 qubits unit norm."""
     n = 1 << (_gpus().bit_length() - 1)
-    out = _torchrun(n, ["--check-n", "24", "--check-depth", "3", "--qubits", "28", "--depth", "6"] + ([] if fuse else ["--no-fuse"]))
+    extra = ["--no-fuse"] if fuse == "nccl" else ["--fuse-where", fuse]
+    out = _torchrun(n, ["--check-n", "24", "--check-depth", "3", "--qubits", "28", "--depth", "6"] + extra)
+    fuse = fuse != "nccl"
     assert out["world"] == n
     assert out["check"]["max_abs_err"] < 1e-12 and abs(out["check"]["norm2"] - 1.0) < 1e-12
     assert out["run"]["exchanges"] >= 1 and abs(out["run"]["norm2"] - 1.0) < 1e-10

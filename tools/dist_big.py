@@ -14,13 +14,13 @@ import torch
 import torch.distributed as dist
 
 
-def check_against_oracle(n, depth, world, rank, engine, fuse):
+def check_against_oracle(n, depth, world, rank, engine, fuse, where="store"):
     """Reference semantics (axis scramble included) on every rank's shard, gathered and compared on rank 0."""
     from qsb.bigstate import BigState
     from qsb.workloads import layered_circuit
     from test_bigstate import ordered
     gl = ordered(n, layered_circuit(n, depth, 7 + n))
-    st = BigState(n, fuse_exchange=fuse, engine=engine)
+    st = BigState(n, fuse_exchange=fuse, engine=engine, fuse_where=where)
     st.apply_gates(gl)
     shard = torch.from_numpy(st.local_shard().view(np.float64).copy()).cuda()
     parts = [torch.empty_like(shard) for _ in range(world)]
@@ -44,13 +44,13 @@ def check_against_oracle(n, depth, world, rank, engine, fuse):
     return res
 
 
-def timed_run(n, depth, world, rank, engine, fuse, reps=3):
+def timed_run(n, depth, world, rank, engine, fuse, reps=3, where="store"):
     from qsb.bigstate import BigState
     from qsb.workloads import layered_circuit
     from quantum_sim.engine.gate_registry import GateRegistry
     from test_bigstate import ordered
     gl = ordered(n, layered_circuit(n, depth, 2026))
-    st = BigState(n, layout="textbook", fuse_exchange=fuse, engine=engine)
+    st = BigState(n, layout="textbook", fuse_exchange=fuse, engine=engine, fuse_where=where)
     lw = st.lowering()
     reg = GateRegistry.instance()
     for name, targets, params in gl:
@@ -59,7 +59,7 @@ def timed_run(n, depth, world, rank, engine, fuse, reps=3):
     times = []
     if engine == "tma":
         comp = st.compile(lw)                                   # plan + upload, outside the timed region
-        kinds = [s.kind for s in comp[0]]
+        kinds = [s.kind for s in comp[0]] + ["exchange"] * sum(1 for s in comp[0] if s.scatter)
         st.execute(comp)                                        # warm-up (also maps the second buffer)
         for _ in range(reps):
             if world > 1:
@@ -109,18 +109,21 @@ def main():
     ap.add_argument("--qubits", type=int, default=30)
     ap.add_argument("--depth", type=int, default=20)
     ap.add_argument("--engine", default="tma", choices=["tma", "executor"])
-    ap.add_argument("--no-fuse", action="store_true", help="NCCL all-to-all exchanges instead of peer loads folded into the next pass")
+    ap.add_argument("--no-fuse", action="store_true", help="NCCL all-to-all exchanges instead of peer-mapped TMA stores / loads")
+    ap.add_argument("--fuse-where", default="store", choices=["store", "load"],
+                    help="fold an exchange into the store of the pass before it (default) or into the load of the pass after it")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     os.environ["QSB_DEVICE"] = str(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    out = {"world": world, "engine": args.engine, "fuse": not args.no_fuse}
+    out = {"world": world, "engine": args.engine, "fuse": not args.no_fuse, "fuse_where": args.fuse_where}
     if args.check_n > 0:
-        out["check"] = check_against_oracle(args.check_n, args.check_depth, world, rank, args.engine, not args.no_fuse)
+        out["check"] = check_against_oracle(args.check_n, args.check_depth, world, rank, args.engine, not args.no_fuse,
+                                            args.fuse_where)
     if args.qubits > 0:
-        out["run"] = timed_run(args.qubits, args.depth, world, rank, args.engine, not args.no_fuse)
+        out["run"] = timed_run(args.qubits, args.depth, world, rank, args.engine, not args.no_fuse, where=args.fuse_where)
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:
