@@ -1269,6 +1269,14 @@ int qsb_stream_create(qsb_ctx* ctx, int32_t n, int32_t m, int32_t l, int32_t e, 
   return QSB_OK;
 }
 
+// tile-number bits that select the peer (positions >= shift on the given side), each set to the matching bit of `rank`
+static uint32_t peer_tile_xor(const qsb_stream* s, const int32_t* tile_pos, int shift, uint32_t rank) {
+  uint32_t x = 0;
+  for (int q = 0; q < s->ka.n - s->ka.m; ++q)
+    if (tile_pos[q] >= shift && ((rank >> (tile_pos[q] - shift)) & 1u)) x |= 1u << q;
+  return x;
+}
+
 static int stream_launch(qsb_stream* s, qsb_stream_maps& maps, int32_t flags) {
   qsb_ctx* ctx = s->ctx;
   const size_t smem = qsb_stream_smem_bytes(s->ka.m);
@@ -1311,6 +1319,7 @@ int qsb_stream_run(qsb_stream* s, qsb_buffer* in, int64_t in_offset, qsb_buffer*
   s->ka.peer_or = 0;
   s->ka.out_shift = 32;
   s->ka.out_or = 0;
+  s->ka.tile_xor = 0;
   return stream_launch(s, maps, flags);
 }
 
@@ -1344,6 +1353,7 @@ int qsb_stream_run_scatter(qsb_stream* s, qsb_buffer* in, int64_t in_offset, con
   s->ka.peer_or = 0;
   s->ka.out_shift = peer_shift;
   s->ka.out_or = (uint32_t)peer_rank_or;
+  s->ka.tile_xor = peer_tile_xor(s, s->ka.tile_pos_out, peer_shift, (uint32_t)(peer_rank_or >> peer_shift));
   return stream_launch(s, maps, flags);
 }
 
@@ -1375,6 +1385,7 @@ int qsb_stream_run_peers(qsb_stream* s, const void* const* peers, int32_t n_peer
   s->ka.peer_or = (uint32_t)peer_rank_or;
   s->ka.out_shift = 32;
   s->ka.out_or = 0;
+  s->ka.tile_xor = peer_tile_xor(s, s->ka.tile_pos, peer_shift, (uint32_t)(peer_rank_or >> peer_shift));
   return stream_launch(s, maps, flags);
 }
 

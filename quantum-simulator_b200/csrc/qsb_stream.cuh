@@ -52,7 +52,10 @@ struct qsb_stream_kargs {
   int32_t peer_shift, pad0;              // source element x comes from in[x >> peer_shift] (peer_shift = n: one source)
   uint32_t peer_or, pad1;                // ... at offset (x & (2^peer_shift - 1)) | peer_or
   int32_t out_shift, pad2;               // destination element x goes to out[x >> out_shift] (out_shift = 32: one destination)
-  uint32_t out_or, pad3;                 // ... at offset (x & (2^out_shift - 1)) | out_or
+  uint32_t out_or;                       // ... at offset (x & (2^out_shift - 1)) | out_or
+  uint32_t tile_xor;                     // XORed into the tile number: with peers, rank r walks its tiles in an order
+                                         // in which the peer-selecting tile bits are flipped by r, so that at any
+                                         // moment the ranks talk to DIFFERENT peers (no incast on one GPU's links)
   int32_t n_sweeps, n_ops;               // sweeps per tile; TMA ops per tile = 2^(m - l - e)
   int32_t op_pos[16];                    // slot l+e+j -> bit position in the (local) amplitude index, load side
   int32_t tile_pos[32];                  // slot m+j   -> bit position, load side
@@ -264,7 +267,7 @@ qsb_stream_kernel(const __grid_constant__ qsb_stream_maps maps, const __grid_con
   const int64_t ntiles = (int64_t)1 << (a.n - a.m);
   const int64_t mine = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;   // tiles of this CTA
   auto tile_base = [&](int64_t j, const int32_t* pos) {
-    const uint32_t t = (uint32_t)(blockIdx.x + j * gridDim.x);
+    const uint32_t t = (uint32_t)(blockIdx.x + j * gridDim.x) ^ a.tile_xor;
     uint32_t off = 0;
     for (int q = 0; q < a.n - a.m; ++q) off |= ((t >> q) & 1u) << pos[q];
     return off;
