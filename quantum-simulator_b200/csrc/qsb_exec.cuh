@@ -69,6 +69,9 @@ struct alignas(8) c64 { float x, y; };
 #define QSB_MAX_LOCAL_BITS 13      // complex128 tile of 128 KiB; complex64 tiles hold one bit more (QSB_MAX_LOCAL_BITS_C64)
 #define QSB_MAX_LOCAL_BITS_C64 14
 #define QSB_AD_MARGIN 1e-10
+#ifndef QSB_AD_BOUNDS
+#define QSB_AD_BOUNDS 1         // amplitude-damping draws outside the certain-K0 range are decided from bounds first (no flush)
+#endif
 #define QSB_CHUNK 128          // ops staged in shared memory per refill
 #ifndef QSB_REMAP_REGS
 #define QSB_REMAP_REGS 16      // amplitudes a thread stages per remap / rank-bit flush round
@@ -169,6 +172,7 @@ struct qsb_ctl {
   double red[2][4];            // this CTA's contribution to a cluster reduction, double-buffered
   double red_total[4];         // cluster-wide result handed to the control warp (RDM1)
   double wtab[256];            // weighted marginal: products of diagonal-pending weights over index bits 0..6 | 7..13
+  double slotw[32][4];         // amplitude-damping draw: diag(P^H P) of each slot's pending matrix and its off-diagonal ratio (control warp)
   unsigned long long xbar;     // mbarrier of the workers-only cluster barrier (device)
   unsigned long long dbar[4];  // decode warp <-> control warp: chunk[b] full (b), chunk[b] empty (2 + b) (device)
 };
@@ -522,9 +526,11 @@ QSB_PASS void qsb_partial_rdm1(Env& env, int m, int b, double v[4]) {
   }
 }
 
-// Marginal of slot bit b when some slots still carry DIAGONAL pending matrices (they need no flush: a diagonal
-// only reweights |amplitude|^2).  wt[j][v] = |P_j[v][v]|^2; v[0], v[1] = sum over x with x_b = 0 / 1 of
-// W(x) |phi_x|^2, W(x) = prod_j wt[j][x_j] (rank bits contribute this CTA's constant factor).
+// 1-qubit reduced density matrix of slot bit b under per-slot diagonal weights: wt[j][v] = weight of value v of slot j
+// (|P_j[v][v]|^2 of a diagonal pending matrix, which needs no flush: a diagonal only reweights |amplitude|^2; the
+// diagonal of P_j^H P_j in the bounded amplitude-damping draw).  W(x) = prod_j wt[j][x_j]; rank bits contribute this
+// CTA's constant factor.  v[0], v[1] = sum over x with x_b = 0 / 1 of W(x) |phi_x|^2; for a local bit b whose own
+// weights are (1, 1) also v[2] + i v[3] = sum W(x) phi_x0 conj(phi_x1).
 template <class Env>
 QSB_PASS void qsb_partial_marginal_w(Env& env, int m, int b, const double* wt, double v[4]) {
   typedef typename Env::amp A;
@@ -549,12 +555,28 @@ QSB_PASS void qsb_partial_marginal_w(Env& env, int m, int b, const double* wt, d
     return;
   }
   const int cnt = 1 << (m - 1);
-  for (int g = env.wid; g < cnt; g += env.W) {
-    const int i0 = qsb_ins0(g, b), i1 = i0 | (1 << b);
-    v[0] += tab[i0 & 127] * tab[128 + (i0 >> 7)] * qsb_norm2(tile[QSB_SLOT(i0)]);
-    v[1] += tab[i1 & 127] * tab[128 + (i1 >> 7)] * qsb_norm2(tile[QSB_SLOT(i1)]);
+  // four pairs per step: all the loads (two amplitudes and four table entries per pair) are in flight together
+  for (int g = env.wid; g < cnt; g += 4 * env.W) {
+    c128 a0[4], a1[4];
+    double w0[4], w1[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gg = g + j * env.W;
+      const bool ok = gg < cnt;
+      const int i0 = qsb_ins0(ok ? gg : g, b), i1 = i0 | (1 << b);
+      a0[j] = qsb_wide(tile[QSB_SLOT(i0)]); a1[j] = qsb_wide(tile[QSB_SLOT(i1)]);
+      w0[j] = ok ? tab[i0 & 127] * tab[128 + (i0 >> 7)] : 0.0;
+      w1[j] = ok ? tab[i1 & 127] * tab[128 + (i1 >> 7)] : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[0] += w0[j] * qsb_norm2(a0[j]);
+      v[1] += w1[j] * qsb_norm2(a1[j]);
+      v[2] += w0[j] * (a0[j].x * a1[j].x + a0[j].y * a1[j].y);   // meaningful when wt[b] = (1, 1): w0 is the pair's weight
+      v[3] += w0[j] * (a0[j].y * a1[j].x - a0[j].x * a1[j].y);
+    }
   }
-  v[0] *= crank; v[1] *= crank;
+  v[0] *= crank; v[1] *= crank; v[2] *= crank; v[3] *= crank;
 }
 
 template <class Env>
@@ -1068,10 +1090,15 @@ QSB_CTL void qsb_flush(Env& env, qsb_cstate& st, int m, uint32_t which) {
 
 // (unnormalised) 1-qubit reduced density matrix sums of slot bit b of the CURRENT state, in every control warp
 template <class Env>
-QSB_CTL void qsb_ctl_rdm1(Env& env, qsb_cstate& st, int b, double v[4], bool weighted = false) {
+QSB_CTL void qsb_ctl_rdm1(Env& env, qsb_cstate& st, int b, double v[4], int weighted = 0, int n = 0, double* clu = nullptr) {
   qsb_desc* d = qsb_desc_begin(env, st);
   if (env.lead) { d->kind = QSB_D_RDM1; d->k = 1; d->b[0] = b; d->flags = weighted ? 1 : 0; }
-  if (weighted) {
+  if (weighted == 2) {
+    // weights = diag(P^H P) of every other slot (ctl->slotw, filled by the caller), (1, 1) for b itself
+    env.sync_control();
+    double* wt = reinterpret_cast<double*>(d->mat);
+    for (int e = env.clane; e < 64; e += env.CL) wt[e] = (e >> 1) == b ? 1.0 : env.ctl()->slotw[e >> 1][e & 1];
+  } else if (weighted) {
     // weights |P[v][v]|^2 of the (diagonal) pending matrices that stay pending; identity where nothing is pending
     env.sync_control();
     double* wt = reinterpret_cast<double*>(d->mat);
@@ -1081,6 +1108,11 @@ QSB_CTL void qsb_ctl_rdm1(Env& env, qsb_cstate& st, int b, double v[4], bool wei
     }
   }
   qsb_desc_end(env, st);
+  if (clu) {             // while the workers read the tile: prod(1 -+ rho_s) of the bounded amplitude-damping draw
+    double cl = 1.0, cu = 1.0;
+    for (int slot = 0; slot < n; ++slot) { const double rho = env.ctl()->slotw[slot][2]; cl *= 1.0 - rho; cu *= 1.0 + rho; }
+    clu[0] = cl; clu[1] = cu;
+  }
   env.handoff_c();
   for (int k = 0; k < 4; ++k) v[k] = env.ctl()->red_total[k];
 }
@@ -1203,12 +1235,75 @@ QSB_CTL void qsb_control_slow(Env& env, const qsb_exec_args& a, qsb_cstate& st, 
       const double* cd = a.cdata + op.data;
       const double u = ck->u[i], gam = cd[0];
       double v[4];
-      // only DENSE pending matrices have to be applied before the marginal is taken: diagonal ones (the K0's of
-      // earlier draws, Rz / phase gates) just reweight |amplitude|^2 and ride along as weights
-      qsb_flush(env, st, m, qsb_cls_dense_mask(st.clsword));
-      qsb_ctl_rdm1(env, st, b, v, true);
-      double p[2] = {v[0] + (1.0 - gam) * v[1], gam * v[1]};
-      const int idx = qsb_choice(p, 2, u);
+      int idx = -1;
+#if QSB_AD_BOUNDS
+      // Bounded draw: nothing is flushed.  With M_s = P_s^H P_s of the pending matrix of every other slot s,
+      // (1 - rho_s) D_s <= M_s <= (1 + rho_s) D_s  (D_s = diag M_s, rho_s = |M_s01| / sqrt(M_s00 M_s11), Loewner order),
+      // so the weighted marginals N_v taken with the DIAGONAL weights D_s bracket the true ones between
+      // prod(1 - rho_s) N_v and prod(1 + rho_s) N_v.  The pending matrices are unitaries times a few damping K0's:
+      // rho_s ~ gamma / 2, the bracket on P(q = 1) is a few per cent wide and decides all but ~2 % of the draws with
+      // ONE read of the tile; the rest take the exact path below.  Slots that are far from diagonal (rho > 0.1: a K1
+      // branch that no sweep has absorbed yet) are flushed on their own first, and so is b when it is a cluster-rank
+      // slot whose pending matrix mixes the two sides (the off-diagonal of its marginal lives in two CTAs).
+      {
+        uint32_t far = 0;
+        env.sync_control();
+        for (int slot = env.clane; slot < 32; slot += env.CL) {
+          double sa = 1.0, sd = 1.0, rho = 0.0;
+          int isfar = 0;
+          if (slot < n) {
+            const c128* P = ctl->pend[slot];
+            if (slot == b) {
+              isfar = slot >= m && (qsb_norm2(P[0]) * qsb_norm2(P[1]) + qsb_norm2(P[2]) * qsb_norm2(P[3]) > 0.0);
+            } else {
+              sa = qsb_norm2(P[0]) + qsb_norm2(P[2]); sd = qsb_norm2(P[1]) + qsb_norm2(P[3]);
+              const double ex = P[0].x * P[1].x + P[0].y * P[1].y + P[2].x * P[3].x + P[2].y * P[3].y;
+              const double ey = P[0].x * P[1].y - P[0].y * P[1].x + P[2].x * P[3].y - P[2].y * P[3].x;
+              const double e2 = ex * ex + ey * ey;
+              if (e2 > 0.0) {
+                rho = sa * sd > 0.0 ? sqrt(e2 / (sa * sd)) : 1.0;
+                if (rho > 1.0) rho = 1.0;
+                isfar = rho > 0.1;
+              }
+            }
+          }
+          ctl->slotw[slot][0] = sa; ctl->slotw[slot][1] = sd; ctl->slotw[slot][2] = rho;
+          far |= env.ballot_slot(isfar, slot);
+        }
+        env.sync_control();
+        if (far) {
+          qsb_flush(env, st, m, far);                 // their pending matrices are the identity now
+          for (int slot = env.clane; slot < 32; slot += env.CL)
+            if ((far >> slot) & 1u) { ctl->slotw[slot][0] = 1.0; ctl->slotw[slot][1] = 1.0; ctl->slotw[slot][2] = 0.0; }
+          env.sync_control();
+        }
+        double clu[2];
+        qsb_ctl_rdm1(env, st, b, v, 2, n, clu);
+        const double cl = clu[0], cu = clu[1];
+        const c128* P = ctl->pend[b];
+        double nv[2];
+        for (int r = 0; r < 2; ++r) {
+          const c128 p0 = P[2 * r], p1 = P[2 * r + 1];      // N_r = sum_ij P[r][i] conj(P[r][j]) R_ij
+          nv[r] = qsb_norm2(p0) * v[0] + qsb_norm2(p1) * v[1] +
+                  2.0 * ((p0.x * p1.x + p0.y * p1.y) * v[2] - (p0.y * p1.x - p0.x * p1.y) * v[3]);
+          if (nv[r] < 0.0) nv[r] = 0.0;
+        }
+        const double dlo = cl * nv[1] + cu * nv[0], dhi = cu * nv[1] + cl * nv[0];
+        if (dlo > 0.0 && dhi > 0.0) {
+          const double lo = cl * nv[1] / dlo, hi = cu * nv[1] / dhi;      // lo <= P(q = 1) <= hi
+          if (u < 1.0 - gam * hi - QSB_AD_MARGIN) idx = 0;                 // cdf[0] = 1 - gamma P(q = 1)
+          else if (u > 1.0 - gam * lo + QSB_AD_MARGIN) idx = 1;
+        }
+      }
+#endif
+      if (idx < 0) {
+        // exact draw.  Only DENSE pending matrices have to be applied before the marginal is taken: diagonal ones (the
+        // K0's of earlier draws, Rz / phase gates) just reweight |amplitude|^2 and ride along as weights
+        qsb_flush(env, st, m, qsb_cls_dense_mask(st.clsword));
+        qsb_ctl_rdm1(env, st, b, v, 1);
+        double p[2] = {v[0] + (1.0 - gam) * v[1], gam * v[1]};
+        idx = qsb_choice(p, 2, u);
+      }
       if (st.record) a.branches[st.t * a.branches_stride + op.draw] = idx;
       const int cls = qsb_cls_of(st.clsword, b);
       if (env.lead) {

@@ -118,6 +118,31 @@ def test_noisy_trajectories_reference_draws(run, golden, gbits):
         assert np.max(np.abs(out["snapshots"][0] - a[rec["tag"] + "_steps"])) < TOL, rec["tag"]
 
 
+@pytest.mark.parametrize("gbits", [0, 1, 3])
+@pytest.mark.parametrize("gamma", [0.02, 0.3])
+def test_amplitude_damping_draws_outside_the_certain_range(run, gbits, gamma):
+    """Most draws are forced into [1 - gamma, 1), where the branch depends on P(q = 1) of the state: the executor
+    first brackets it with diagonal weights (no flush; csrc/qsb_exec.cuh, QSB_AD_BOUNDS) and falls back to the exact
+    marginal; either way branches and amplitudes are the reference's (noise.py:241-255)."""
+    n = 7
+    gates = layered_circuit(n, 6, 23)
+    noise = {"global": [("depolarizing", 0.01), ("amplitude_damping", gamma)], "gate": {}}
+    qc = make_circuit(n, gates)
+    prog, _ = lower_circuit(n, qc.get_ordered_gates(), REG, channels_of_factory(noise), local_bits=n - gbits)
+    rng = np.random.default_rng(100 + gbits)
+    draws = rng.random((8, prog.n_draws))
+    slow = rng.random(draws.shape) < 0.7
+    draws = np.where(slow, 1.0 - gamma * rng.random(draws.shape), draws)
+    out = run(prog, count=8, T=2, uniforms=draws, want_branches=True)
+    n_k1 = 0
+    for t in range(8):
+        psi, _, br, _ = O.run_state(n, gates, None, noise, draws[t])
+        assert out["branches"][t].tolist() == br
+        assert np.max(np.abs(out["states"][t] - psi)) < TOL
+        n_k1 += sum(1 for k, x in enumerate(br) if k % 2 == 1 and x == 1)
+    assert n_k1 > 0                                  # K1 branches (rank-1 pending matrices) were exercised
+
+
 def test_generic_kraus_matches_builtin_channels(run):
     rng = np.random.default_rng(11)
     n = 5
