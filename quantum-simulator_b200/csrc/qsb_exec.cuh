@@ -171,6 +171,7 @@ struct qsb_ctl {
   double wpart[32 * 4];        // per-warp partial sums (workers)
   double red[2][4];            // this CTA's contribution to a cluster reduction, double-buffered
   double red_total[4];         // cluster-wide result handed to the control warp (RDM1)
+  double redx[2][8][4];        // RDM1: the partial sums every CTA of the cluster pushed here (by source rank), double-buffered
   double wtab[256];            // weighted marginal: products of diagonal-pending weights over index bits 0..6 | 7..13
   double slotw[32][4];         // amplitude-damping draw: diag(P^H P) of each slot's pending matrix and its off-diagonal ratio (control warp)
   unsigned long long xbar;     // mbarrier of the workers-only cluster barrier (device)
@@ -884,7 +885,7 @@ QSB_PASS void qsb_do_gflush(Env& env, int m, const qsb_desc* d) {
 template <class Env>
 QSB_HD void qsb_worker_loop(Env& env, const qsb_exec_args& a) {
   const int m = a.m;
-  int parity = 0;
+  int parity = 0, xpar = 0;
   const bool prof = Env::PROF && a.prof != nullptr && env.wid == 0;
   const bool wprof = Env::PROF && a.prof != nullptr && env.lane == 0;      // per-warp busy / wait cycles
   unsigned long long wb = 0, ww = 0, w0 = 0, w1 = 0;
@@ -907,22 +908,37 @@ QSB_HD void qsb_worker_loop(Env& env, const qsb_exec_args& a) {
         double v[4];
         if (d->flags & 1) qsb_partial_marginal_w(env, m, d->b[0], reinterpret_cast<const double*>(d->mat), v);
         else qsb_partial_rdm1(env, m, d->b[0], v);
-        qsb_block_reduce(env, v, 4);
-        if (env.C > 1) {
-          if (env.wid == 0)
-            for (int k = 0; k < 4; ++k) env.ctl()->red[parity][k] = v[k];
-          env.cluster_sync_w();
-          if (env.wid == 0)
-            for (int k = 0; k < 4; ++k) {
-              double s = 0.0;
-              for (int r = 0; r < env.C; ++r) s += env.peer_ctl(r)->red[parity][k];
-              v[k] = s;
-            }
+        // CTA sums: one partial per warp; cluster sums: entry (r, k) of this CTA's sums is PUSHED into the buffer of
+        // CTA r (remote store, then the workers' cluster barrier), so that after the barrier every CTA adds eight
+        // local values in the same order -- the same bits everywhere, and no remote load on the critical path
+        double* wp = env.ctl()->wpart;
+        env.sync_workers();                 // previous users of wpart are done
+        for (int k = 0; k < 4; ++k) {
+          const double x = env.warp_sum(v[k]);
+          if (env.lane == 0) wp[env.warp * 4 + k] = x;
         }
-        if (env.wid == 0)
-          for (int k = 0; k < 4; ++k) env.ctl()->red_total[k] = v[k];
+        env.sync_workers();
+        if (env.C > 1) {
+          for (int e = env.wid; e < 4 * env.C; e += env.W) {
+            const int r = e >> 2, k = e & 3;
+            double sum = 0.0;
+            for (int w = 0; w < env.nwarps; ++w) sum += wp[w * 4 + k];
+            env.peer_ctl_w(r)->redx[xpar][env.rank][k] = sum;
+            env.fence_cluster();            // the remote store is ordered before the barrier's release-arrive of another thread
+          }
+          env.cluster_sync_w();
+          if (env.wid < 4) {
+            double sum = 0.0;
+            for (int r = 0; r < env.C; ++r) sum += env.ctl()->redx[xpar][r][env.wid];
+            env.ctl()->red_total[env.wid] = sum;
+          }
+          xpar ^= 1;
+        } else if (env.wid < 4) {
+          double sum = 0.0;
+          for (int w = 0; w < env.nwarps; ++w) sum += wp[w * 4 + env.wid];
+          env.ctl()->red_total[env.wid] = sum;
+        }
         env.handoff_w();                    // the local control warp reads red_total after this barrier
-        parity ^= 1;
         break;
       }
       case QSB_D_STORE: qsb_do_store(env, a, d, parity); break;

@@ -83,6 +83,10 @@ struct DeviceEnv {
     if (CS > 1) return cg::this_cluster().map_shared_rank(ctl(), r);
     return ctl();
   }
+  __device__ __forceinline__ qsb_ctl* peer_ctl_w(int r) {
+    if (CS > 1) return cg::this_cluster().map_shared_rank(ctl(), r);
+    return ctl();
+  }
   __device__ __forceinline__ void atomic_add(double* p, double v) { atomicAdd(p, v); }
   __device__ __forceinline__ double warp_sum(double x) {
     for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);

@@ -50,6 +50,7 @@ struct HostEnv {
   c128* peer_tile_w(int r) { return sh->cta[r]->tile.data(); }
   void fence_cluster() {}
   const qsb_ctl* peer_ctl(int r) { return C > 1 ? &sh->cta[r]->ctl : &me().ctl; }
+  qsb_ctl* peer_ctl_w(int r) { return C > 1 ? &sh->cta[r]->ctl : &me().ctl; }
   void atomic_add(double* p, double v) { std::lock_guard<std::mutex> g(sh->mu); *p += v; }
   double warp_sum(double x) { return x; }     // one-lane "warps"
   unsigned long long clock() { return 0; }
