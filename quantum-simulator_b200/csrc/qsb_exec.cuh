@@ -139,6 +139,12 @@ struct alignas(16) qsb_desc {
   int32_t hmask;           // SWEEP: index bits the group-number bits above log2(W) land on (ascending)
   int32_t pad1;
   c128 P[3][4];            // pending matrices (row-major), valid where cls != NONE
+  // SWEEP without a dense gate (filled by the control warp, qsb_sweep_tables): swizzled tile offsets local index r is
+  // loaded from / stored to (the permutation gates only move the store), and its real factor (damping scales of the
+  // bits without a full 2x2, sign of CZ)
+  alignas(16) int32_t off[8];
+  alignas(16) int32_t ost[8];
+  alignas(16) double f[8];
   c128 mat[64];            // dense 4x4 / 8x8 gate of this sweep
 };
 
@@ -477,9 +483,105 @@ QSB_PASS void qsb_sweep(Env& env, int m, const qsb_desc* d) {
   }
 }
 
+// The same sweep with the run-time choices taken out of the loop.  DM (compile time): bit k set = the pending matrix of
+// b[k] is a full 2x2.  Everything else is data: the other bits carry a real scale of their |1> half (the damping
+// K0's; 1.0 when nothing is pending), folded with the sign of CZ into one factor per local index, and the permutation
+// gates (CX, SWAP, Toffoli, Fredkin) only change where a register is STORED.  With the class and gate branches inside
+// the loop (qsb_sweep above) ptxas cannot move a group's arithmetic under the loads and stores of its neighbours and
+// the workers of a CTA, which enter a sweep together, alternate between the shared-memory pipe and the FP64 pipe:
+// tools/micro/sweep_real.cu, one dense pending matrix: 3 720 -> 2 620 cycles per sweep.
+template <int K, int DM, class Env>
+QSB_PASS void qsb_sweep_s(Env& env, int m, const qsb_desc* d) {
+  typedef typename Env::amp A;
+  typedef typename qsb_amp<A>::real R;
+  A* tile = env.tile();
+  const unsigned long long sq0 = env.prof_on() ? env.clock() : 0;
+  constexpr int D = 1 << K;
+  constexpr int ND = (DM & 1) + ((DM >> 1) & 1) + ((DM >> 2) & 1);
+  constexpr int DIDX = ((DM & 1) ? (1 << (K - 1)) : 0) | ((K > 1 && (DM & 2)) ? (1 << (K - 2)) : 0) | ((K > 2 && (DM & 4)) ? 1 : 0);   // local-index bits with a full 2x2
+  constexpr int NG = (K == 3 && ND >= 2) ? 1 : (QSB_AMPS / D > 0 ? QSB_AMPS / D : 1);   // 16 amplitudes + 3 matrices would spill
+  const int wbits = env.wbits;
+  const int lo_base = qsb_deposit(env.wid, d->pos, wbits < m - K ? wbits : m - K);
+  const int hmask = d->hmask;
+  int hi = 0;
+  int off[D], ost[D];               // swizzled offsets: where local index r is loaded from / stored to
+  R f[D];                           // real factor of local index r (scales of the non-dense bits, sign of CZ)
+#pragma unroll
+  for (int r = 0; r < D; ++r) { off[r] = d->off[r]; ost[r] = d->ost[r]; f[r] = (R)d->f[r]; }
+  A P[K][4];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    if (!((DM >> k) & 1)) continue;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) P[k][e] = qsb_cvt<A>(d->P[k][e]);
+  }
+  const int cnt = 1 << (m - K);
+  if (env.prof_on()) env.prof_add(124, env.clock() - sq0);
+  for (int g0 = env.wid; g0 < cnt; g0 += NG * env.W) {
+    A a[NG][D];
+    int base[NG];
+#pragma unroll
+    for (int j = 0; j < NG; ++j) {
+      const int bs = lo_base | hi;        // out-of-range groups of a short tile wrap onto valid ones (never stored)
+      hi = ((hi | ~hmask) + 1) & hmask;
+      base[j] = QSB_SLOT(bs);
+#pragma unroll
+      for (int r = 0; r < D; ++r) a[j][r] = tile[base[j] ^ off[r]];
+    }
+#pragma unroll
+    for (int j = 0; j < NG; ++j) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        if (!((DM >> k) & 1)) continue;
+        const int bit = 1 << (K - 1 - k);
+#pragma unroll
+        for (int r = 0; r < D; ++r) {
+          if (r & bit) continue;
+          const A lo = a[j][r], up = a[j][r | bit];
+          a[j][r] = qsb_fma(P[k][1], up, qsb_mul(P[k][0], lo));
+          a[j][r | bit] = qsb_fma(P[k][3], up, qsb_mul(P[k][2], lo));
+        }
+      }
+      if (g0 + j * env.W < cnt) {
+#pragma unroll
+        for (int r = 0; r < D; ++r) {
+          A v = a[j][r];
+          // a factor other than 1 needs a |1> on a bit without a full 2x2, or is the sign of CZ on |11>
+          if ((r & ~DIDX) != 0 || (K == 2 && r == D - 1)) { v.x *= f[r]; v.y *= f[r]; }
+          tile[base[j] ^ ost[r]] = v;
+        }
+      }
+    }
+  }
+}
+
 template <class Env>
 QSB_HD void qsb_do_sweep(Env& env, int m, const qsb_desc* d) {
   const bool dg = d->gate == QSB_G_DENSE;
+#if QSB_GROUP_POS
+  if (!dg) {
+    int dm = 0;
+    for (int k = 0; k < d->k; ++k) if (d->cls[k] >= QSB_CLS_DIAG) dm |= 1 << k;
+    switch (d->k * 8 + dm) {
+      case 8: qsb_sweep_s<1, 0>(env, m, d); break;
+      case 9: qsb_sweep_s<1, 1>(env, m, d); break;
+      case 16: qsb_sweep_s<2, 0>(env, m, d); break;
+      case 17: qsb_sweep_s<2, 1>(env, m, d); break;
+      case 18: qsb_sweep_s<2, 2>(env, m, d); break;
+      case 19: qsb_sweep_s<2, 3>(env, m, d); break;
+      case 24: qsb_sweep_s<3, 0>(env, m, d); break;
+      case 25: qsb_sweep_s<3, 1>(env, m, d); break;
+      case 26: qsb_sweep_s<3, 2>(env, m, d); break;
+      case 27: qsb_sweep_s<3, 3>(env, m, d); break;
+      case 28: qsb_sweep_s<3, 4>(env, m, d); break;
+      case 29: qsb_sweep_s<3, 5>(env, m, d); break;
+      case 30: qsb_sweep_s<3, 6>(env, m, d); break;
+      case 31: qsb_sweep_s<3, 7>(env, m, d); break;
+      default: break;
+    }
+    return;
+  }
+#endif
   if (d->k == 1) qsb_sweep<1, false>(env, m, d);
   else if (d->k == 2) { if (dg) qsb_sweep<2, true>(env, m, d); else qsb_sweep<2, false>(env, m, d); }
   else if (d->k == 3) { if (dg) qsb_sweep<3, true>(env, m, d); else qsb_sweep<3, false>(env, m, d); }
@@ -1028,6 +1130,35 @@ QSB_HD void qsb_desc_end(Env& env, qsb_cstate& st) {
   env.ring_publish((int)(st.seq % QSB_RING));
   ++st.seq;
 }
+// load / store offsets and real factors of a sweep's local indices (qsb_desc::off, ost, f): lane r works out entry r.
+// d->P and the class word `w` (before this sweep's reset) describe the pending matrices of the sweep's bits.
+template <class Env>
+QSB_CTL void qsb_sweep_tables(Env& env, qsb_desc* d, uint64_t w, int gate, int nb, int b0, int b1, int b2) {
+  const int D = 1 << nb;
+  for (int r = env.clane; r < D; r += env.CL) {
+    int pr = r;                     // the gate moves the amplitude of local index r to local index pr
+    if (nb == 2) {
+      if (gate == QSB_G_CX) pr = (r & 2) ? (r ^ 1) : r;                          // b[0] control, b[1] target
+      else if (gate == QSB_G_SWAP) pr = ((r & 1) << 1) | (r >> 1);
+    } else if (nb == 3) {
+      if (gate == QSB_G_CCX) pr = ((r & 6) == 6) ? (r ^ 1) : r;                  // 110 <-> 111
+      else if (gate == QSB_G_CSWAP) pr = (r & 4) ? (4 | ((r & 1) << 1) | ((r >> 1) & 1)) : r;   // 101 <-> 110
+    }
+    int o = 0, os = 0;
+    double fr = 1.0;
+    for (int k = 0; k < nb; ++k) {
+      const int b = k == 0 ? b0 : (k == 1 ? b1 : b2);
+      if ((r >> (nb - 1 - k)) & 1) {
+        o |= 1 << b;
+        if (qsb_cls_of(w, b) == QSB_CLS_RDIAG) fr *= d->P[k][3].x;
+      }
+      if ((pr >> (nb - 1 - k)) & 1) os |= 1 << b;
+    }
+    if (nb == 2 && r == 3 && gate == QSB_G_CZ) fr = -fr;
+    d->off[r] = QSB_SLOT(o); d->ost[r] = QSB_SLOT(os); d->f[r] = fr;
+  }
+}
+
 // publish one sweep over `nb` local bits (bits[0] = MSB of the gate index) and reset their pending matrices.
 // The lanes of the control warp share the copies: entry e of bit k goes through lane 4k + e.
 template <class Env>
@@ -1044,6 +1175,10 @@ QSB_CTL void qsb_emit_sweep(Env& env, qsb_cstate& st, int m, int gate, int nb, i
     const int b = k == 0 ? b0 : (k == 1 ? b1 : b2);
     d->P[k][j] = ctl->pend[b][j];
     ctl->pend[b][j] = qsb_c((j == 0 || j == 3) ? 1.0 : 0.0, 0.0);
+  }
+  if (gate != QSB_G_DENSE) {
+    env.sync_control();                        // d->P is complete
+    qsb_sweep_tables(env, d, w, gate, nb, b0, b1, b2);
   }
   const unsigned long long pq1 = st.prof ? env.clock() : 0;
   uint32_t used = 1u << b0;
