@@ -142,6 +142,10 @@ struct alignas(16) qsb_desc {
   // SWEEP without a dense gate (filled by the control warp, qsb_sweep_tables): swizzled tile offsets local index r is
   // loaded from / stored to (the permutation gates only move the store), and its real factor (damping scales of the
   // bits without a full 2x2, sign of CZ)
+  // SWEEP: tile-index bits of a worker's first group = tabl[worker & 31] | tabw[worker >> 5] (the group-number bits below
+  // log2(W) laid onto `pos`; one entry per control lane, so the workers replace a dependent bit loop by two loads)
+  alignas(16) int32_t tabl[32];
+  alignas(16) int32_t tabw[8];
   alignas(16) int32_t off[8];
   alignas(16) int32_t ost[8];
   alignas(16) double f[8];
@@ -378,8 +382,7 @@ QSB_PASS void qsb_sweep(Env& env, int m, const qsb_desc* d) {
   // group g = wid + j W (W = 2^wbits): the bits of wid are laid onto the tile index once per sweep; the
   // bits of j land on `hmask` in ascending order, so consecutive j are a masked increment
 #if QSB_GROUP_POS
-  const int wbits = env.wbits;
-  const int lo_base = qsb_deposit(env.wid, d->pos, wbits < m - K ? wbits : m - K);
+  const int lo_base = d->tabl[env.wid & 31] | d->tabw[env.wid >> 5];
   const int hmask = d->hmask;
   int hi = 0;
 #else
@@ -500,8 +503,7 @@ QSB_PASS void qsb_sweep_s(Env& env, int m, const qsb_desc* d) {
   constexpr int ND = (DM & 1) + ((DM >> 1) & 1) + ((DM >> 2) & 1);
   constexpr int DIDX = ((DM & 1) ? (1 << (K - 1)) : 0) | ((K > 1 && (DM & 2)) ? (1 << (K - 2)) : 0) | ((K > 2 && (DM & 4)) ? 1 : 0);   // local-index bits with a full 2x2
   constexpr int NG = (K == 3 && ND >= 2) ? 1 : (QSB_AMPS / D > 0 ? QSB_AMPS / D : 1);   // 16 amplitudes + 3 matrices would spill
-  const int wbits = env.wbits;
-  const int lo_base = qsb_deposit(env.wid, d->pos, wbits < m - K ? wbits : m - K);
+  const int lo_base = d->tabl[env.wid & 31] | d->tabw[env.wid >> 5];
   const int hmask = d->hmask;
   int hi = 0;
   int off[D], ost[D];               // swizzled offsets: where local index r is loaded from / stored to
@@ -560,9 +562,7 @@ QSB_HD void qsb_do_sweep(Env& env, int m, const qsb_desc* d) {
   const bool dg = d->gate == QSB_G_DENSE;
 #if QSB_GROUP_POS
   if (!dg) {
-    int dm = 0;
-    for (int k = 0; k < d->k; ++k) if (d->cls[k] >= QSB_CLS_DIAG) dm |= 1 << k;
-    switch (d->k * 8 + dm) {
+    switch (d->k * 8 + d->flags) {          // flags = dense mask (qsb_emit_sweep)
       case 8: qsb_sweep_s<1, 0>(env, m, d); break;
       case 9: qsb_sweep_s<1, 1>(env, m, d); break;
       case 16: qsb_sweep_s<2, 0>(env, m, d); break;
@@ -1191,11 +1191,20 @@ QSB_CTL void qsb_emit_sweep(Env& env, qsb_cstate& st, int m, int gate, int nb, i
   const unsigned long long pq2 = st.prof ? env.clock() : 0;
   if (st.prof) { st.t_e[0] += pq0 - pe0; st.t_e[1] += pq1 - pq0; st.t_e[2] += pq2 - pq1; }
   if (env.lead) {
-    d->kind = QSB_D_SWEEP; d->gate = gate; d->k = nb; d->flags = 0;
     d->b[0] = b0; d->b[1] = b1; d->b[2] = b2;
     d->cls[0] = qsb_cls_of(w, b0); d->cls[1] = nb > 1 ? qsb_cls_of(w, b1) : 0; d->cls[2] = nb > 2 ? qsb_cls_of(w, b2) : 0;
+    // flags: which bits carry a full 2x2 -- the workers pick the sweep variant from the descriptor's first 16 bytes
+    d->kind = QSB_D_SWEEP; d->gate = gate; d->k = nb;
+    d->flags = (d->cls[0] >= QSB_CLS_DIAG ? 1 : 0) | (d->cls[1] >= QSB_CLS_DIAG ? 2 : 0) | (d->cls[2] >= QSB_CLS_DIAG ? 4 : 0);
     d->pos = pos;
     d->hmask = hm;
+  }
+  {
+    const int nbits = env.wbits < m - nb ? env.wbits : m - nb;
+    for (int e = env.clane; e < 32; e += env.CL) {
+      d->tabl[e] = qsb_deposit(e, pos, nbits < 5 ? nbits : 5);
+      if (e < 8) d->tabw[e] = qsb_deposit(e << 5, pos, nbits);        // bits 0..4 of e << 5 are clear
+    }
   }
   if (mat_src) {
     const int cnt = 1 << (2 * nb);

@@ -41,12 +41,13 @@ __global__ void __launch_bounds__(256, 1) k(int sweeps, int mode, int ndense, in
       rng = rng * 1664525u + 1013904223u;
       int b1 = mode ? (rng >> 8) % 13 : 6 + (rng >> 8) % 7;
       if (b1 == b0) b1 = mode ? (b0 + 1) % 13 : 6 + (b0 - 6 + 1) % 7;
-      d->kind = QSB_D_SWEEP; d->gate = gate; d->k = 2; d->flags = 0;
+      d->kind = QSB_D_SWEEP; d->gate = gate; d->k = 2; d->flags = (ndense > 0 ? 1 : 0) | (ndense > 1 ? 2 : 0);
       d->b[0] = b0; d->b[1] = b1; d->b[2] = 0;
       d->cls[0] = ndense > 0 ? QSB_CLS_DENSE : QSB_CLS_NONE; d->cls[1] = ndense > 1 ? QSB_CLS_DENSE : QSB_CLS_NONE; d->cls[2] = 0;
       int hm;
       d->pos = qsb_group_order(m, (1u << b0) | (1u << b1), 8, m - 2, 3, &hm);
       d->hmask = hm;
+      for (int e = 0; e < 32; ++e) { d->tabl[e] = qsb_deposit(e, d->pos, 5); if (e < 8) d->tabw[e] = qsb_deposit(e << 5, d->pos, 8); }
       for (int kk = 0; kk < 2; ++kk) { d->P[kk][0] = qsb_c(0.8, 0); d->P[kk][1] = qsb_c(0, -0.6); d->P[kk][2] = qsb_c(0, -0.6); d->P[kk][3] = qsb_c(0.8, 0); }
       uint64_t w = qsb_cls_set(qsb_cls_set(0, b0, d->cls[0]), b1, d->cls[1]);
       qsb_sweep_tables(env, d, w, gate, 2, b0, b1, 0);
