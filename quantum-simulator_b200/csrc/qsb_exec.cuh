@@ -557,12 +557,15 @@ QSB_PASS void qsb_sweep_s(Env& env, int m, const qsb_desc* d) {
   }
 }
 
+// first 16 bytes of a descriptor, read with one load
+struct alignas(16) qsb_desc_hdr { int32_t kind, gate, k, flags; };
+
 template <class Env>
-QSB_HD void qsb_do_sweep(Env& env, int m, const qsb_desc* d) {
-  const bool dg = d->gate == QSB_G_DENSE;
+QSB_HD void qsb_do_sweep(Env& env, int m, const qsb_desc* d, const qsb_desc_hdr& h) {
+  const bool dg = h.gate == QSB_G_DENSE;
 #if QSB_GROUP_POS
   if (!dg) {
-    switch (d->k * 8 + d->flags) {          // flags = dense mask (qsb_emit_sweep)
+    switch (h.k * 8 + h.flags) {            // flags = dense mask (qsb_emit_sweep)
       case 8: qsb_sweep_s<1, 0>(env, m, d); break;
       case 9: qsb_sweep_s<1, 1>(env, m, d); break;
       case 16: qsb_sweep_s<2, 0>(env, m, d); break;
@@ -582,9 +585,9 @@ QSB_HD void qsb_do_sweep(Env& env, int m, const qsb_desc* d) {
     return;
   }
 #endif
-  if (d->k == 1) qsb_sweep<1, false>(env, m, d);
-  else if (d->k == 2) { if (dg) qsb_sweep<2, true>(env, m, d); else qsb_sweep<2, false>(env, m, d); }
-  else if (d->k == 3) { if (dg) qsb_sweep<3, true>(env, m, d); else qsb_sweep<3, false>(env, m, d); }
+  if (h.k == 1) qsb_sweep<1, false>(env, m, d);
+  else if (h.k == 2) { if (dg) qsb_sweep<2, true>(env, m, d); else qsb_sweep<2, false>(env, m, d); }
+  else if (h.k == 3) { if (dg) qsb_sweep<3, true>(env, m, d); else qsb_sweep<3, false>(env, m, d); }
 }
 
 // sum v[0..nv) over the workers of this CTA; every worker gets the bit-identical result
@@ -992,18 +995,18 @@ QSB_HD void qsb_worker_loop(Env& env, const qsb_exec_args& a) {
   const bool wprof = Env::PROF && a.prof != nullptr && env.lane == 0;      // per-warp busy / wait cycles
   unsigned long long wb = 0, ww = 0, w0 = 0, w1 = 0;
   unsigned long long pw = 0, pb[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pn[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t0 = 0, t1 = 0;
-  for (uint32_t seq = 0;; ++seq) {
-    const int slot = (int)(seq % QSB_RING);
+  for (int slot = 0;; slot = slot + 1 == QSB_RING ? 0 : slot + 1) {
     if (prof) t0 = env.clock();
     if (wprof) w0 = env.clock();
     env.ring_wait_full(slot);               // also: every worker finished the previous descriptor
     if (wprof) { w1 = env.clock(); ww += w1 - w0; }
     if (prof) { t1 = env.clock(); pw += t1 - t0; }
     const qsb_desc* d = &env.ctl()->ring[slot];
-    const int kind = d->kind;
+    const qsb_desc_hdr hdr = *reinterpret_cast<const qsb_desc_hdr*>(d);      // kind, gate, k, flags: one 16-byte load
+    const int kind = hdr.kind;
     switch (kind) {
       case QSB_D_INIT: qsb_do_init(env, a, d); break;
-      case QSB_D_SWEEP: qsb_do_sweep(env, m, d); break;
+      case QSB_D_SWEEP: qsb_do_sweep(env, m, d, hdr); break;
       case QSB_D_REMAP: qsb_do_remap(env, m, d); break;
       case QSB_D_GFLUSH: qsb_do_gflush(env, m, d); break;
       case QSB_D_RDM1: {

@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(256, 1) k(int sweeps, int mode, int ndense, in
       qsb_sweep_tables(env, d, w, gate, 2, b0, b1, 0);
     }
     __syncthreads();
-    qsb_do_sweep(env, m, d);
+    qsb_do_sweep(env, m, d, *reinterpret_cast<const qsb_desc_hdr*>(d));
   }
   __syncthreads();
   if (threadIdx.x == 0) cyc[blockIdx.x] = clock64() - t0;
