@@ -42,8 +42,8 @@ def algorithmic_bytes_per_trajectory(n, gates, k_pauli, k_ad):
 
 
 # DRAM bytes one trajectory really moves (ncu dram__bytes_read.sum + dram__bytes_write.sum of the trajectory
-# kernel divided by its trajectories: profiles/r02b_traj_kernel_ncu_full_traj480.csv, 465.8 MB / 480)
-MEASURED_DRAM_BYTES_PER_TRAJECTORY = (10761984 + 455046400) / 480
+# kernel divided by its trajectories: profiles/r02c_traj_kernel_ncu_full_traj480.csv, 469.9 MB / 480)
+MEASURED_DRAM_BYTES_PER_TRAJECTORY = (13242880 + 456623104) / 480
 
 
 def measured_peak():
@@ -465,7 +465,7 @@ def run_ours(args):
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "algorithmic_bytes_per_launch": alg_bytes * T, "peak_source": peak_src,
                          "traffic": MEASURED_DRAM_BYTES_PER_TRAJECTORY * T,
-                         "traffic_source": "ncu dram bytes per trajectory (profiles/r02b_traj_kernel_ncu_full_traj480.csv) x "
+                         "traffic_source": "ncu dram bytes per trajectory (profiles/r02c_traj_kernel_ncu_full_traj480.csv) x "
                                            "trajectories per launch",
                          "note": "every trajectory lives in the shared memory of an 8-CTA cluster from |0> to its final "
                                  "store: HBM sees ~1 MiB per trajectory, so the HBM fraction of the algorithmic bytes is far "
