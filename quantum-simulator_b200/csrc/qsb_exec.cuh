@@ -493,8 +493,23 @@ QSB_PASS void qsb_sweep(Env& env, int m, const qsb_desc* d) {
 // the loop (qsb_sweep above) ptxas cannot move a group's arithmetic under the loads and stores of its neighbours and
 // the workers of a CTA, which enter a sweep together, alternate between the shared-memory pipe and the FP64 pipe:
 // tools/micro/sweep_real.cu, one dense pending matrix: 3 720 -> 2 620 cycles per sweep.
+// what every specialised sweep reads from its descriptor before the first tile load; fetched by the worker loop TOGETHER
+// with the descriptor header, so the loads are in flight while the kind / variant jumps resolve
+struct qsb_sweep_pro {
+  int lo_base, hmask;
+  int off[8], ost[8];
+  double f[8];
+};
+template <class Env>
+QSB_HD void qsb_sweep_prologue(Env& env, const qsb_desc* d, qsb_sweep_pro& p) {
+  p.lo_base = d->tabl[env.wid & 31] | d->tabw[env.wid >> 5];
+  p.hmask = d->hmask;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) { p.off[r] = d->off[r]; p.ost[r] = d->ost[r]; p.f[r] = d->f[r]; }
+}
+
 template <int K, int DM, class Env>
-QSB_PASS void qsb_sweep_s(Env& env, int m, const qsb_desc* d) {
+QSB_PASS void qsb_sweep_s(Env& env, int m, const qsb_desc* d, const qsb_sweep_pro& pro) {
   typedef typename Env::amp A;
   typedef typename qsb_amp<A>::real R;
   A* tile = env.tile();
@@ -503,13 +518,13 @@ QSB_PASS void qsb_sweep_s(Env& env, int m, const qsb_desc* d) {
   constexpr int ND = (DM & 1) + ((DM >> 1) & 1) + ((DM >> 2) & 1);
   constexpr int DIDX = ((DM & 1) ? (1 << (K - 1)) : 0) | ((K > 1 && (DM & 2)) ? (1 << (K - 2)) : 0) | ((K > 2 && (DM & 4)) ? 1 : 0);   // local-index bits with a full 2x2
   constexpr int NG = (K == 3 && ND >= 2) ? 1 : (QSB_AMPS / D > 0 ? QSB_AMPS / D : 1);   // 16 amplitudes + 3 matrices would spill
-  const int lo_base = d->tabl[env.wid & 31] | d->tabw[env.wid >> 5];
-  const int hmask = d->hmask;
+  const int lo_base = pro.lo_base;
+  const int hmask = pro.hmask;
   int hi = 0;
   int off[D], ost[D];               // swizzled offsets: where local index r is loaded from / stored to
   R f[D];                           // real factor of local index r (scales of the non-dense bits, sign of CZ)
 #pragma unroll
-  for (int r = 0; r < D; ++r) { off[r] = d->off[r]; ost[r] = d->ost[r]; f[r] = (R)d->f[r]; }
+  for (int r = 0; r < D; ++r) { off[r] = pro.off[r]; ost[r] = pro.ost[r]; f[r] = (R)pro.f[r]; }
   A P[K][4];
 #pragma unroll
   for (int k = 0; k < K; ++k) {
@@ -561,25 +576,25 @@ QSB_PASS void qsb_sweep_s(Env& env, int m, const qsb_desc* d) {
 struct alignas(16) qsb_desc_hdr { int32_t kind, gate, k, flags; };
 
 template <class Env>
-QSB_HD void qsb_do_sweep(Env& env, int m, const qsb_desc* d, const qsb_desc_hdr& h) {
+QSB_HD void qsb_do_sweep(Env& env, int m, const qsb_desc* d, const qsb_desc_hdr& h, const qsb_sweep_pro& pro) {
   const bool dg = h.gate == QSB_G_DENSE;
 #if QSB_GROUP_POS
   if (!dg) {
     switch (h.k * 8 + h.flags) {            // flags = dense mask (qsb_emit_sweep)
-      case 8: qsb_sweep_s<1, 0>(env, m, d); break;
-      case 9: qsb_sweep_s<1, 1>(env, m, d); break;
-      case 16: qsb_sweep_s<2, 0>(env, m, d); break;
-      case 17: qsb_sweep_s<2, 1>(env, m, d); break;
-      case 18: qsb_sweep_s<2, 2>(env, m, d); break;
-      case 19: qsb_sweep_s<2, 3>(env, m, d); break;
-      case 24: qsb_sweep_s<3, 0>(env, m, d); break;
-      case 25: qsb_sweep_s<3, 1>(env, m, d); break;
-      case 26: qsb_sweep_s<3, 2>(env, m, d); break;
-      case 27: qsb_sweep_s<3, 3>(env, m, d); break;
-      case 28: qsb_sweep_s<3, 4>(env, m, d); break;
-      case 29: qsb_sweep_s<3, 5>(env, m, d); break;
-      case 30: qsb_sweep_s<3, 6>(env, m, d); break;
-      case 31: qsb_sweep_s<3, 7>(env, m, d); break;
+      case 8: qsb_sweep_s<1, 0>(env, m, d, pro); break;
+      case 9: qsb_sweep_s<1, 1>(env, m, d, pro); break;
+      case 16: qsb_sweep_s<2, 0>(env, m, d, pro); break;
+      case 17: qsb_sweep_s<2, 1>(env, m, d, pro); break;
+      case 18: qsb_sweep_s<2, 2>(env, m, d, pro); break;
+      case 19: qsb_sweep_s<2, 3>(env, m, d, pro); break;
+      case 24: qsb_sweep_s<3, 0>(env, m, d, pro); break;
+      case 25: qsb_sweep_s<3, 1>(env, m, d, pro); break;
+      case 26: qsb_sweep_s<3, 2>(env, m, d, pro); break;
+      case 27: qsb_sweep_s<3, 3>(env, m, d, pro); break;
+      case 28: qsb_sweep_s<3, 4>(env, m, d, pro); break;
+      case 29: qsb_sweep_s<3, 5>(env, m, d, pro); break;
+      case 30: qsb_sweep_s<3, 6>(env, m, d, pro); break;
+      case 31: qsb_sweep_s<3, 7>(env, m, d, pro); break;
       default: break;
     }
     return;
@@ -1003,10 +1018,12 @@ QSB_HD void qsb_worker_loop(Env& env, const qsb_exec_args& a) {
     if (prof) { t1 = env.clock(); pw += t1 - t0; }
     const qsb_desc* d = &env.ctl()->ring[slot];
     const qsb_desc_hdr hdr = *reinterpret_cast<const qsb_desc_hdr*>(d);      // kind, gate, k, flags: one 16-byte load
+    qsb_sweep_pro pro;
+    qsb_sweep_prologue(env, d, pro);          // only sweeps use it; for the other kinds these are loads of unused fields
     const int kind = hdr.kind;
     switch (kind) {
       case QSB_D_INIT: qsb_do_init(env, a, d); break;
-      case QSB_D_SWEEP: qsb_do_sweep(env, m, d, hdr); break;
+      case QSB_D_SWEEP: qsb_do_sweep(env, m, d, hdr, pro); break;
       case QSB_D_REMAP: qsb_do_remap(env, m, d); break;
       case QSB_D_GFLUSH: qsb_do_gflush(env, m, d); break;
       case QSB_D_RDM1: {

@@ -53,7 +53,9 @@ __global__ void __launch_bounds__(256, 1) k(int sweeps, int mode, int ndense, in
       qsb_sweep_tables(env, d, w, gate, 2, b0, b1, 0);
     }
     __syncthreads();
-    qsb_do_sweep(env, m, d, *reinterpret_cast<const qsb_desc_hdr*>(d));
+    qsb_sweep_pro pro;
+    qsb_sweep_prologue(env, d, pro);
+    qsb_do_sweep(env, m, d, *reinterpret_cast<const qsb_desc_hdr*>(d), pro);
   }
   __syncthreads();
   if (threadIdx.x == 0) cyc[blockIdx.x] = clock64() - t0;
