@@ -156,13 +156,30 @@ class Simulator:
 
     def run_step_by_step(self, circuit: QuantumCircuit,
                          rng: np.random.Generator | None = None) -> Generator:
-        """Yields (state, index) after each non-empty column, starting with (initial, -1).
+        """Yields (state, column_index) after each column, starting with (initial, -1)  (simulator.py:93-108).
 
-        Evaluation is EAGER where the reference is lazy (simulator.py:93-108): the whole circuit runs as one launch
-        on the first `next()` after the initial state, so all of the noise model's draws are taken from
-        `NoiseModel._rng` at that moment (a caller that interleaves its own draws from that generator between
-        columns sees a different stream), and an unknown gate name in a late column raises before the earlier
-        columns are yielded.  The yielded states and indices are the reference's."""
+        Lazy like the reference: a column is applied when the caller asks for it, gate by gate through
+        `_apply_gate_instance` + `NoiseModel.apply` (one launch each on the device-resident state), so the noise
+        model's draws are taken from `NoiseModel._rng` column by column, and an unknown gate name in a late column
+        raises only when that column is reached, after the earlier columns were yielded.  Complex64 and Philox
+        simulators keep the one-launch form (`_steps_one_launch`): those modes have no reference stream to follow."""
+        if self._precision != "c128" or self._rng_mode != "reference":
+            yield from self._steps_one_launch(circuit)
+            return
+        state = StateVector.from_initial_states(circuit.initial_states)
+        yield state.copy(), -1
+        for col_idx, column_gates in enumerate(circuit.get_ordered_gates()):
+            for gate_inst in column_gates:
+                gate_def = self._gate_registry.get(gate_inst.gate_name)
+                if gate_def.gate_type in (GateType.MEASUREMENT, GateType.BARRIER):
+                    continue
+                self._apply_gate_instance(state, gate_inst)
+                if self._noise_model is not None:
+                    self._noise_model.apply(state, gate_inst)
+            yield state.copy(), col_idx
+
+    def _steps_one_launch(self, circuit: QuantumCircuit) -> Generator:
+        """All columns in one launch with a snapshot per column (eager: every draw is taken up front)."""
         yield StateVector.from_initial_states(circuit.initial_states), -1
         n = circuit.num_qubits
         dp, _ = self._program(circuit, record_steps=True)

@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 
 from conftest import as_gates, as_noise
+from oracle import qsim_oracle as O
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-12
@@ -100,6 +101,38 @@ def test_random_circuits_run_and_steps(E, golden):
     seq = list(E.Simulator().run_step_by_step(qc))
     assert seq[0][1] == -1 and [i for _, i in seq[1:]] == list(range(len(seq) - 1))
     assert np.max(np.abs(np.array([s.data for s, _ in seq[1:]]) - a[rec["tag"] + "_steps"])) < TOL
+
+
+def test_run_step_by_step_is_lazy_like_the_reference(E, golden):
+    """simulator.py:93-108 is a generator over columns: the noise model's draws are taken column by column, and an
+    unknown gate in a late column raises only once that column is reached."""
+    j, a = golden
+    rec = next(r for r in j["noisy"] if len({g[3] for g in r["gates"]}) >= 3)
+    n, gates, noise = rec["n"], as_gates(rec["gates"]), as_noise(rec["noise"])
+    qc = circuit_of(E, n, gates)
+    nm = model_of(E, noise, seed=rec["noise_seed"])
+    it = E.Simulator(nm).run_step_by_step(qc)
+    s0, i0 = next(it)
+    assert i0 == -1 and abs(s0.data[0] - 1.0) < TOL
+    ref_rng = np.random.default_rng(rec["noise_seed"])
+    assert nm._rng.bit_generator.state == ref_rng.bit_generator.state           # nothing drawn yet
+    s1, i1 = next(it)
+    first_col = min(g[3] for g in gates)
+    ref_rng.random(O.draw_count(n, [g for g in gates if g[3] == first_col], noise))
+    assert i1 == 0 and nm._rng.bit_generator.state == ref_rng.bit_generator.state   # ... only the first column's draws
+    last = s1
+    for st, _ in it:
+        last = st
+    assert np.max(np.abs(last.data - a[rec["tag"]])) < TOL
+    # a gate name the registry does not know, in the last column
+    qc2 = circuit_of(E, n, gates)
+    qc2.add_gate(E.GateInstance("NoSuchGate", [0], [], max(g[3] for g in gates) + 1))
+    it2 = E.Simulator().run_step_by_step(qc2)
+    seen = 0
+    with pytest.raises(KeyError):
+        for _ in it2:
+            seen += 1
+    assert seen == 1 + len({g[3] for g in gates})                                # the initial state and every good column
 
 
 def test_per_gate_api_matches_batched_run(E, golden):
