@@ -1249,8 +1249,14 @@ int qsb_stream_create(qsb_ctx* ctx, int32_t n, int32_t m, int32_t l, int32_t e, 
       uint32_t used = 0;
       for (int j = 0; j < 4; ++j) used |= 1u << descs[i].b[j];
       int hm = 0;
-      descs[i].pos = qsb_group_order(m, used, pass == 0 ? 8 : 7, m - 4, 3, &hm);
+      const int wb = pass == 0 ? 8 : 7;
+      descs[i].pos = qsb_group_order(m, used, wb, m - 4, 3, &hm);
       descs[i].hmask = hm;
+      const int nbits = wb < m - 4 ? wb : m - 4;
+      for (int e = 0; e < 32; ++e) descs[i].tabl[e] = qsb_deposit(e, descs[i].pos, nbits < 5 ? nbits : 5);
+      for (int e = 0; e < 8; ++e) descs[i].tabw[e] = qsb_deposit(e << 5, descs[i].pos, nbits);
+      descs[i].variant = (descs[i].cls[0] != QSB_CLS_NONE ? 1 : 0) | (descs[i].cls[1] != QSB_CLS_NONE ? 2 : 0) |
+                         (descs[i].cls[2] != QSB_CLS_NONE ? 4 : 0) | (descs[i].cls[3] != QSB_CLS_NONE ? 8 : 0);
       descs[i].mat = mat_at[i] >= 0 ? s->d_mats + mat_at[i] : nullptr;
     }
     er = cudaMemcpyAsync(s->d_sweeps + pass * nb, descs.data(), nb * sizeof(qsb_blk), cudaMemcpyHostToDevice, ctx->stream);

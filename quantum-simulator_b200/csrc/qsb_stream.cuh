@@ -123,7 +123,9 @@ struct alignas(16) qsb_blk {
   const c128* mat;           // dense matrix in device memory
   int32_t dense;             // 0 | 2 | 3
   int32_t b[4];
-  int32_t pad;
+  int32_t variant;           // dense == 0: mask of the local bits with a 2x2 (picks qsb_block_sweep_s<MASK>)
+  int32_t tabl[32];          // first register block of worker w: tabl[w & 31] | tabw[w >> 5] (qsb_deposit of w onto `pos`, per worker count)
+  int32_t tabw[8];
 };
 
 // 2x2 on local bit T of the register block
@@ -228,6 +230,83 @@ __device__ __forceinline__ void qsb_block_sweep(StreamEnv& env, int m, const qsb
       *reinterpret_cast<c128*>(tile + (sbs ^ o.z)) = a[4 * q + 2];
       *reinterpret_cast<c128*>(tile + (sbs ^ o.w)) = a[4 * q + 3];
     }
+  }
+}
+
+// The same round trip for blocks without a dense 4x4 / 8x8, with the run-time choices taken out of the loop: MASK (compile
+// time) says which local bits carry a 2x2 (whatever its class: a real or complex diagonal is applied as a full matrix),
+// the signs of CZ are XORed into the sign bits.  With the class branches inside the loop ptxas cannot move a step's
+// arithmetic under its loads and stores (the same finding as in the resident executor, tools/micro/sweep_real.cu).
+template <int MASK>
+__device__ __forceinline__ void qsb_block_sweep_s(StreamEnv& env, int m, const qsb_blk* d) {
+  unsigned char* tile = reinterpret_cast<unsigned char*>(env.tile());
+  const int free_bits = m - 4;
+  const int lo_base = d->tabl[env.wid & 31] | d->tabw[env.wid >> 5];
+  const int hmask = d->hmask;
+  const uint32_t neg = d->neg_mask;
+  const uint4* ldo = reinterpret_cast<const uint4*>(d->ld_off);
+  const uint4* sto = reinterpret_cast<const uint4*>(d->st_off);
+  int hi = 0;
+  for (int g0 = env.wid; g0 < (1 << free_bits); g0 += env.W) {
+    const int bs = lo_base | hi;
+    hi = ((hi | ~hmask) + 1) & hmask;
+    const uint32_t sbs = (uint32_t)qsb_slot(bs) << 4;
+    c128 a[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 o = ldo[q];
+      a[4 * q + 0] = *reinterpret_cast<const c128*>(tile + (sbs ^ o.x));
+      a[4 * q + 1] = *reinterpret_cast<const c128*>(tile + (sbs ^ o.y));
+      a[4 * q + 2] = *reinterpret_cast<const c128*>(tile + (sbs ^ o.z));
+      a[4 * q + 3] = *reinterpret_cast<const c128*>(tile + (sbs ^ o.w));
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      if (!((MASK >> t) & 1)) continue;
+      const c128 u0 = d->U[t][0], u1 = d->U[t][1], u2 = d->U[t][2], u3 = d->U[t][3];
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        if ((r >> t) & 1) continue;
+        const c128 lo = a[r], up = a[r | (1 << t)];
+        a[r] = qsb_fma(u1, up, qsb_mul(u0, lo));
+        a[r | (1 << t)] = qsb_fma(u3, up, qsb_mul(u2, lo));
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {                     // sign gates: flip the sign bits (integer pipe, no branch)
+      const long long flip = (long long)((neg >> r) & 1u) << 63;
+      a[r].x = __longlong_as_double(__double_as_longlong(a[r].x) ^ flip);
+      a[r].y = __longlong_as_double(__double_as_longlong(a[r].y) ^ flip);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 o = sto[q];
+      *reinterpret_cast<c128*>(tile + (sbs ^ o.x)) = a[4 * q + 0];
+      *reinterpret_cast<c128*>(tile + (sbs ^ o.y)) = a[4 * q + 1];
+      *reinterpret_cast<c128*>(tile + (sbs ^ o.z)) = a[4 * q + 2];
+      *reinterpret_cast<c128*>(tile + (sbs ^ o.w)) = a[4 * q + 3];
+    }
+  }
+}
+__device__ __forceinline__ void qsb_block_dispatch(StreamEnv& env, int m, const qsb_blk* d) {
+  if (d->dense != 0) { qsb_block_sweep(env, m, d); return; }
+  switch (d->variant) {
+    case 0: qsb_block_sweep_s<0>(env, m, d); break;
+    case 1: qsb_block_sweep_s<1>(env, m, d); break;
+    case 2: qsb_block_sweep_s<2>(env, m, d); break;
+    case 3: qsb_block_sweep_s<3>(env, m, d); break;
+    case 4: qsb_block_sweep_s<4>(env, m, d); break;
+    case 5: qsb_block_sweep_s<5>(env, m, d); break;
+    case 6: qsb_block_sweep_s<6>(env, m, d); break;
+    case 7: qsb_block_sweep_s<7>(env, m, d); break;
+    case 8: qsb_block_sweep_s<8>(env, m, d); break;
+    case 9: qsb_block_sweep_s<9>(env, m, d); break;
+    case 10: qsb_block_sweep_s<10>(env, m, d); break;
+    case 11: qsb_block_sweep_s<11>(env, m, d); break;
+    case 12: qsb_block_sweep_s<12>(env, m, d); break;
+    case 13: qsb_block_sweep_s<13>(env, m, d); break;
+    case 14: qsb_block_sweep_s<14>(env, m, d); break;
+    default: qsb_block_sweep_s<15>(env, m, d); break;
   }
 }
 
@@ -336,7 +415,7 @@ qsb_stream_kernel(const __grid_constant__ qsb_stream_maps maps, const __grid_con
       qsb_st_mbar_wait(qsb_st_smem_u32(&bars[QSB_ST_BUFS + b]), (uint32_t)(((j - QSB_ST_BUFS) / QSB_ST_BUFS) & 1));
     qsb_st_mbar_wait(qsb_st_smem_u32(&bars[b]), (uint32_t)((j / QSB_ST_BUFS) & 1));                 // tile j has landed
     for (int s = 0; s < a.n_sweeps; ++s) {
-      qsb_block_sweep(env, a.m, &descs[s]);
+      qsb_block_dispatch(env, a.m, &descs[s]);
       if (s + 1 < a.n_sweeps) asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(GT) : "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy writes -> visible to the TMA store
