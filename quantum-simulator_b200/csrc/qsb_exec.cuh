@@ -599,10 +599,15 @@ QSB_HD void qsb_do_sweep(Env& env, int m, const qsb_desc* d, const qsb_desc_hdr&
     }
     return;
   }
-#endif
+  // dense 4x4 / 8x8 gates: the generic sweep (run-time pending-matrix classes)
+  if (h.k == 2) qsb_sweep<2, true>(env, m, d);
+  else if (h.k == 3) qsb_sweep<3, true>(env, m, d);
+#else
+  (void)pro;
   if (h.k == 1) qsb_sweep<1, false>(env, m, d);
   else if (h.k == 2) { if (dg) qsb_sweep<2, true>(env, m, d); else qsb_sweep<2, false>(env, m, d); }
   else if (h.k == 3) { if (dg) qsb_sweep<3, true>(env, m, d); else qsb_sweep<3, false>(env, m, d); }
+#endif
 }
 
 // sum v[0..nv) over the workers of this CTA; every worker gets the bit-identical result
