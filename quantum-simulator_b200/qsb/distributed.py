@@ -94,11 +94,28 @@ def gather_concat(array: np.ndarray, device=None):
     return np.concatenate([o[: int(sizes[r].item())].cpu().numpy() for r, o in enumerate(out)])
 
 
+_BYTE_DIGITS = (((np.arange(256)[:, None] >> np.arange(7, -1, -1)) & 1) + 48).astype(np.uint8)     # byte -> its 8 ASCII binary digits
+
+
 def merge_counts_in_shot_order(indices: np.ndarray, n: int) -> dict:
     """{bitstring: count} with keys inserted in order of first occurrence, as the reference's per-shot
-    loop builds them (simulator.py:144-145)."""
-    out: dict = {}
-    for i in indices.tolist():
-        key = format(i, f"0{n}b")
-        out[key] = out.get(key, 0) + 1
-    return out
+    loop builds them (simulator.py:144-145).  Vectorised (the per-shot Python loop costs 12 ms for the 16 k shots of
+    an 8-GPU step, a tenth of the step): distinct outcomes with their first positions and counts, one sort of the
+    distinct outcomes by first position, keys written as ASCII digits through a byte table."""
+    idx = np.asarray(indices, dtype=np.int64).reshape(-1)
+    if idx.size == 0:
+        return {}
+    if (1 << n) <= 8 * idx.size:                  # direct tables over the 2^n outcomes: no sort of the shots
+        cnt_all = np.bincount(idx, minlength=1 << n)
+        first_all = np.empty(1 << n, dtype=np.int64)
+        first_all[idx[::-1]] = np.arange(idx.size - 1, -1, -1, dtype=np.int64)     # the earliest shot is written last
+        vals = np.flatnonzero(cnt_all)
+        first, cnt = first_all[vals], cnt_all[vals]
+    else:
+        vals, first, cnt = np.unique(idx, return_index=True, return_counts=True)
+    order = np.argsort(first, kind="stable")
+    vals, cnt = vals[order], cnt[order]
+    nbytes = (n + 7) // 8
+    digits = np.concatenate([_BYTE_DIGITS[(vals >> (8 * (nbytes - 1 - j))) & 255] for j in range(nbytes)], axis=1)[:, 8 * nbytes - n:]
+    text = np.ascontiguousarray(digits).tobytes().decode("ascii")
+    return dict(zip([text[i:i + n] for i in range(0, len(text), n)], cnt.tolist()))

@@ -219,10 +219,8 @@ class Simulator:
             rng = np.random.default_rng(seed)
         n = circuit.num_qubits
         idx = self._noisy_indices(circuit, shots, self._noise_model._rng, rng)
-        counts: dict = {}
-        for i in idx.tolist():
-            key = format(i, f"0{n}b")
-            counts[key] = counts.get(key, 0) + 1
+        from qsb.distributed import merge_counts_in_shot_order
+        counts = merge_counts_in_shot_order(idx, n)            # keys in order of first occurrence (simulator.py:144-145)
         final_state = StateVector.from_initial_states(circuit.initial_states)   # placeholder, as in the reference
         return SimulationResult(final_state=final_state, measurement_counts=counts, num_shots=shots, seed=seed)
 
