@@ -88,3 +88,19 @@ def test_philox_threshold_sweep_agrees_with_the_reference_stream_sweep_statistic
         assert abs(x.logical_rate - z.logical_rate) < 0.1 and abs(x.avg_fidelity - z.avg_fidelity) < 0.1
         assert abs(x.decoder_success_rate - z.decoder_success_rate) < 0.1
     assert a[0].logical_rate < a[1].logical_rate < a[2].logical_rate
+
+
+def test_lean_batches_return_the_same_scalars():
+    """`run_cycles(..., lean=True)` (the throughput sweep's mode: no per-trial Python lists) gives the same fidelity /
+    <Z_L> / logical-error arrays as the full form, for every built-in code."""
+    from quantum_sim.engine import qec as Q
+    rng = np.random.default_rng(3)
+    for code in (Q.BitFlipCode(), Q.PhaseFlipCode(), Q.SteaneCode()):
+        sim = Q.QECSimulator(code)
+        u = rng.random((300, code.data_qubits))
+        lg = rng.integers(0, 2, 300)
+        full = sim.run_cycles(lg.tolist(), "depolarizing", 0.15, None, uniforms=u)
+        lean = sim.run_cycles(lg, "depolarizing", 0.15, None, uniforms=u, lean=True)
+        for key in ("fidelity_before", "fidelity_after", "z_exp", "logical_error"):
+            assert np.array_equal(np.asarray(full[key]), np.asarray(lean[key])), (type(code).__name__, key)
+        assert lean["corrections"] is None and len(full["corrections"]) == 300
