@@ -342,3 +342,40 @@ def test_multi_pair_remaps(run, gbits):
         psi, _, br, _ = O.run_state(n, gates, None, noise, draws[t])
         assert out["branches"][t][:len(br)].tolist() == br
         assert np.max(np.abs(out["states"][t] - psi)) < TOL
+
+
+# ---- every specialised sweep variant: (gate, class of the pending matrix of each of its bits) ---------------------
+@pytest.mark.parametrize("gate,k", [("CNOT", 2), ("CZ", 2), ("SWAP", 2), ("Toffoli", 3), ("Fredkin", 3)])
+@pytest.mark.parametrize("gbits", [0, 2])
+def test_every_dense_mask_and_gate_of_the_specialised_sweeps(run, gate, k, gbits):
+    """csrc/qsb_exec.cuh instantiates the sweep per mask of bits that carry a full 2x2; the other bits carry a real scale
+    (a damping K0) or nothing, and permutation gates only move the store.  All 3^k class combinations of every gate:
+    nothing pending / K0 pending (identity gate with certain-K0 amplitude damping) / Ry pending, on an entangled state."""
+    import itertools
+    n = 7
+    targets = [5, 1, 3][:k]
+    noise = {"global": [], "gate": {"I": [("amplitude_damping", 0.2)]}}
+    for classes in itertools.product((0, 1, 2), repeat=k):
+        gates, col = [], 0
+        for q in range(n):
+            gates.append(("Ry", [q], [0.3 + 0.2 * q], col))
+        col += 1
+        for q in range(0, n - 1, 2):
+            gates.append(("CNOT", [q, q + 1], [], col))
+        col += 1
+        for q in range(1, n - 1, 2):
+            gates.append(("CZ", [q, q + 1], [], col))
+        gates.append(("CNOT", [0, n - 1], [], col + 1))          # every qubit met a 2-qubit gate: nothing is pending
+        col += 2
+        for q, c in zip(targets, classes):
+            if c == 1:
+                gates.append(("I", [q], [], col))
+            elif c == 2:
+                gates.append(("Ry", [q], [0.9 - 0.1 * q], col))
+        gates.append((gate, targets, [], col + 1))
+        qc = make_circuit(n, gates)
+        prog, _ = lower_circuit(n, qc.get_ordered_gates(), REG, channels_of_factory(noise), local_bits=n - gbits)
+        draws = np.full((1, max(prog.n_draws, 1)), 0.5)           # below 1 - gamma: K0 whatever the state
+        out = run(prog, count=1, T=2, uniforms=draws)
+        psi, _, _, _ = O.run_state(n, gates, None, noise, draws[0])
+        assert np.max(np.abs(out["states"][0] - psi)) < TOL, (gate, classes)
