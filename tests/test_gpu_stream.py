@@ -226,3 +226,39 @@ def test_argument_checks():
     with pytest.raises(ValueError):
         ctx.stream_pass(S.StreamPass(18, 12, 4, 3, list(range(18)), list(range(18)), [],
                                      blocks=[S.Block([3, 4, 5, 6], [])] * (S.MAX_SWEEPS + 1)), np.zeros(2))
+
+
+def test_every_matrix_mask_of_the_block_sweep():
+    """csrc/qsb_stream.cuh instantiates the block sweep per mask of local bits that carry a 2x2 (16 variants); classes
+    (real diagonal, complex diagonal, dense) are all applied as full matrices, signs by XOR.  One hand-made block per
+    mask -- its matrices, then CX and CZ -- against NumPy."""
+    from qsb import capi
+    from test_stream_plan import block_op_matrix
+    L, m, l, e = 17, 12, 5, 3
+    rng = np.random.default_rng(11)
+    psi = rng.normal(size=2 ** L) + 1j * rng.normal(size=2 ** L)
+    psi /= np.linalg.norm(psi)
+    ctx = capi.get_context()
+
+    def matrix(kind):
+        if kind == 0:                                             # dense unitary
+            return np.linalg.qr(rng.normal(size=(2, 2)) + 1j * rng.normal(size=(2, 2)))[0]
+        if kind == 1:                                             # complex diagonal (Rz-like)
+            th = rng.uniform(-3, 3)
+            return np.diag([np.exp(-0.5j * th), np.exp(0.5j * th)])
+        return np.diag([1.0, rng.uniform(0.5, 1.0)]).astype(np.complex128)   # real diagonal (a damping K0)
+
+    for mask in range(16):
+        bits = [int(x) for x in rng.permutation(m)[:4]]
+        ops = [S.BlockOp(S.B_MAT1, [t], matrix((mask + t) % 3)) for t in range(4) if (mask >> t) & 1]
+        ops += [S.BlockOp(S.B_CX, [3, 0]), S.BlockOp(S.B_CZ, [1, 2])]
+        blk = S.Block(bits, ops)
+        sp = S.StreamPass(L, m, l, e, list(range(L)), list(range(L)), [], blocks=[blk])
+        buf = ctx.to_device(psi)
+        ctx.stream_pass(sp, np.zeros(2)).run(buf)
+        ctx.sync()
+        got = buf.download(np.complex128, (2 ** L,))
+        want = psi
+        for op in ops:
+            want = O.apply_textbook(want, L, block_op_matrix(op, np.zeros(2), -1), [L - 1 - bits[x] for x in op.t])
+        assert np.max(np.abs(got - want)) < 1e-12, mask
